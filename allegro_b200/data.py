@@ -1,0 +1,211 @@
+"""AtomicDataDict keys, neighbour lists and the centre-sorted CSR edge format.
+
+Key strings are nequip's ``AtomicDataDict`` constants (the three output
+keys are confirmed by /root/reference/tests/model/test_allegro.py:233).
+
+The on-device edge format every kernel consumes is *centre-sorted CSR*: edges ordered by
+``edge_index[0]`` (the centre, allegro/nn/_allegro.py:238), ``row_ptr[N+1]`` int32,
+``ctr[E]``/``nbr[E]`` int32.  With it, the per-centre environment sum of
+allegro/nn/_strided/_contract.py:199-205 is a reduction over a contiguous edge range.
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, Optional, Tuple
+
+import torch
+
+POSITIONS_KEY = "pos"
+EDGE_INDEX_KEY = "edge_index"
+ATOM_TYPE_KEY = "atom_types"
+CELL_KEY = "cell"
+PBC_KEY = "pbc"
+EDGE_CELL_SHIFT_KEY = "edge_cell_shift"
+BATCH_KEY = "batch"
+NUM_NODES_KEY = "num_atoms"
+EDGE_VECTORS_KEY = "edge_vectors"
+EDGE_LENGTH_KEY = "edge_lengths"
+NORM_LENGTH_KEY = "normed_edge_lengths"
+EDGE_TYPE_KEY = "edge_type"
+EDGE_ATTRS_KEY = "edge_attrs"
+EDGE_EMBEDDING_KEY = "edge_embedding"
+EDGE_FEATURES_KEY = "edge_features"
+EDGE_CUTOFF_KEY = "edge_cutoff"
+EDGE_ENERGY_KEY = "edge_energy"
+PER_ATOM_ENERGY_KEY = "atomic_energy"
+TOTAL_ENERGY_KEY = "total_energy"
+FORCE_KEY = "forces"
+
+Type = Dict[str, torch.Tensor]
+
+
+def num_nodes(data: Type) -> int:
+    return data[POSITIONS_KEY].shape[0]
+
+
+# --------------------------------------------------------------------------- #
+# neighbour lists
+# --------------------------------------------------------------------------- #
+def _brute_force(pos, cell, pbc, r_max):
+    n = pos.shape[0]
+    dev = pos.device
+    if cell is None or not any(pbc):
+        shifts = torch.zeros(1, 3, dtype=torch.long, device=dev)
+        cell_m = torch.zeros(3, 3, dtype=pos.dtype, device=dev)
+    else:
+        cell_m = cell.view(3, 3).to(pos.dtype)
+        # number of images needed per axis: r_max / (height of the cell along that axis)
+        vol = torch.det(cell_m).abs()
+        cr = torch.stack([torch.linalg.cross(cell_m[1], cell_m[2]), torch.linalg.cross(cell_m[2], cell_m[0]), torch.linalg.cross(cell_m[0], cell_m[1])])
+        heights = vol / cr.norm(dim=-1)
+        reps = [int(math.ceil(r_max / float(h))) if p else 0 for h, p in zip(heights, pbc)]
+        rng = [torch.arange(-r, r + 1, device=dev) for r in reps]
+        shifts = torch.stack(torch.meshgrid(*rng, indexing="ij"), dim=-1).reshape(-1, 3)
+    ei, sh = [], []
+    for s in shifts:
+        off = s.to(pos.dtype) @ cell_m
+        d = pos.unsqueeze(0) + off - pos.unsqueeze(1)  # [i, j]
+        mask = d.norm(dim=-1) < r_max
+        if not bool(s.any()):
+            mask.fill_diagonal_(False)
+        ij = mask.nonzero()
+        ei.append(ij.T)
+        sh.append(s.expand(ij.shape[0], 3))
+    return torch.cat(ei, dim=1), torch.cat(sh, dim=0)
+
+
+def _cell_list(pos, box, r_max, chunk: int = 1 << 22):
+    """Orthorhombic fully periodic box with >= 3 cells per axis."""
+    dev = pos.device
+    n = pos.shape[0]
+    ncell = torch.floor(box / r_max).to(torch.long).clamp(min=1)
+    assert int(ncell.min()) >= 3, "cell list needs box >= 3 r_max on every axis"
+    frac = pos / box
+    frac = frac - torch.floor(frac)
+    cidx3 = torch.minimum((frac * ncell).to(torch.long), ncell - 1)
+    nc = [int(v) for v in ncell]
+    cid = (cidx3[:, 0] * nc[1] + cidx3[:, 1]) * nc[2] + cidx3[:, 2]
+    order = torch.argsort(cid, stable=True)
+    cid_sorted = cid[order]
+    ncells = nc[0] * nc[1] * nc[2]
+    counts = torch.bincount(cid_sorted, minlength=ncells)
+    starts = torch.cumsum(counts, 0) - counts
+    ei, sh = [], []
+    wrapped = pos - torch.floor(pos / box) * box  # positions folded into the box
+    base_shift = torch.floor(pos / box).to(torch.long)  # image index of the raw position
+    ar = torch.arange(n, device=dev)
+    for dx in (-1, 0, 1):
+        for dy in (-1, 0, 1):
+            for dz in (-1, 0, 1):
+                d = torch.tensor([dx, dy, dz], device=dev)
+                c3 = cidx3 + d
+                img = torch.div(c3, ncell, rounding_mode="floor")  # -1, 0, +1
+                c3w = c3 - img * ncell
+                ncid = (c3w[:, 0] * nc[1] + c3w[:, 1]) * nc[2] + c3w[:, 2]
+                cnt = counts[ncid]
+                tot = int(cnt.sum())
+                if tot == 0:
+                    continue
+                i_rep = torch.repeat_interleave(ar, cnt)
+                offs = torch.arange(tot, device=dev) - torch.repeat_interleave(torch.cumsum(cnt, 0) - cnt, cnt)
+                j_rep = order[starts[ncid][i_rep] + offs]
+                img_rep = img[i_rep]
+                rij = wrapped[j_rep] + img_rep.to(pos.dtype) * box - wrapped[i_rep]
+                keep = (rij.norm(dim=-1) < r_max) & ~((i_rep == j_rep) & (img_rep == 0).all(-1))
+                i_k, j_k = i_rep[keep], j_rep[keep]
+                # shift relative to the *raw* positions: r = pos[j] + shift*box - pos[i]
+                s = img_rep[keep] - base_shift[j_k] + base_shift[i_k]
+                ei.append(torch.stack([i_k, j_k]))
+                sh.append(s)
+    return torch.cat(ei, dim=1), torch.cat(sh, dim=0)
+
+
+def neighbor_list(
+    pos: torch.Tensor,
+    r_max: float,
+    cell: Optional[torch.Tensor] = None,
+    pbc=(True, True, True),
+    method: str = "auto",
+) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Full (directed) neighbour list, sorted by centre then neighbour.
+    Returns edge_index [2,E] int64 (row 0 = centre) and edge_cell_shift [E,3] (pos dtype)."""
+    pbc = tuple(bool(p) for p in (pbc if not isinstance(pbc, bool) else (pbc,) * 3))
+    ortho = cell is not None and bool((cell.view(3, 3) - torch.diag(torch.diagonal(cell.view(3, 3)))).abs().max() == 0)
+    if method == "auto":
+        big = pos.shape[0] > 3000
+        can = cell is not None and ortho and all(pbc) and float(torch.diagonal(cell.view(3, 3)).min()) >= 3 * r_max
+        method = "cell" if (big and can) else "brute"
+    if method == "cell":
+        ei, sh = _cell_list(pos, torch.diagonal(cell.view(3, 3)).to(pos.dtype), float(r_max))
+    else:
+        ei, sh = _brute_force(pos, cell, pbc, float(r_max))
+    n = pos.shape[0]
+    key = ei[0] * n + ei[1]
+    # ties (same pair through different images) keep a deterministic order via the shift
+    sk = ((sh[:, 0] + 8) * 17 + (sh[:, 1] + 8)) * 17 + (sh[:, 2] + 8)
+    order = torch.argsort(key * 4913 + sk)
+    return ei[:, order].contiguous(), sh[order].to(pos.dtype).contiguous()
+
+
+# --------------------------------------------------------------------------- #
+# CSR edge format
+# --------------------------------------------------------------------------- #
+class EdgeCSR:
+    """Centre-sorted edge list. ``perm`` maps sorted position -> original edge (None if the
+    input was already sorted)."""
+
+    __slots__ = ("num_atoms", "num_edges", "ctr", "nbr", "row_ptr", "perm", "max_degree")
+
+    def __init__(self, num_atoms, ctr, nbr, row_ptr, perm, max_degree):
+        self.num_atoms = int(num_atoms)
+        self.num_edges = int(ctr.shape[0])
+        self.ctr, self.nbr, self.row_ptr, self.perm = ctr, nbr, row_ptr, perm
+        self.max_degree = int(max_degree)
+
+
+def build_csr(edge_index: torch.Tensor, num_centres: int) -> EdgeCSR:
+    """Sort edges by centre (stable) and build row_ptr.  ``num_centres`` = number of atoms that
+    may be centres (owned atoms); neighbour indices may exceed it (ghost atoms,
+    /root/reference/allegro/_compile.py:41-61)."""
+    ctr64, nbr64 = edge_index[0], edge_index[1]
+    E = ctr64.shape[0]
+    if E > 0 and bool((ctr64[1:] >= ctr64[:-1]).all()):
+        perm = None
+    else:
+        perm = torch.argsort(ctr64, stable=True)
+        ctr64, nbr64 = ctr64[perm], nbr64[perm]
+    counts = torch.bincount(ctr64, minlength=num_centres)
+    if counts.shape[0] != num_centres:
+        raise ValueError("edge centre index out of range")
+    row_ptr = torch.zeros(num_centres + 1, dtype=torch.int32, device=edge_index.device)
+    row_ptr[1:] = torch.cumsum(counts, 0).to(torch.int32)
+    maxdeg = int(counts.max()) if E > 0 else 0
+    return EdgeCSR(num_centres, ctr64.to(torch.int32).contiguous(), nbr64.to(torch.int32).contiguous(), row_ptr, perm, maxdeg)
+
+
+def to_ghost_format(data: Type) -> Type:
+    """PBC (cell shifts) -> appended ghost atoms, the pair_allegro data contract
+    (/root/reference/allegro/_compile.py:17-65): ghost pos = pos[j] + shift @ cell, ghost index
+    = N + arange, inside-cell edges first.  Also the single-r_max halo format used for the
+    multi-GPU decomposition."""
+    data = dict(data)
+    data.pop(BATCH_KEY, None)
+    data.pop(NUM_NODES_KEY, None)
+    if EDGE_CELL_SHIFT_KEY not in data:
+        return data
+    pos, ei = data[POSITIONS_KEY], data[EDGE_INDEX_KEY]
+    shift, cell = data[EDGE_CELL_SHIFT_KEY], data[CELL_KEY].view(3, 3)
+    outside = shift.abs().sum(-1) != 0
+    ei_out = ei[:, outside].clone()
+    pos_out = pos[ei_out[1]] + shift[outside].to(pos.dtype) @ cell.to(pos.dtype)
+    typ = data[ATOM_TYPE_KEY].reshape(-1)
+    typ_out = typ[ei_out[1]]
+    ei_out[1] = torch.arange(pos.shape[0], pos.shape[0] + pos_out.shape[0], device=pos.device)
+    data[POSITIONS_KEY] = torch.cat([pos, pos_out], 0)
+    data[ATOM_TYPE_KEY] = torch.cat([typ, typ_out], 0)
+    data[EDGE_INDEX_KEY] = torch.cat([ei[:, ~outside], ei_out], 1)
+    data.pop(EDGE_CELL_SHIFT_KEY)
+    data.pop(CELL_KEY)
+    data.pop(PBC_KEY, None)
+    data["num_local_atoms"] = torch.tensor(pos.shape[0])
+    return data
