@@ -1,0 +1,279 @@
+"""ctypes binding of liballegro_b200.so (the C ABI declared in include/allegro_b200.h).
+
+There is NO CPU fallback: if the shared library is missing, or a tensor is not on a CUDA
+device, these wrappers raise.  PyTorch is used only for device memory and streams.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional, Sequence
+
+import torch
+
+from . import build as _build
+
+AB2_F64, AB2_F32, AB2_BF16 = 0, 1, 2
+ACT_NONE, ACT_SILU = 0, 1
+EPI_NONE, EPI_MUL_DSILU = 0, 1
+MAX_SEG = 4
+
+DTYPE_ENUM = {torch.float64: AB2_F64, torch.float32: AB2_F32, torch.bfloat16: AB2_BF16}
+ACC_DTYPE = {torch.float64: torch.float64, torch.float32: torch.float32, torch.bfloat16: torch.float32}
+
+_LIB: Optional[C.CDLL] = None
+
+_vp, _i64, _i32, _dbl = C.c_void_p, C.c_int64, C.c_int, C.c_double
+
+_SIGNATURES = {
+    "ab2_version": ([], C.c_int),
+    "ab2_device_ok": ([], C.c_int),
+    "ab2_last_error": ([], C.c_char_p),
+    "ab2_op_scatter_env": ([_i32, _i64, _i64, _dbl, _vp, _vp, _vp, _vp], C.c_int),
+    "ab2_op_contract": ([_i32, _i32, _i64, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp], C.c_int),
+    "ab2_op_gather_rows": ([_i32, _i64, _i64, _dbl, _vp, _vp, _vp, _vp], C.c_int),
+    "ab2_sh_fwd": ([_i32, _i32, _i64, _vp, _vp, _vp], C.c_int),
+    "ab2_sh_bwd": ([_i32, _i32, _i64, _vp, _vp, _vp, _i32, _vp], C.c_int),
+    "ab2_linear": ([_i32, _i64, _i32, _i32, _i32, _vp, _vp, _vp, _i32, _vp, _i32, _vp, _vp, _vp, _vp, _i32, _vp, _i64, _vp], C.c_int),
+    "ab2_env_sum": ([_i32, _i32, _i64, _i32, _vp, _vp, _vp, _i64, _dbl, _vp, _vp], C.c_int),
+    "ab2_env_bwd": ([_i32, _i32, _i64, _i32, _vp, _vp, _vp, _i64, _vp, _dbl, _vp, _i64, _vp, _vp], C.c_int),
+    "ab2_tp_fwd": ([_i32, _i32, _i64, _i64, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _i64, _vp, _vp], C.c_int),
+    "ab2_tp_bwd": ([_i32, _i32, _i64, _i64, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _i64, _vp, _vp, _vp, _i64, _vp, _vp, _vp], C.c_int),
+    "ab2_edge_sum": ([_i32, _i64, _vp, _vp, _dbl, _vp, _vp], C.c_int),
+    "ab2_edge_sum_bwd": ([_i32, _i64, _vp, _vp, _dbl, _vp, _vp], C.c_int),
+    "ab2_force_scatter": ([_i32, _i64, _i64, _vp, _vp, _vp, _vp, _vp], C.c_int),
+    "ab2_transpose_ui": ([_i32, _i64, _i32, _i32, _vp, _vp, _i32, _vp], C.c_int),
+}
+
+
+def exported_symbols() -> Sequence[str]:
+    return tuple(_SIGNATURES)
+
+
+def lib_path() -> str:
+    return _build.LIB
+
+
+def load() -> C.CDLL:
+    """Load the shared library (never builds implicitly on import paths that would hide a
+    missing extension: a missing .so is an error unless ALLEGRO_B200_AUTOBUILD=1)."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    path = lib_path()
+    if not os.path.exists(path):
+        if os.environ.get("ALLEGRO_B200_AUTOBUILD", "0") == "1":
+            _build.build()
+        else:
+            raise RuntimeError(
+                f"allegro_b200: CUDA extension {path} not built. Run `python -m allegro_b200.build` "
+                "(or __graft_entry__.build()).  There is no CPU fallback."
+            )
+    lib = C.CDLL(path)
+    for name, (args, res) in _SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the symbol is missing
+        fn.argtypes = args
+        fn.restype = res
+    _LIB = lib
+    return lib
+
+
+def _check(rc: int):
+    if rc != 0:
+        msg = load().ab2_last_error()
+        raise RuntimeError(f"allegro_b200 kernel call failed (rc={rc}): {msg.decode() if msg else '?'}")
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise RuntimeError("allegro_b200: tensor is not on a CUDA device (no CPU fallback on the hot path)")
+    return C.c_void_p(t.data_ptr())
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _contig(t: torch.Tensor, name: str):
+    if not t.is_contiguous():
+        raise RuntimeError(f"allegro_b200: {name} must be contiguous")
+    return t
+
+
+def _row_strided(t: torch.Tensor, name: str):
+    """2-D view with unit inner stride -> (tensor, leading dimension)."""
+    if t.dim() != 2 or t.stride(1) != 1:
+        raise RuntimeError(f"allegro_b200: {name} must be 2-D with unit inner stride")
+    return t, int(t.stride(0))
+
+
+# --------------------------------------------------------------------------- #
+# thin typed wrappers
+# --------------------------------------------------------------------------- #
+def sh_fwd(vec: torch.Tensor, lmax: int) -> torch.Tensor:
+    E = vec.shape[0]
+    Y = torch.empty(E, (lmax + 1) ** 2, dtype=vec.dtype, device=vec.device)
+    _check(load().ab2_sh_fwd(DTYPE_ENUM[vec.dtype], lmax, E, _ptr(_contig(vec, "vec")), _ptr(Y), _stream()))
+    return Y
+
+
+def sh_bwd(vec: torch.Tensor, gY: torch.Tensor, lmax: int, out: Optional[torch.Tensor] = None, accumulate: bool = False):
+    E = vec.shape[0]
+    if out is None:
+        out = torch.empty_like(vec)
+        accumulate = False
+    _check(load().ab2_sh_bwd(DTYPE_ENUM[vec.dtype], lmax, E, _ptr(_contig(vec, "vec")), _ptr(_contig(gY, "gY")), _ptr(out), int(accumulate), _stream()))
+    return out
+
+
+def linear(
+    a_segs: Sequence[torch.Tensor],
+    W: torch.Tensor,
+    o_segs: Sequence[torch.Tensor],
+    o_accum: Optional[Sequence[bool]] = None,
+    act: int = ACT_NONE,
+    epi: int = EPI_NONE,
+    aux: Optional[torch.Tensor] = None,
+):
+    """Out (+)= epi(act(cat(a_segs, -1)) @ W); a_segs / o_segs are 2-D row-strided views."""
+    M = a_segs[0].shape[0]
+    K, N = W.shape
+    dt = W.dtype
+    na, no = len(a_segs), len(o_segs)
+    a_ptr = (C.c_void_p * na)()
+    a_ld = (C.c_int64 * na)()
+    a_w = (C.c_int32 * na)()
+    for s, t in enumerate(a_segs):
+        t, ld = _row_strided(t, f"A segment {s}")
+        assert t.dtype == dt and t.shape[0] == M
+        a_ptr[s], a_ld[s], a_w[s] = t.data_ptr(), ld, t.shape[1]
+        _ptr(t)
+    o_ptr = (C.c_void_p * no)()
+    o_ld = (C.c_int64 * no)()
+    o_w = (C.c_int32 * no)()
+    o_acc = (C.c_int32 * no)()
+    for s, t in enumerate(o_segs):
+        t, ld = _row_strided(t, f"output segment {s}")
+        assert t.dtype == dt and t.shape[0] == M
+        o_ptr[s], o_ld[s], o_w[s] = t.data_ptr(), ld, t.shape[1]
+        o_acc[s] = int(bool(o_accum[s])) if o_accum is not None else 0
+        _ptr(t)
+    aux_ld = 0
+    if aux is not None:
+        aux, aux_ld = _row_strided(aux, "aux")
+        assert aux.dtype == dt
+    _check(
+        load().ab2_linear(
+            DTYPE_ENUM[dt], M, K, N, na, a_ptr, a_ld, a_w, act, _ptr(_contig(W, "W")), no, o_ptr, o_ld, o_w, o_acc, epi,
+            _ptr(aux), aux_ld, _stream(),
+        )
+    )
+
+
+def env_sum(dtype, lmax: int, N: int, U: int, row_ptr, Y, w: torch.Tensor, sf: float, out: Optional[torch.Tensor] = None):
+    w, w_ld = _row_strided(w, "w")
+    D = (lmax + 1) ** 2
+    if out is None:
+        out = torch.empty(N, D, U, dtype=ACC_DTYPE[dtype], device=Y.device)
+    _check(load().ab2_env_sum(DTYPE_ENUM[dtype], lmax, N, U, _ptr(row_ptr), _ptr(_contig(Y, "Y")), _ptr(w), w_ld, float(sf), _ptr(out), _stream()))
+    return out
+
+
+def env_bwd(dtype, lmax: int, U: int, ctr, Y, w: torch.Tensor, ggamma, sf: float, gw: torch.Tensor, gY: torch.Tensor):
+    w, w_ld = _row_strided(w, "w")
+    gw, gw_ld = _row_strided(gw, "gw")
+    E = Y.shape[0]
+    _check(
+        load().ab2_env_bwd(
+            DTYPE_ENUM[dtype], lmax, E, U, _ptr(ctr), _ptr(_contig(Y, "Y")), _ptr(w), w_ld, _ptr(_contig(ggamma, "ggamma")), float(sf),
+            _ptr(gw), gw_ld, _ptr(_contig(gY, "gY")), _stream(),
+        )
+    )
+
+
+def tp_fwd(dtype, lmax, N, E, U, d_in, d_out, tab, cgw, row_ptr, ctr, gamma, Vin, Y, w0, Vout):
+    implicit = Vin is None
+    w0_ld = 0
+    if implicit:
+        w0, w0_ld = _row_strided(w0, "w0")
+    _check(
+        load().ab2_tp_fwd(
+            DTYPE_ENUM[dtype], lmax, N, E, U, d_in, d_out, tab.shape[0], _ptr(tab), _ptr(cgw), _ptr(row_ptr), _ptr(ctr), _ptr(gamma),
+            _ptr(Vin), int(implicit), _ptr(Y), _ptr(w0) if implicit else None, w0_ld, _ptr(Vout), _stream(),
+        )
+    )
+
+
+def tp_bwd(dtype, lmax, N, E, U, d_in, d_out, tab, cgw, row_ptr, ctr, gamma, Vin, Y, w0, gVout, gVin, gw0, gY, ggamma):
+    implicit = Vin is None
+    w0_ld = gw0_ld = 0
+    if implicit:
+        w0, w0_ld = _row_strided(w0, "w0")
+        gw0, gw0_ld = _row_strided(gw0, "gw0")
+    _check(
+        load().ab2_tp_bwd(
+            DTYPE_ENUM[dtype], lmax, N, E, U, d_in, d_out, tab.shape[0], _ptr(tab), _ptr(cgw), _ptr(row_ptr), _ptr(ctr), _ptr(gamma),
+            _ptr(Vin), int(implicit), _ptr(Y), _ptr(w0) if implicit else None, w0_ld, _ptr(gVout), _ptr(gVin),
+            _ptr(gw0) if implicit else None, gw0_ld, _ptr(gY) if implicit else None, _ptr(ggamma), _stream(),
+        )
+    )
+
+
+def edge_sum(Ez: torch.Tensor, row_ptr: torch.Tensor, factor: float) -> torch.Tensor:
+    N = row_ptr.shape[0] - 1
+    Ei = torch.empty(N, dtype=Ez.dtype, device=Ez.device)
+    _check(load().ab2_edge_sum(DTYPE_ENUM[Ez.dtype], N, _ptr(row_ptr), _ptr(_contig(Ez, "Ez")), float(factor), _ptr(Ei), _stream()))
+    return Ei
+
+
+def edge_sum_bwd(gEi: torch.Tensor, ctr: torch.Tensor, factor: float) -> torch.Tensor:
+    E = ctr.shape[0]
+    gEz = torch.empty(E, dtype=gEi.dtype, device=gEi.device)
+    _check(load().ab2_edge_sum_bwd(DTYPE_ENUM[gEi.dtype], E, _ptr(ctr), _ptr(_contig(gEi, "gEi")), float(factor), _ptr(gEz), _stream()))
+    return gEz
+
+
+def force_scatter(gvec: torch.Tensor, row_ptr: torch.Tensor, nbr: torch.Tensor, num_atoms_total: int) -> torch.Tensor:
+    N = row_ptr.shape[0] - 1
+    E = nbr.shape[0]
+    F = torch.zeros(num_atoms_total, 3, dtype=gvec.dtype, device=gvec.device)
+    _check(load().ab2_force_scatter(DTYPE_ENUM[gvec.dtype], N, E, _ptr(row_ptr), _ptr(nbr), _ptr(_contig(gvec, "gvec")), _ptr(F), _stream()))
+    return F
+
+
+def transpose_ui(x: torch.Tensor, to_internal: bool) -> torch.Tensor:
+    """[E,U,d] (reference strided layout) <-> [E,d,U] (internal)."""
+    E, a, b = x.shape
+    U, d = (a, b) if to_internal else (b, a)
+    out = torch.empty(E, d, U, dtype=x.dtype, device=x.device) if to_internal else torch.empty(E, U, d, dtype=x.dtype, device=x.device)
+    _check(load().ab2_transpose_ui(DTYPE_ENUM[x.dtype], E, U, d, _ptr(_contig(x, "x")), _ptr(out), int(to_internal), _stream()))
+    return out
+
+
+def op_scatter_env(x2: torch.Tensor, idxs: torch.Tensor, n: int, sf: float) -> torch.Tensor:
+    E = x2.shape[0]
+    row = x2[0].numel() if E else 0
+    gamma = torch.zeros((n,) + tuple(x2.shape[1:]), dtype=x2.dtype, device=x2.device)
+    _check(load().ab2_op_scatter_env(DTYPE_ENUM[x2.dtype], E, row, float(sf), _ptr(_contig(x2, "x2")), _ptr(_contig(idxs, "idxs")), _ptr(gamma), _stream()))
+    return gamma
+
+
+def op_gather_rows(src: torch.Tensor, idxs: torch.Tensor, sf: float) -> torch.Tensor:
+    E = idxs.shape[0]
+    row = src[0].numel()
+    out = torch.empty((E,) + tuple(src.shape[1:]), dtype=src.dtype, device=src.device)
+    _check(load().ab2_op_gather_rows(DTYPE_ENUM[src.dtype], E, row, float(sf), _ptr(_contig(src, "src")), _ptr(_contig(idxs, "idxs")), _ptr(out), _stream()))
+    return out
+
+
+def op_contract(mode: int, U, d1, d2, dout, tab, cgw, a, b, idxs, out):
+    E = idxs.shape[0]
+    _check(
+        load().ab2_op_contract(
+            DTYPE_ENUM[a.dtype], mode, E, U, d1, d2, dout, tab.shape[0], _ptr(tab), _ptr(cgw), _ptr(_contig(a, "a")), _ptr(_contig(b, "b")),
+            _ptr(_contig(idxs, "idxs")), _ptr(out), _stream(),
+        )
+    )
+    return out

@@ -1,0 +1,105 @@
+// Per-centre environment sum and its adjoint.
+//
+// Reference: MakeWeightedChannels (allegro/nn/_strided/_channels.py:44-57) builds
+// A[z][u][j] = Y[z][j] * w[z][u][irrep(j)] for every edge, Contracter.forward
+// (_contract.py:195-205) scales by 1/sqrt(avg_num_neighbors), scatter-sums over the centre and
+// gathers the sum back per edge.  With centre-sorted edges the sum is a reduction over a
+// contiguous row; A is never materialised and the gather is a broadcast read of gamma[c].
+//
+// Layouts: Y[E][D] (TAcc), w[z][n_ir][U] (TAct, leading dim w_ld), gamma[N][D][U] (TAcc).
+#include "common.cuh"
+
+template <typename TAct, typename TAcc, int LMAX>
+__global__ void __launch_bounds__(128) env_sum_kernel(int64_t N, int U, const int32_t* __restrict__ row_ptr,
+                                                      const TAcc* __restrict__ Y, const TAct* __restrict__ w, int64_t w_ld,
+                                                      TAcc sf, TAcc* __restrict__ gamma) {
+    constexpr int D = (LMAX + 1) * (LMAX + 1);
+    const int nchunk = (U + 31) >> 5;
+    const int64_t wid = ((int64_t)blockIdx.x * 128 + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    const int64_t c = wid / nchunk;
+    if (c >= N) return;
+    const int u = (int)(wid % nchunk) * 32 + lane;
+    const bool live = u < U;
+    const int beg = row_ptr[c], end = row_ptr[c + 1];
+    TAcc acc[D];
+#pragma unroll
+    for (int j = 0; j < D; ++j) acc[j] = TAcc(0);
+    for (int z = beg; z < end; ++z) {
+        const TAcc* __restrict__ Yz = Y + (int64_t)z * D;
+        const TAct* __restrict__ wz = w + (int64_t)z * w_ld;
+#pragma unroll
+        for (int l = 0; l <= LMAX; ++l) {
+            const TAcc wl = live ? to_acc<TAcc>(wz[l * U + u]) : TAcc(0);
+#pragma unroll
+            for (int j = l * l; j < (l + 1) * (l + 1); ++j) acc[j] += Yz[j] * wl;
+        }
+    }
+    if (live) {
+#pragma unroll
+        for (int j = 0; j < D; ++j) gamma[((int64_t)c * D + j) * U + u] = sf * acc[j];
+    }
+}
+
+// One warp per edge.  gw[z][l][u] = sf * sum_{j in l} Y[z][j] ggamma[c][j][u];
+// gY[z][j] += sf * sum_u w[z][l(j)][u] ggamma[c][j][u]  (warp-shuffle reduction over u).
+template <typename TAct, typename TAcc, int LMAX>
+__global__ void __launch_bounds__(128) env_bwd_kernel(int64_t E, int U, const int32_t* __restrict__ ctr, const TAcc* __restrict__ Y,
+                                                      const TAct* __restrict__ w, int64_t w_ld, const TAcc* __restrict__ ggamma,
+                                                      TAcc sf, TAct* __restrict__ gw, int64_t gw_ld, TAcc* __restrict__ gY) {
+    constexpr int D = (LMAX + 1) * (LMAX + 1);
+    const int64_t z = ((int64_t)blockIdx.x * 128 + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (z >= E) return;
+    const int64_t c = ctr[z];
+    TAcc Yz[D], gy[D];
+#pragma unroll
+    for (int j = 0; j < D; ++j) {
+        Yz[j] = Y[z * D + j];
+        gy[j] = TAcc(0);
+    }
+    for (int u = lane; u < U; u += 32) {
+#pragma unroll
+        for (int l = 0; l <= LMAX; ++l) {
+            const TAcc wl = to_acc<TAcc>(w[z * w_ld + l * U + u]);
+            TAcc gwl = TAcc(0);
+#pragma unroll
+            for (int j = l * l; j < (l + 1) * (l + 1); ++j) {
+                const TAcc ga = sf * ggamma[(c * D + j) * U + u];
+                gwl += Yz[j] * ga;
+                gy[j] += wl * ga;
+            }
+            gw[z * gw_ld + l * U + u] = from_acc<TAct>(gwl);
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < D; ++j) {
+        const TAcc s = warp_sum(gy[j]);
+        if (lane == (j & 31)) gY[z * D + j] += s;
+    }
+}
+
+extern "C" int ab2_env_sum(int dtype, int lmax, int64_t N, int U, const int32_t* row_ptr, const void* Y, const void* w,
+                           int64_t w_ld, double sf, void* gamma, void* stream) {
+    if (N == 0) return 0;
+    AB2_CHECK_ARG(row_ptr && Y && w && gamma && U > 0, "null pointer / U");
+    AB2_CHECK_ARG(w_ld >= (int64_t)(lmax + 1) * U, "w_ld too small");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t warps = N * ((U + 31) / 32);
+    AB2_DISPATCH_DTYPE(dtype, AB2_DISPATCH_LMAX(lmax, env_sum_kernel<TAct, TAcc, LMAX><<<ab2_blocks(warps * 32, 128), 128, 0, st>>>(
+                                                          N, U, row_ptr, (const TAcc*)Y, (const TAct*)w, w_ld, (TAcc)sf, (TAcc*)gamma)));
+    AB2_CUDA_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int ab2_env_bwd(int dtype, int lmax, int64_t E, int U, const int32_t* ctr, const void* Y, const void* w, int64_t w_ld,
+                           const void* ggamma, double sf, void* gw, int64_t gw_ld, void* gY, void* stream) {
+    if (E == 0) return 0;
+    AB2_CHECK_ARG(ctr && Y && w && ggamma && gw && gY && U > 0, "null pointer / U");
+    cudaStream_t st = (cudaStream_t)stream;
+    AB2_DISPATCH_DTYPE(dtype, AB2_DISPATCH_LMAX(lmax, env_bwd_kernel<TAct, TAcc, LMAX><<<ab2_blocks(E * 32, 128), 128, 0, st>>>(
+                                                          E, U, ctr, (const TAcc*)Y, (const TAct*)w, w_ld, (const TAcc*)ggamma, (TAcc)sf,
+                                                          (TAct*)gw, gw_ld, (TAcc*)gY)));
+    AB2_CUDA_LAUNCH_CHECK();
+    return 0;
+}

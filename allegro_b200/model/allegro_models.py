@@ -1,0 +1,248 @@
+"""Model builders with the reference's kwargs: AllegroModel / AllegroEnergyModel /
+FullAllegroEnergyModel / FullAllegroModel
+(/root/reference/allegro/model/allegro_models.py:70-305).
+
+``AllegroModel(**kwargs)(data) -> data`` reads ``pos``, ``edge_index`` [2,E] int64 (row 0 =
+centre), ``atom_types`` and optional ``cell``/``edge_cell_shift`` and writes
+``atomic_energy`` [N,1], ``total_energy``, ``forces`` [N,3] (+ ``edge_features``,
+``edge_energy``), exactly the fields the reference model writes.  Sub-module names are the
+reference's SequentialGraphNetwork keys (:222-228,262-268,297) so state_dict prefixes match.
+
+The energy model is ONE fused module: the per-edge hot path runs in liballegro_b200.so;
+there is no torch/e3nn fallback for it.
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, Optional, Sequence, Union
+
+import torch
+
+from .. import _lib
+from .. import data as D
+from ..nn._modules import (
+    Allegro_Module,
+    EdgeLengthNormalizer,
+    EdgewiseReduce,
+    PerTypeScaleShift,
+    TwoBodyBesselScalarEmbed,
+    TwoBodySphericalHarmonicTensorEmbed,
+)
+from ..nn._mlp import ScalarMLPFunction
+from ..nn._pipeline import AllegroCore, core_apply
+from ..o3 import Irreps
+
+_DTYPES = {"float32": torch.float32, "float64": torch.float64, "bfloat16": torch.bfloat16}
+_EMBED_TARGETS = {
+    "allegro.nn.TwoBodyBesselScalarEmbed": TwoBodyBesselScalarEmbed,
+    "allegro_b200.nn.TwoBodyBesselScalarEmbed": TwoBodyBesselScalarEmbed,
+}
+
+
+def _instantiate_embed(cfg: Dict, **kw):
+    cfg = dict(cfg or {"_target_": "allegro.nn.TwoBodyBesselScalarEmbed"})
+    target = cfg.pop("_target_", "allegro.nn.TwoBodyBesselScalarEmbed")
+    if target not in _EMBED_TARGETS:
+        raise NotImplementedError(f"radial_chemical_embed target {target!r} (spline embedding is SURVEY row f4, not built)")
+    return _EMBED_TARGETS[target](**cfg, **kw)
+
+
+class FusedAllegroEnergy(torch.nn.Module):
+    """What FullAllegroEnergyModel returns: the reference's module sequence as one module."""
+
+    def __init__(
+        self,
+        r_max: float,
+        type_names: Sequence[str],
+        irreps_edge_sh,
+        tensor_track_allowed_irreps,
+        radial_chemical_embed: Dict,
+        radial_chemical_embed_dim: Optional[int] = None,
+        per_edge_type_cutoff=None,
+        scalar_embed_mlp_hidden_layers_depth: int = 1,
+        scalar_embed_mlp_hidden_layers_width: int = 64,
+        scalar_embed_mlp_nonlinearity: Optional[str] = "silu",
+        num_layers: int = 2,
+        num_scalar_features: int = 64,
+        num_tensor_features: int = 16,
+        allegro_mlp_hidden_layers_depth: int = 1,
+        allegro_mlp_hidden_layers_width: int = 64,
+        allegro_mlp_nonlinearity: Optional[str] = "silu",
+        tp_path_channel_coupling: bool = True,
+        readout_mlp_hidden_layers_depth: int = 1,
+        readout_mlp_hidden_layers_width: int = 32,
+        readout_mlp_nonlinearity: Optional[str] = "silu",
+        avg_num_neighbors: Optional[float] = None,
+        weight_individual_irreps: bool = True,
+        per_type_energy_scales=None,
+        per_type_energy_shifts=None,
+        per_type_energy_scales_trainable: bool = False,
+        per_type_energy_shifts_trainable: bool = False,
+        pair_potential: Optional[Dict] = None,
+        forward_normalize: bool = True,
+        model_dtype: str = "float32",
+    ):
+        super().__init__()
+        if pair_potential is not None:
+            raise NotImplementedError("pair_potential (ZBL) is SURVEY row f4, not built")
+        assert avg_num_neighbors is not None, "`avg_num_neighbors` must be set for Allegro models"
+        self.model_dtype = _DTYPES[model_dtype]
+        self.type_names = list(type_names)
+        self.r_max = float(r_max)
+        self.avg_num_neighbors = float(avg_num_neighbors)
+        S = num_scalar_features
+        self.edge_norm = EdgeLengthNormalizer(r_max, type_names, per_edge_type_cutoff)
+        self.radial_chemical_embed = _instantiate_embed(
+            radial_chemical_embed,
+            type_names=type_names,
+            module_output_dim=S if radial_chemical_embed_dim is None else radial_chemical_embed_dim,
+            forward_weight_init=forward_normalize,
+        )
+        self.scalar_embed_mlp = ScalarMLPFunction(
+            self.radial_chemical_embed.out_dim, S, scalar_embed_mlp_hidden_layers_depth,
+            scalar_embed_mlp_hidden_layers_width, scalar_embed_mlp_nonlinearity, forward_weight_init=forward_normalize,
+        )
+        self.tensor_embed = TwoBodySphericalHarmonicTensorEmbed(
+            irreps_edge_sh, num_tensor_features, S, forward_weight_init=forward_normalize,
+            weight_individual_irreps=weight_individual_irreps,
+        )
+        self.allegro = Allegro_Module(
+            num_layers=num_layers, num_scalar_features=S, num_tensor_features=num_tensor_features,
+            tensor_track_allowed_irreps=tensor_track_allowed_irreps, input_irreps=self.tensor_embed.irreps_edge_sh,
+            scalar_input_dim=S, avg_num_neighbors=avg_num_neighbors, tp_path_channel_coupling=tp_path_channel_coupling,
+            weight_individual_irreps=weight_individual_irreps,
+            latent_kwargs=dict(
+                hidden_layers_depth=allegro_mlp_hidden_layers_depth, hidden_layers_width=allegro_mlp_hidden_layers_width,
+                nonlinearity=allegro_mlp_nonlinearity, bias=False, forward_weight_init=forward_normalize,
+            ),
+        )
+        self.edge_readout = ScalarMLPFunction(
+            S * (num_layers + 1), 1, readout_mlp_hidden_layers_depth, readout_mlp_hidden_layers_width,
+            readout_mlp_nonlinearity, forward_weight_init=forward_normalize,
+        )
+        self.edge_eng_sum = EdgewiseReduce(D.EDGE_ENERGY_KEY, D.PER_ATOM_ENERGY_KEY, factor=1.0 / math.sqrt(2 * avg_num_neighbors))
+        self.per_type_energy_scale_shift = PerTypeScaleShift(
+            type_names, per_type_energy_scales, per_type_energy_shifts, per_type_energy_scales_trainable,
+            per_type_energy_shifts_trainable,
+        )
+        self._core: Optional[AllegroCore] = None
+        self._core_key = None
+        self._csr_cache = None
+
+    # ------------------------------------------------------------------------------------
+    def _param_key(self):
+        return tuple((p.data_ptr(), p._version) for p in self.parameters())
+
+    def core(self) -> AllegroCore:
+        dev = next(self.parameters()).device
+        key = (self._param_key(), str(dev))
+        if self._core is None or self._core_key != key:
+            if dev.type != "cuda":
+                raise RuntimeError("allegro_b200: the model must live on a CUDA device (no CPU path for the hot path)")
+            self._core = AllegroCore(self.tensor_embed, self.allegro, self.edge_readout, self.avg_num_neighbors,
+                                     self.model_dtype, dev)
+            self._core_key = key
+        return self._core
+
+    def _csr(self, edge_index: torch.Tensor, n: int):
+        key = (edge_index.data_ptr(), edge_index._version, tuple(edge_index.shape), n)
+        if self._csr_cache is None or self._csr_cache[0] != key:
+            self._csr_cache = (key, D.build_csr(edge_index, n))
+        return self._csr_cache[1]
+
+    def forward(self, data: D.Type) -> D.Type:
+        pos = data[D.POSITIONS_KEY]
+        if not pos.is_cuda:
+            raise RuntimeError("allegro_b200: inputs must be CUDA tensors (no CPU fallback on the hot path)")
+        core = self.core()
+        ei = data[D.EDGE_INDEX_KEY]
+        n = pos.shape[0]
+        csr = self._csr(ei, n)
+        ctr, nbr = csr.ctr.long(), csr.nbr.long()
+        # a1: edge vectors (nequip with_edge_vectors_, tensorembed.py:86), in the positions' dtype
+        vec = pos[nbr] - pos[ctr]
+        if D.EDGE_CELL_SHIFT_KEY in data and D.CELL_KEY in data:
+            sh = data[D.EDGE_CELL_SHIFT_KEY]
+            if csr.perm is not None:
+                sh = sh[csr.perm]
+            vec = vec + sh.to(pos.dtype) @ data[D.CELL_KEY].view(3, 3).to(pos.dtype)
+        types = data[D.ATOM_TYPE_KEY].reshape(-1)
+        tc, tn = types[ctr], types[nbr]
+        # upstream two-body scalar embedding (row f1; torch ops on the device)
+        r = vec.norm(dim=-1)
+        x_norm = self.edge_norm(r, tc, tn)
+        mdt = torch.float32 if self.model_dtype == torch.bfloat16 else self.model_dtype
+        x_emb = self.scalar_embed_mlp(self.radial_chemical_embed(x_norm, tc, tn, mdt))
+        stash: Dict[str, torch.Tensor] = {}
+        Ei = core_apply(core, csr, vec.to(core.acc), x_emb.to(self.model_dtype), stash)
+        e_atom = self.per_type_energy_scale_shift(Ei.unsqueeze(-1), types)
+        out = dict(data)
+        inv = None
+        if csr.perm is not None:
+            inv = torch.empty_like(csr.perm)
+            inv[csr.perm] = torch.arange(csr.perm.shape[0], device=csr.perm.device)
+        for k_src, k_dst in (("edge_features", D.EDGE_FEATURES_KEY), ("edge_energy", D.EDGE_ENERGY_KEY)):
+            v = stash[k_src]
+            out[k_dst] = v if inv is None else v[inv]
+        out[D.PER_ATOM_ENERGY_KEY] = e_atom
+        out[D.TOTAL_ENERGY_KEY] = e_atom.sum(dim=0, keepdim=True)
+        return out
+
+
+class ForceStressOutput(torch.nn.Module):
+    """nequip ForceStressOutput (wrapped at allegro_models.py:101-103): forces = -dE/dpos."""
+
+    def __init__(self, model: torch.nn.Module):
+        super().__init__()
+        self.model = model
+
+    def forward(self, data: D.Type) -> D.Type:
+        data = dict(data)
+        pos = data[D.POSITIONS_KEY].detach().clone().requires_grad_(True)
+        data[D.POSITIONS_KEY] = pos
+        with torch.enable_grad():
+            out = self.model(data)
+            (g,) = torch.autograd.grad(out[D.TOTAL_ENERGY_KEY].sum(), pos)
+        out[D.FORCE_KEY] = -g
+        out[D.POSITIONS_KEY] = pos.detach()
+        return {k: (v.detach() if isinstance(v, torch.Tensor) else v) for k, v in out.items()}
+
+
+def _builder_common(kwargs: Dict):
+    """What nequip's @model_builder consumes: seed, model_dtype, compile_mode."""
+    kwargs = dict(kwargs)
+    seed = kwargs.pop("seed", None)
+    kwargs.pop("compile_mode", None)  # CUDA graphs, not a tracing compiler, on this path
+    model_dtype = kwargs.get("model_dtype", "float32")
+    if seed is not None:
+        torch.manual_seed(seed)
+    return kwargs, model_dtype
+
+
+def FullAllegroEnergyModel(**kwargs) -> FusedAllegroEnergy:
+    kwargs, model_dtype = _builder_common(kwargs)
+    prev = torch.get_default_dtype()
+    torch.set_default_dtype(torch.float32 if model_dtype == "bfloat16" else _DTYPES[model_dtype])
+    try:
+        return FusedAllegroEnergy(**kwargs)
+    finally:
+        torch.set_default_dtype(prev)
+
+
+def AllegroEnergyModel(l_max: int, parity: bool = True, **kwargs) -> FusedAllegroEnergy:
+    """allegro_models.py:70-92."""
+    irreps_edge_sh = Irreps.spherical_harmonics(l_max, p=-1)
+    if parity:
+        allowed = Irreps([(1, (l, p)) for l in range(l_max + 1) for p in (1, -1)])
+    else:
+        allowed = irreps_edge_sh
+    return FullAllegroEnergyModel(irreps_edge_sh=irreps_edge_sh, tensor_track_allowed_irreps=allowed, **kwargs)
+
+
+def AllegroModel(**kwargs) -> ForceStressOutput:
+    """allegro_models.py:101-103."""
+    return ForceStressOutput(AllegroEnergyModel(**kwargs))
+
+
+def FullAllegroModel(**kwargs) -> ForceStressOutput:
+    return ForceStressOutput(FullAllegroEnergyModel(**kwargs))

@@ -1,0 +1,186 @@
+"""Contracter: the reference's kernel plug-in point, backed by the sm_100a operator kernels.
+
+Mirrors allegro/nn/_strided/_contract.py:11-313 -- same constructor kwargs, same
+``state_dict`` (``weights`` of shape (mul,P)/(mul,)/(P,)/(), dense ``w3j`` buffer), same
+``forward(x1, x2, idxs, scatter_dim_size)`` on the strided [z][u][i] layout -- but the
+arithmetic runs in ``liballegro_b200.so`` (ab2_op_scatter_env / ab2_op_contract /
+ab2_op_gather_rows) with hand-written backward w.r.t. x1 and x2 (like the Triton back-end,
+_flashallegro.py:583-666, inference-style: no weight gradient, no double backward).
+There is no CPU path: tensors must be CUDA tensors.
+"""
+from __future__ import annotations
+
+import math
+from typing import List, Optional, Tuple
+
+import torch
+
+from .. import _lib
+from ..o3 import CouplingTable, Irreps, build_coupling_table
+
+
+class _ContractFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x1, x2, idxs, n_atoms: int, mod: "Contracter"):
+        U, d1, d2, dout = mod.mul, mod.base_dim1, mod.base_dim2, mod.base_dim_out
+        x1c = x1.reshape(-1, U, d1).contiguous()
+        x2c = x2.reshape(-1, U, d2).contiguous()
+        idxs = idxs.contiguous()
+        sf = 1.0 if mod.scatter_factor is None else float(mod.scatter_factor)
+        tab, cgw = mod.device_tables(x1c.dtype, x1c.device)
+        gamma = _lib.op_scatter_env(x2c, idxs, n_atoms, sf)
+        out = torch.empty(x1c.shape[0], U, dout, dtype=x1c.dtype, device=x1c.device)
+        _lib.op_contract(0, U, d1, d2, dout, tab, cgw, x1c, gamma, idxs, out)
+        ctx.save_for_backward(x1c, gamma, idxs, tab, cgw)
+        ctx.meta = (U, d1, d2, dout, sf, n_atoms, x1.shape, x2.shape)
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        x1c, gamma, idxs, tab, cgw = ctx.saved_tensors
+        U, d1, d2, dout, sf, n_atoms, s1, s2 = ctx.meta
+        gout = gout.contiguous()
+        gx1 = gx2 = None
+        if ctx.needs_input_grad[0]:
+            gx1 = torch.empty_like(x1c)
+            _lib.op_contract(1, U, d1, d2, dout, tab, cgw, gout, gamma, idxs, gx1)
+            gx1 = gx1.reshape(s1)
+        if ctx.needs_input_grad[1]:
+            ggamma = torch.zeros_like(gamma)
+            _lib.op_contract(2, U, d1, d2, dout, tab, cgw, x1c, gout, idxs, ggamma)
+            gx2 = _lib.op_gather_rows(ggamma, idxs, sf).reshape(s2)
+        return gx1, gx2, None, None, None
+
+
+class Contracter(torch.nn.Module):
+    def __init__(
+        self,
+        irreps_in1,
+        irreps_in2,
+        irreps_out,
+        mul: int,
+        instructions: Optional[List[Tuple[int, int, int]]] = None,
+        path_channel_coupling: bool = True,
+        scatter_factor: Optional[float] = None,
+        irrep_normalization: Optional[str] = "component",
+    ):
+        super().__init__()
+        assert mul > 0
+        self.scatter_factor = scatter_factor
+        self.instructions = instructions
+        self.irreps_in1, self.irreps_in2, self.irreps_out = Irreps(irreps_in1), Irreps(irreps_in2), Irreps(irreps_out)
+        self.table: CouplingTable = build_coupling_table(
+            self.irreps_in1, self.irreps_in2, self.irreps_out, instructions, irrep_normalization
+        )
+        self.irrep_normalization = irrep_normalization
+        self.mul = mul
+        self.base_dim1, self.base_dim2, self.base_dim_out = self.table.dim1, self.table.dim2, self.table.dim_out
+        self.num_paths = self.table.num_paths
+        self.w3j_is_ij_diagonal = self.table.is_ij_diagonal
+        self.path_channel_coupling = path_channel_coupling
+        # dense w3j buffer exactly as the reference registers it (_contract.py:135-168)
+        if self.w3j_is_ij_diagonal:
+            w3j = torch.zeros(self.num_paths, self.base_dim1, self.base_dim_out)
+            for i, j, k, p, v in self.table.entries:
+                w3j[p, i, k] = v
+        else:
+            w3j = torch.zeros(self.num_paths, self.base_dim1, self.base_dim2, self.base_dim_out)
+            for i, j, k, p, v in self.table.entries:
+                w3j[p, i, j, k] = v
+        if self.num_paths == 1:
+            w3j = w3j.squeeze(0)
+        self.register_buffer("w3j", w3j)
+        shape = (mul,) if path_channel_coupling else tuple()
+        if self.num_paths > 1:
+            shape = shape + (self.num_paths,)
+        self.weights = torch.nn.Parameter(torch.empty(shape).uniform_(-math.sqrt(3), math.sqrt(3)))
+        self._tab_cache = {}
+
+    # ---- tables for the kernels --------------------------------------------------------
+    def sparse_table(self):
+        """(ijk int32 [nnz,3], path int64 [nnz], value fp64 [nnz]) on the CPU."""
+        e = self.table.entries
+        ijk = torch.tensor([[a[0], a[1], a[2]] for a in e], dtype=torch.int32)
+        path = torch.tensor([a[3] for a in e], dtype=torch.long)
+        val = torch.tensor([a[4] for a in e], dtype=torch.float64)
+        return ijk, path, val
+
+    def cgw(self, dtype: torch.dtype, device) -> torch.Tensor:
+        """cgw[nnz][u] = value[nnz] * weights[u, path[nnz]] (the reference's ww3j, _contract.py:218-219)."""
+        _, path, val = self.sparse_table()
+        w = self.weights.detach().to(device="cpu", dtype=torch.float64)
+        if self.num_paths > 1:
+            wp = w[..., path]  # (mul, nnz) or (nnz,)
+        else:
+            wp = w.unsqueeze(-1).expand(*w.shape, path.shape[0])
+        if self.path_channel_coupling:
+            out = (wp * val).T  # (nnz, mul)
+        else:
+            out = (wp * val).unsqueeze(-1).expand(path.shape[0], self.mul)
+        return out.contiguous().to(device=device, dtype=dtype)
+
+    def device_tables(self, dtype, device):
+        key = (dtype, str(device), self.weights._version, self.weights.data_ptr())
+        hit = self._tab_cache.get("k")
+        if hit is None or hit[0] != key:
+            ijk, _, _ = self.sparse_table()
+            hit = (key, ijk.to(device), self.cgw(dtype, device))
+            self._tab_cache["k"] = hit
+        return hit[1], hit[2]
+
+    # ---- the operator -------------------------------------------------------------------
+    def forward(self, x1: torch.Tensor, x2: torch.Tensor, idxs: torch.Tensor, scatter_dim_size) -> torch.Tensor:
+        if not x1.is_cuda:
+            raise RuntimeError("allegro_b200.nn.Contracter has no CPU path (B200 kernels only)")
+        if x1.dtype not in (torch.float32, torch.float64):
+            raise RuntimeError("operator-level Contracter supports float32/float64")
+        n = int(scatter_dim_size.reshape(-1)[0]) if isinstance(scatter_dim_size, torch.Tensor) else int(scatter_dim_size)
+        return _ContractFn.apply(x1, x2.to(x1.dtype), idxs, n, self)
+
+    def extra_repr(self):
+        return f"{self.irreps_in1} x {self.irreps_in2} -> {self.irreps_out} | {self.mul} channels | {self.num_paths} paths"
+
+    # ---- model modifier (the reference's enable_<Name>Contracter pattern, :253-310) ------
+    @classmethod
+    def enable_B200Contracter(cls, model: torch.nn.Module) -> torch.nn.Module:
+        """Replace every module whose class is named ``Contracter`` (reference or ours) by a
+        B200-backed one with identical constructor kwargs and state_dict."""
+
+        def factory(old):
+            dt = old.w3j.dtype
+            prev = torch.get_default_dtype()
+            torch.set_default_dtype(dt)
+            try:
+                new = cls(
+                    irreps_in1=repr(old.irreps_in1).replace(" ", ""),
+                    irreps_in2=repr(old.irreps_in2).replace(" ", ""),
+                    irreps_out=repr(old.irreps_out).replace(" ", ""),
+                    mul=old.mul,
+                    instructions=old.instructions,
+                    path_channel_coupling=old.path_channel_coupling,
+                    scatter_factor=old.scatter_factor,
+                    irrep_normalization=old.irrep_normalization,
+                )
+            finally:
+                torch.set_default_dtype(prev)
+            new.load_state_dict(old.state_dict())
+            return new.to(old.w3j.device)
+
+        def walk(mod):
+            for name, child in list(mod.named_children()):
+                if type(child).__name__ == "Contracter" and not isinstance(child, cls):
+                    setattr(mod, name, factory(child))
+                elif isinstance(child, torch.nn.ModuleList):
+                    for i, c in enumerate(child):
+                        if type(c).__name__ == "Contracter" and not isinstance(c, cls):
+                            child[i] = factory(c)
+                        else:
+                            walk(c)
+                else:
+                    walk(child)
+
+        walk(model)
+        return model
+
+
+B200Contracter = Contracter

@@ -1,0 +1,142 @@
+"""ScalarMLPFunction: parameter holder + the fused-linear execution plan.
+
+Mirrors nequip.nn.ScalarMLPFunction as the reference uses it
+(/root/reference/allegro/nn/_allegro.py:90-93,192-213; tensorembed.py:76-81;
+_edgeembed.py:59-64; allegro_models.py:173-183,231-241): layer k computes x @ (alpha_k W_k),
+W_k ~ U(-sqrt3, sqrt3) of shape [h_in, h_out], alpha_k = gain_k / sqrt(fan), SiLU between
+layers, no bias.  alpha is folded into the packed device weights, so
+the kernels see plain [K, N] matrices.
+"""
+from __future__ import annotations
+
+import math
+from typing import List, Optional, Sequence
+
+import torch
+
+from .. import _lib
+
+# second-moment gain of SiLU: 1/sqrt(E_{z~N(0,1)}[silu(z)^2]) (e3nn normalize2mom), by quadrature
+def _silu_gain() -> float:
+    n = 200001
+    z = torch.linspace(-12.0, 12.0, n, dtype=torch.float64)
+    w = torch.exp(-0.5 * z * z) / math.sqrt(2 * math.pi)
+    s = z * torch.sigmoid(z)
+    return float(1.0 / math.sqrt(torch.trapezoid(s * s * w, z)))
+
+
+SILU_GAIN = _silu_gain()
+
+
+class ScalarMLPFunction(torch.nn.Module):
+    def __init__(
+        self,
+        input_dim: int,
+        output_dim: int,
+        hidden_layers_depth: int = 0,
+        hidden_layers_width: Optional[int] = None,
+        nonlinearity: Optional[str] = "silu",
+        bias: bool = False,
+        forward_weight_init: bool = True,
+    ):
+        super().__init__()
+        if bias:
+            raise NotImplementedError("bias=True is not used by Allegro models (allegro_models.py:204-210)")
+        if nonlinearity not in ("silu", None):
+            raise NotImplementedError(f"nonlinearity {nonlinearity!r}: only 'silu' / None have CUDA kernels")
+        if hidden_layers_depth > 0 and hidden_layers_width is None:
+            raise ValueError("hidden_layers_width required")
+        self.dims = [input_dim] + hidden_layers_depth * [hidden_layers_width] + [output_dim]
+        self.nonlinearity = nonlinearity
+        self.is_nonlinear = hidden_layers_depth > 0 and nonlinearity is not None
+        self.weights = torch.nn.ParameterList()
+        self.alphas: List[float] = []
+        gain = 1.0
+        for h_in, h_out in zip(self.dims, self.dims[1:]):
+            w = torch.empty(h_in, h_out)
+            torch.nn.init.uniform_(w, -math.sqrt(3), math.sqrt(3))
+            self.weights.append(torch.nn.Parameter(w))
+            self.alphas.append(gain / math.sqrt(h_in if forward_weight_init else h_out))
+            gain = SILU_GAIN if nonlinearity == "silu" else 1.0
+
+    @property
+    def input_dim(self):
+        return self.dims[0]
+
+    @property
+    def output_dim(self):
+        return self.dims[-1]
+
+    def folded_weights(self) -> List[torch.Tensor]:
+        """alpha_k * W_k in fp64 (host packing input)."""
+        return [a * w.detach().double() for w, a in zip(self.weights, self.alphas)]
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        """Library (torch) evaluation; only used for the upstream two-body scalar embedding,
+        which is outside the named hot path."""
+        n = len(self.weights)
+        for k, (w, a) in enumerate(zip(self.weights, self.alphas)):
+            x = x @ (a * w).to(x.dtype)
+            if k < n - 1 and self.nonlinearity == "silu":
+                x = torch.nn.functional.silu(x)
+        return x
+
+
+class PackedMLP:
+    """Device-resident weights of one ScalarMLPFunction + forward/backward through ab2_linear.
+
+    ``out_perm``: optional permutation applied to the output columns of the last layer (used to
+    bring env weights from the reference's [u][r] order to the internal [r][u] order).
+    ``in_perm``: likewise for the input rows of the first layer.
+    """
+
+    def __init__(self, mlp: ScalarMLPFunction, dtype: torch.dtype, device, out_perm=None, in_perm=None, extra_first=None):
+        ws = mlp.folded_weights()
+        if extra_first is not None:  # horizontally fused sibling linears sharing the input
+            assert len(ws) == 1
+            ws = [torch.cat([ws[0]] + list(extra_first), dim=1)]
+        if in_perm is not None:
+            ws[0] = ws[0][in_perm, :]
+        if out_perm is not None:
+            ws[-1] = ws[-1][:, out_perm]
+        self.silu = mlp.nonlinearity == "silu"
+        self.W = [w.to(device=device, dtype=dtype).contiguous() for w in ws]
+        self.WT = [w.T.to(device=device, dtype=dtype).contiguous() for w in ws]
+        self.dims = [ws[0].shape[0]] + [w.shape[1] for w in ws]
+        self.dtype = dtype
+        self.device = device
+
+    @property
+    def n_layers(self):
+        return len(self.W)
+
+    def forward(self, in_segs: Sequence[torch.Tensor], out_segs: Sequence[torch.Tensor]) -> List[torch.Tensor]:
+        """Returns the list of stored pre-activations (needed by backward)."""
+        M = in_segs[0].shape[0]
+        pre: List[torch.Tensor] = []
+        cur = list(in_segs)
+        for k in range(self.n_layers):
+            last = k == self.n_layers - 1
+            act = _lib.ACT_SILU if (k > 0 and self.silu) else _lib.ACT_NONE
+            if last:
+                _lib.linear(cur, self.W[k], out_segs, act=act)
+            else:
+                h = torch.empty(M, self.dims[k + 1], dtype=self.dtype, device=self.device)
+                _lib.linear(cur, self.W[k], [h], act=act)
+                pre.append(h)
+                cur = [h]
+        return pre
+
+    def backward(self, gout_segs: Sequence[torch.Tensor], pre: List[torch.Tensor], gin_segs: Sequence[torch.Tensor], gin_accum: Sequence[bool]):
+        M = gout_segs[0].shape[0]
+        cur = list(gout_segs)
+        for k in range(self.n_layers - 1, -1, -1):
+            if k == 0:
+                _lib.linear(cur, self.WT[0], gin_segs, o_accum=gin_accum)
+            else:
+                g = torch.empty(M, self.dims[k], dtype=self.dtype, device=self.device)
+                if self.silu:
+                    _lib.linear(cur, self.WT[k], [g], epi=_lib.EPI_MUL_DSILU, aux=pre[k - 1])
+                else:
+                    _lib.linear(cur, self.WT[k], [g])
+                cur = [g]

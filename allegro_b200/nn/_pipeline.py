@@ -1,0 +1,187 @@
+"""The fused per-edge pipeline: SH embedding -> L x (env sum, CG tensor product, latent MLP)
+-> readout MLP -> edge->atom energy sum, forward AND hand-written backward (forces), all in
+liballegro_b200.so.
+
+Replaces, for centre-sorted CSR edges, the reference call stack
+  TwoBodySphericalHarmonicTensorEmbed.forward  (allegro/nn/tensorembed.py:85-96)
+  Allegro_Module.forward                       (allegro/nn/_allegro.py:237-301)
+  edge_readout ScalarMLP                       (allegro/model/allegro_models.py:231-241)
+  EdgewiseReduce.forward                       (allegro/nn/edgewise.py:40-60)
+and their autograd backward.
+
+HBM layout: per-edge tensors are edge-major, edges sorted by centre;
+tensor features are component-major V[E][d][U] (channel fastest), env weights w[E][n_ir][U];
+the densenet scalars x_0..x_L live in ONE buffer X[E][S(L+1)] that every MLP writes a column
+block of (so torch.cat of _allegro.py:278,300 never happens).
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, List, Optional
+
+import torch
+
+from .. import _lib
+from ..data import EdgeCSR
+from ._mlp import PackedMLP
+
+
+def _env_perm(U: int, n_ir: int) -> torch.Tensor:
+    """internal column r*U+u  <-  reference column u*n_ir+r  (_channels.py:46-51)."""
+    r = torch.arange(n_ir).view(-1, 1)
+    u = torch.arange(U).view(1, -1)
+    return (u * n_ir + r).reshape(-1)
+
+
+class _Saved:
+    __slots__ = ("csr", "vec", "Y", "w0", "omega", "V", "gamma", "pre_lat", "pre_read", "X")
+
+
+class AllegroCore:
+    """Packed weights + kernel sequencing.  Built from the parameter-holding modules by
+    ``FusedAllegroEnergy`` (model/allegro_models.py)."""
+
+    def __init__(self, tensor_embed, allegro, edge_readout, avg_num_neighbors: float, dtype: torch.dtype, device):
+        self.dtype = dtype
+        self.acc = _lib.ACC_DTYPE[dtype]
+        self.device = torch.device(device)
+        self.lmax = tensor_embed.lmax
+        self.D = (self.lmax + 1) ** 2
+        self.n_ir = self.lmax + 1
+        self.U = allegro.num_tensor_features
+        self.S = allegro.num_scalar_features
+        self.L = allegro.num_layers
+        self.S_in = tensor_embed.env_embed_linear.input_dim
+        self.sf = 1.0 / math.sqrt(avg_num_neighbors)
+        self.factor = 1.0 / math.sqrt(2.0 * avg_num_neighbors)
+        U, n_ir, S = self.U, self.n_ir, self.S
+        perm = _env_perm(U, n_ir)
+        nw = n_ir * U
+        # one GEMM for both linears that read the two-body embedding:
+        #   [ w0 (tensorembed.py:88-89) | x_0 | omega_0 (_allegro.py:251-258) ]
+        proj = allegro.first_layer_env_embed_projection.folded_weights()[0]
+        proj_perm = torch.cat([torch.arange(S), S + perm])
+        self.embed = PackedMLP(
+            tensor_embed.env_embed_linear, dtype, device, out_perm=torch.cat([perm, nw + proj_perm]),
+            extra_first=[proj],
+        )
+        self.layers = []
+        for l, (tp, lat) in enumerate(zip(allegro.tps, allegro.latents)):
+            last = l == self.L - 1
+            ijk, _, _ = tp.sparse_table()
+            out_perm = None if last else torch.cat([torch.arange(S), S + perm])
+            self.layers.append(
+                dict(
+                    d_in=tp.base_dim1,
+                    d_out=tp.base_dim_out,
+                    tab=ijk.to(device),
+                    cgw=tp.cgw(self.acc, device),
+                    mlp=PackedMLP(lat, dtype, device, out_perm=out_perm),
+                    last=last,
+                )
+            )
+            assert tp.base_dim2 == self.D
+        self.readout = PackedMLP(edge_readout, dtype, device)
+        self.nw = nw
+
+    # ------------------------------------------------------------------------------------
+    def forward(self, csr: EdgeCSR, vec: torch.Tensor, x_emb: torch.Tensor, keep: bool = True):
+        """vec [E,3] (acc dtype), x_emb [E,S_in] (act dtype), both in CSR edge order.
+        Returns (Ei [N] acc dtype, X [E,S(L+1)], Ez [E,1], saved-for-backward)."""
+        E, N, U, S, L, D = csr.num_edges, csr.num_atoms, self.U, self.S, self.L, self.D
+        dt, dev = self.dtype, self.device
+        assert vec.dtype == self.acc and x_emb.dtype == dt
+        sv = _Saved()
+        sv.csr, sv.vec = csr, vec
+        Y = _lib.sh_fwd(vec, self.lmax)
+        X = torch.empty(E, S * (L + 1), dtype=dt, device=dev)
+        w0 = torch.empty(E, self.nw, dtype=dt, device=dev)
+        omega = [torch.empty(E, self.nw, dtype=dt, device=dev)]
+        self.embed.forward([x_emb], [w0, X[:, :S], omega[0]])
+        V: List[Optional[torch.Tensor]] = [None]
+        gammas, pre_lat = [], []
+        for l, ly in enumerate(self.layers):
+            gamma = _lib.env_sum(dt, self.lmax, N, U, csr.row_ptr, Y, omega[l], self.sf)
+            Vn = torch.empty(E, ly["d_out"], U, dtype=dt, device=dev)
+            _lib.tp_fwd(dt, self.lmax, N, E, U, ly["d_in"], ly["d_out"], ly["tab"], ly["cgw"], csr.row_ptr, csr.ctr, gamma,
+                        V[l], Y, w0 if l == 0 else None, Vn)
+            s = Vn.view(E, ly["d_out"] * U)[:, :U]  # scalar (k=0) slab, _allegro.py:272-275
+            outs = [X[:, S * (l + 1) : S * (l + 2)]]
+            if not ly["last"]:
+                omega.append(torch.empty(E, self.nw, dtype=dt, device=dev))
+                outs.append(omega[l + 1])
+            pre_lat.append(ly["mlp"].forward([X[:, : S * (l + 1)], s], outs))
+            V.append(Vn)
+            gammas.append(gamma)
+        Ez = torch.empty(E, 1, dtype=dt, device=dev)
+        pre_read = self.readout.forward([X], [Ez])
+        Ei = _lib.edge_sum(Ez.view(E).to(self.acc), csr.row_ptr, self.factor)
+        sv.Y, sv.w0, sv.omega, sv.V, sv.gamma, sv.pre_lat, sv.pre_read, sv.X = Y, w0, omega, V, gammas, pre_lat, pre_read, X
+        return Ei, X, Ez, sv
+
+    # ------------------------------------------------------------------------------------
+    def backward(self, sv: _Saved, gEi: torch.Tensor):
+        """gEi [N] (acc dtype) -> (gvec [E,3] acc dtype, gx_emb [E,S_in] act dtype)."""
+        csr = sv.csr
+        E, N, U, S, L, D = csr.num_edges, csr.num_atoms, self.U, self.S, self.L, self.D
+        dt, dev = self.dtype, self.device
+        gEz = _lib.edge_sum_bwd(gEi.contiguous(), csr.ctr, self.factor).to(dt).view(E, 1)
+        gX = torch.empty(E, S * (L + 1), dtype=dt, device=dev)
+        self.readout.backward([gEz], sv.pre_read, [gX], [False])
+        gY = torch.zeros(E, D, dtype=self.acc, device=dev)
+        gV_next: Optional[torch.Tensor] = None   # grad wrt V_{l+1}
+        gomega_next: Optional[torch.Tensor] = None  # grad wrt omega_{l+1}
+        gw0 = None
+        for l in range(L - 1, -1, -1):
+            ly = self.layers[l]
+            if ly["last"]:
+                gV_next = torch.empty(E, ly["d_out"], U, dtype=dt, device=dev)
+                if ly["d_out"] > 1:
+                    gV_next.zero_()
+                gs_acc = False
+            else:
+                gs_acc = True
+            gs = gV_next.view(E, ly["d_out"] * U)[:, :U]
+            gouts = [gX[:, S * (l + 1) : S * (l + 2)]]
+            if not ly["last"]:
+                gouts.append(gomega_next)
+            ly["mlp"].backward(gouts, sv.pre_lat[l], [gX[:, : S * (l + 1)], gs], [True, gs_acc])
+            ggamma = torch.empty(N, D, U, dtype=self.acc, device=dev)
+            if l == 0:
+                gw0 = torch.empty(E, self.nw, dtype=dt, device=dev)
+                _lib.tp_bwd(dt, self.lmax, N, E, U, ly["d_in"], ly["d_out"], ly["tab"], ly["cgw"], csr.row_ptr, csr.ctr,
+                            sv.gamma[l], None, sv.Y, sv.w0, gV_next, None, gw0, gY, ggamma)
+                gV_in = None
+            else:
+                gV_in = torch.empty(E, ly["d_in"], U, dtype=dt, device=dev)
+                _lib.tp_bwd(dt, self.lmax, N, E, U, ly["d_in"], ly["d_out"], ly["tab"], ly["cgw"], csr.row_ptr, csr.ctr,
+                            sv.gamma[l], sv.V[l], None, None, gV_next, gV_in, None, None, ggamma)
+            gomega = torch.empty(E, self.nw, dtype=dt, device=dev)
+            _lib.env_bwd(dt, self.lmax, U, csr.ctr, sv.Y, sv.omega[l], ggamma, self.sf, gomega, gY)
+            gV_next, gomega_next = gV_in, gomega
+        gx_emb = torch.empty(E, self.S_in, dtype=dt, device=dev)
+        self.embed.backward([gw0, gX[:, :S], gomega_next], [], [gx_emb], [False])
+        gvec = _lib.sh_bwd(sv.vec, gY, self.lmax)
+        return gvec, gx_emb
+
+
+class _CoreFn(torch.autograd.Function):
+    """(vec, x_emb) -> per-atom energies; backward gives (d/dvec, d/dx_emb).  Weights are not
+    differentiated (inference / MD path, like the reference's Triton back-end)."""
+
+    @staticmethod
+    def forward(ctx, vec, x_emb, core: AllegroCore, csr: EdgeCSR, stash: Dict):
+        Ei, X, Ez, sv = core.forward(csr, vec.detach(), x_emb.detach())
+        ctx.core, ctx.sv = core, sv
+        stash["edge_features"], stash["edge_energy"] = X, Ez
+        return Ei
+
+    @staticmethod
+    def backward(ctx, gEi):
+        gvec, gx = ctx.core.backward(ctx.sv, gEi.to(ctx.core.acc))
+        ctx.sv = None
+        return gvec, gx, None, None, None
+
+
+def core_apply(core: AllegroCore, csr: EdgeCSR, vec: torch.Tensor, x_emb: torch.Tensor, stash: Dict) -> torch.Tensor:
+    return _CoreFn.apply(vec, x_emb, core, csr, stash)

@@ -1,0 +1,139 @@
+/* allegro_b200 C ABI -- B200 (sm_100a) kernels for Allegro's per-edge hot path.
+ *
+ * The reference (mir-group/allegro v0.7.1) is pure Python; its "FFI" for this path is the
+ * kernel plug-in point Contracter.forward(x1, x2, idxs, scatter_dim_size)
+ * (allegro/nn/_strided/_contract.py:185-211, swapped by enable_TritonContracter :253-282 and
+ * enable_CuEquivarianceContracter :284-310) plus the graph modules whose forward(data) the
+ * fused pipeline replaces (allegro/nn/tensorembed.py:85-96, allegro/nn/_allegro.py:237-301,
+ * allegro/nn/edgewise.py:40-60).  Each entry point below cites the reference lines it replaces.
+ *
+ * Conventions
+ *  - plain C types only; every pointer is a DEVICE pointer unless its name ends in _host;
+ *  - the caller owns every buffer (kernels never allocate); work is enqueued on `stream`
+ *    (a cudaStream_t passed as void*) and is asynchronous;
+ *  - return 0 on success, non-zero on error; ab2_last_error() gives the message
+ *    (thread-local);
+ *  - dtype: AB2_F64 / AB2_F32 / AB2_BF16 selects the storage type of activations ("TAct").
+ *    Accumulation type ("TAcc") is double for AB2_F64, float otherwise.  Geometry, spherical
+ *    harmonics, environment sums, energies and gradients w.r.t. them are always TAcc.
+ *  - edges are sorted by centre ("CSR": row_ptr[N+1], int32); internal feature layout is
+ *    component-major  V[E][d][U]  (channel u fastest), env weights  w[E][n_ir][U].
+ */
+#ifndef ALLEGRO_B200_H
+#define ALLEGRO_B200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum { AB2_F64 = 0, AB2_F32 = 1, AB2_BF16 = 2 };
+enum { AB2_ACT_NONE = 0, AB2_ACT_SILU = 1 };
+enum { AB2_EPI_NONE = 0, AB2_EPI_MUL_DSILU = 1 };
+
+#define AB2_MAX_SEG 4
+#define AB2_MAX_LMAX 4
+
+const char* ab2_last_error(void);
+int ab2_version(void);
+/* 1 if a CUDA device with compute capability 10.x is current, else 0 (no error). */
+int ab2_device_ok(void);
+
+/* ---- operator level: the reference's own kernel plug-in point ----------------------- */
+
+/* Contracter.forward, part 1 (_contract.py:195-204): gamma[n][u][j] += sf * x2[z][u][j] for
+ * n = idxs[z] (reference "strided" layout [z][u][j], unsorted int64 idxs).  gamma must be
+ * zeroed by the caller.  dtype AB2_F64 / AB2_F32. */
+int ab2_op_scatter_env(int dtype, int64_t E, int64_t row /* = U*d2 */, double sf,
+                       const void* x2, const int64_t* idxs, void* gamma, void* stream);
+
+/* Contracter.forward, part 2 (_contract.py:205-251): out[z][u][k] =
+ *   sum_nnz cgw[nnz][u] * x1[z][u][i_nnz] * gamma[idxs[z]][u][j_nnz]
+ * with cgw[nnz][u] = w3j_value * weights[u, path]  (pre-contracted, _contract.py:218-219).
+ * tab_ijk: int32 [nnz][3].  Also used for both backward products (caller permutes roles):
+ *   mode 0: out[k] from (x1[i], g[j])      forward
+ *   mode 1: gx1[i] from (gout[k], g[j])    (Triton "bwd1" table, _flashallegro.py:352-355)
+ *   mode 2: gg[j]  from (x1[i], gout[k])   per-edge term, atomically added into
+ *           ggamma[idxs[z]] (adjoint of the gather _contract.py:205); ggamma pre-zeroed. */
+int ab2_op_contract(int dtype, int mode, int64_t E, int U, int d1, int d2, int dout, int nnz,
+                    const int32_t* tab_ijk, const void* cgw, const void* a, const void* b,
+                    const int64_t* idxs, void* out, void* stream);
+
+/* Gather rows: out[z][:] = sf * src[idxs[z]][:]  (adjoint of the scatter; _contract.py:205). */
+int ab2_op_gather_rows(int dtype, int64_t E, int64_t row, double sf, const void* src,
+                       const int64_t* idxs, void* out, void* stream);
+
+/* ---- fused pipeline (centre-sorted CSR edges, component-major layout) --------------- */
+
+/* tensorembed.py:86,91-93: Y[z][0..d) = SH_{l<=lmax}(vec[z]/|vec[z]|), "component"
+ * normalisation; vec, Y are TAcc.  (a1, a2) */
+int ab2_sh_fwd(int acc_dtype, int lmax, int64_t E, const void* vec, void* Y, void* stream);
+/* backward of the above: gvec[z] (+)= d Y/d vec ^T gY[z]   (SURVEY appendix B step 8). */
+int ab2_sh_bwd(int acc_dtype, int lmax, int64_t E, const void* vec, const void* gY, void* gvec,
+               int accumulate, void* stream);
+
+/* Generic fused linear layer (nequip ScalarMLPFunction layer, _allegro.py:251,278;
+ * tensorembed.py:88-89; allegro_models.py:231-241):
+ *   Out[M][N] (split over <=4 column segments) (+)= epi( act(concat_k A_k)[M][K] @ W[K][N] )
+ * act: AB2_ACT_SILU applies silu to A on load.  epi: AB2_EPI_MUL_DSILU multiplies by
+ * silu'(aux[m][n]) (MLP backward).  W is [K][N] row-major in TAct (alpha pre-folded on host).
+ * A segments: (ptr, leading dim in elements, width); widths sum to K; outputs likewise to N. */
+int ab2_linear(int dtype, int64_t M, int K, int N, int n_a, const void* const* a_ptr_host,
+               const int64_t* a_ld_host, const int32_t* a_width_host, int act, const void* W,
+               int n_o, void* const* o_ptr_host, const int64_t* o_ld_host,
+               const int32_t* o_width_host, const int32_t* o_accum_host, int epi, const void* aux,
+               int64_t aux_ld, void* stream);
+
+/* _channels.py:44-57 + _contract.py:195-204 fused: gamma[c][j][u] =
+ *   sf * sum_{z in row c} Y[z][j] * w[z][irrep(j)][u]      (a4, a7; deterministic, no atomics) */
+int ab2_env_sum(int dtype, int lmax, int64_t N, int U, const int32_t* row_ptr, const void* Y,
+                const void* w, int64_t w_ld, double sf, void* gamma, void* stream);
+
+/* Adjoint of ab2_env_sum given ggamma[N][d][U]:
+ *   gw[z][r][u] = sf * sum_{j in r} Y[z][j] ggamma[c][j][u]
+ *   gY[z][j]   += sf * sum_u w[z][irrep(j)][u] ggamma[c][j][u]     (appendix B steps 3-4) */
+int ab2_env_bwd(int dtype, int lmax, int64_t E, int U, const int32_t* ctr, const void* Y,
+                const void* w, int64_t w_ld, const void* ggamma, double sf, void* gw,
+                int64_t gw_ld, void* gY, void* stream);
+
+/* _contract.py:205-251 for one layer on the fused layout (a8, a10):
+ *   Vout[z][k][u] = sum_i Vin[z][i][u] * M_c[u][i][k],
+ *   M_c[u][i][k]  = sum_nnz cgw[nnz][u] * gamma[c][j_nnz][u]      (built once per centre)
+ * implicit_v0 != 0: Vin[z][i][u] = Y[z][i] * w0[z][irrep(i)][u] is formed on the fly
+ * (tensorembed.py:95) and never stored. */
+int ab2_tp_fwd(int dtype, int lmax, int64_t N, int64_t E, int U, int d_in, int d_out, int nnz,
+               const int32_t* tab_ijk, const void* cgw, const int32_t* row_ptr, const int32_t* ctr,
+               const void* gamma, const void* Vin, int implicit_v0, const void* Y, const void* w0,
+               int64_t w0_ld, void* Vout, void* stream);
+
+/* Backward of ab2_tp_fwd (appendix B steps 1-2): given gVout,
+ *   gVin[z][i][u] = sum_k M_c[u][i][k] gVout[z][k][u]
+ *   ggamma[c][j][u] = sum_nnz cgw * sum_{z in c} Vin[z][i][u] gVout[z][k][u]
+ * implicit_v0: instead of gVin writes gw0[z][r][u] and accumulates into gY[z][i]. */
+int ab2_tp_bwd(int dtype, int lmax, int64_t N, int64_t E, int U, int d_in, int d_out, int nnz,
+               const int32_t* tab_ijk, const void* cgw, const int32_t* row_ptr, const int32_t* ctr,
+               const void* gamma, const void* Vin, int implicit_v0, const void* Y, const void* w0,
+               int64_t w0_ld, const void* gVout, void* gVin, void* gw0, int64_t gw0_ld, void* gY,
+               void* ggamma, void* stream);
+
+/* edgewise.py:40-60 (a12): Ei[c] = factor * sum_{z in row c} Ez[z]   (TAcc, deterministic). */
+int ab2_edge_sum(int acc_dtype, int64_t N, const int32_t* row_ptr, const void* Ez, double factor,
+                 void* Ei, void* stream);
+/* adjoint: gEz[z] = factor * gEi[ctr[z]] */
+int ab2_edge_sum_bwd(int acc_dtype, int64_t E, const int32_t* ctr, const void* gEi, double factor,
+                     void* gEz, void* stream);
+
+/* Force assembly (appendix B step 9): F[ctr[z]] += g[z], F[nbr[z]] -= g[z]; centre side is a
+ * segmented sum over the CSR row, neighbour side a warp-aggregated atomic add.  F pre-zeroed
+ * (fp64 or fp32 = acc dtype). */
+int ab2_force_scatter(int acc_dtype, int64_t N, int64_t E, const int32_t* row_ptr,
+                      const int32_t* nbr, const void* gvec, void* F, void* stream);
+
+/* layout helpers between the reference strided layout [z][u][i] and the internal [z][i][u] */
+int ab2_transpose_ui(int dtype, int64_t E, int U, int d, const void* src, void* dst, int to_internal,
+                     void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,300 @@
+"""GPU parity tests, kernel by kernel, through the C ABI (ctypes) against the CPU oracle.
+
+Tolerances follow the reference's own kernel tests
+(/root/reference/tests/nn/test_contract_kernels.py:117: 1e-5 fp32 / 1e-10 fp64).
+"""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from allegro_b200 import _lib, o3
+from allegro_b200 import data as D
+from allegro_b200.nn import Contracter as B200Contracter
+from oracle import nn_ref as R
+from oracle import o3_ref
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+TOL = {torch.float64: 1e-10, torch.float32: 2e-5, torch.bfloat16: 3e-2}
+
+
+def _rel(a, b):
+    return (a.double().cpu() - b.double().cpu()).abs().max().item() / max(b.double().abs().max().item(), 1e-30)
+
+
+def _csr_random(N, E, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    ctr = torch.sort(torch.randint(0, N, (E,), generator=g)).values
+    ei = torch.stack([ctr, torch.randint(0, N, (E,), generator=g)])
+    return D.build_csr(ei.to(DEV), N), ctr
+
+
+@pytest.mark.parametrize("lmax", [1, 2, 3, 4])
+@pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
+def test_sh_fwd_bwd(lmax, dtype):
+    g = torch.Generator().manual_seed(lmax)
+    vec = torch.randn(1000, 3, generator=g, dtype=torch.float64) * 2.0
+    Yr = o3_ref.spherical_harmonics(lmax, vec)
+    Y = _lib.sh_fwd(vec.to(DEV, dtype), lmax)
+    assert _rel(Y, Yr) < TOL[dtype]
+    gY = torch.randn(1000, (lmax + 1) ** 2, generator=g, dtype=torch.float64)
+    v = vec.clone().requires_grad_(True)
+    (gr,) = torch.autograd.grad((o3_ref.spherical_harmonics(lmax, v) * gY).sum(), v)
+    gv = _lib.sh_bwd(vec.to(DEV, dtype), gY.to(DEV, dtype), lmax)
+    assert _rel(gv, gr) < TOL[dtype] * 10
+    # accumulate mode
+    base = torch.ones(1000, 3, device=DEV, dtype=dtype)
+    _lib.sh_bwd(vec.to(DEV, dtype), gY.to(DEV, dtype), lmax, out=base, accumulate=True)
+    assert _rel(base - 1.0, gr) < TOL[dtype] * 100
+
+
+@pytest.mark.parametrize("dtype", [torch.float64, torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("shape", [(1000, 96, 160), (77, 64, 1), (130, 5, 70), (64, 192, 64)])
+def test_linear_concat_split_act_epi(dtype, shape):
+    M, K, N = shape
+    g = torch.Generator().manual_seed(M + K)
+    k1 = K // 3 if K >= 3 else K
+    widths = [k1, K - k1] if K - k1 > 0 else [K]
+    # A segments are column slices of wider buffers (exercises leading dimensions)
+    bufs = [torch.randn(M, w + 3, generator=g, dtype=torch.float64) for w in widths]
+    segs = [b[:, 1 : 1 + w] for b, w in zip(bufs, widths)]
+    W = torch.randn(K, N, generator=g, dtype=torch.float64) / math.sqrt(K)
+    aux = torch.randn(M, N, generator=g, dtype=torch.float64)
+    n1 = N // 2 if N >= 2 else N
+    owid = [n1, N - n1] if N - n1 > 0 else [N]
+    for act, epi in [(0, 0), (1, 0), (0, 1)]:
+        A = torch.cat(segs, -1).to(dtype).double()
+        if act:
+            A = torch.nn.functional.silu(A)
+        ref = A @ W.to(dtype).double()
+        if epi:
+            x = aux.to(dtype).double()
+            s = torch.sigmoid(x)
+            ref = ref * (s * (1 + x * (1 - s)))
+        dsegs = [b.to(DEV, dtype)[:, 1 : 1 + w] for b, w in zip(bufs, widths)]
+        obufs = [torch.full((M, w + 2), 0.5, device=DEV, dtype=dtype) for w in owid]
+        osegs = [b[:, 2:] for b in obufs]
+        accum = [False, True][: len(owid)]
+        _lib.linear(dsegs, W.to(DEV, dtype), osegs, o_accum=accum, act=act, epi=epi, aux=aux.to(DEV, dtype) if epi else None)
+        got = torch.cat([o.double().cpu() for o in osegs], -1)
+        exp = ref.clone()
+        if len(owid) > 1:
+            exp[:, n1:] += 0.5
+        scale = exp.abs().max().item()
+        assert (got - exp).abs().max().item() / scale < (TOL[dtype] if dtype != torch.float32 else 1e-5)
+        for b in obufs:  # padding columns untouched
+            assert (b[:, :2] == 0.5).all()
+
+
+@pytest.mark.parametrize("lmax", [1, 2, 3])
+@pytest.mark.parametrize("U", [4, 32, 48])
+@pytest.mark.parametrize("dtype", [torch.float64, torch.float32, torch.bfloat16])
+def test_env_sum_and_bwd(lmax, U, dtype):
+    N, E = 37, 600
+    csr, ctr = _csr_random(N, E, seed=U)
+    g = torch.Generator().manual_seed(lmax * 10 + U)
+    Dd, n_ir = (lmax + 1) ** 2, lmax + 1
+    acc = _lib.ACC_DTYPE[dtype]
+    Y = torch.randn(E, Dd, generator=g, dtype=torch.float64)
+    wbuf = torch.randn(E, n_ir * U + 5, generator=g, dtype=torch.float64)
+    w_int = wbuf[:, 2 : 2 + n_ir * U]  # internal layout [r][u]
+    w_q = w_int.to(dtype).double()
+    sf = 0.3
+    # oracle: MakeWeightedChannels (ref layout [u][r]) + scatter
+    irreps = o3_ref.Irreps.spherical_harmonics(lmax)
+    m = R.MakeWeightedChannels(irreps, U)
+    w_ref = w_q.view(E, n_ir, U).transpose(1, 2).reshape(E, U * n_ir)
+    A = m(Y.to(acc).double(), w_ref)  # [E,U,D]
+    gam_ref = sf * R.scatter(A, ctr, N)  # [N,U,D]
+    gam = _lib.env_sum(dtype, lmax, N, U, csr.row_ptr, Y.to(DEV, acc), wbuf.to(DEV, dtype)[:, 2 : 2 + n_ir * U], sf)
+    assert _rel(gam.transpose(1, 2), gam_ref) < (1e-5 if dtype != torch.float64 else 1e-12)
+    # backward
+    gg = torch.randn(N, Dd, U, generator=g, dtype=torch.float64)
+    Yt = Y.to(acc).double().clone().requires_grad_(True)
+    wt = w_q.clone().requires_grad_(True)
+    A2 = m(Yt, wt.view(E, n_ir, U).transpose(1, 2).reshape(E, U * n_ir))
+    loss = (sf * R.scatter(A2, ctr, N) * gg.transpose(1, 2)).sum()
+    gY_ref, gw_ref = torch.autograd.grad(loss, (Yt, wt))
+    gw = torch.zeros(E, n_ir * U + 1, device=DEV, dtype=dtype)
+    gY = torch.ones(E, Dd, device=DEV, dtype=acc)
+    _lib.env_bwd(dtype, lmax, U, csr.ctr, Y.to(DEV, acc), wbuf.to(DEV, dtype)[:, 2 : 2 + n_ir * U], gg.to(DEV, acc), sf, gw[:, 1:], gY)
+    tol = {torch.float64: 1e-12, torch.float32: 1e-5, torch.bfloat16: 1e-2}[dtype]
+    assert _rel(gw[:, 1:], gw_ref) < tol
+    assert _rel(gY - 1.0, gY_ref) < (1e-5 if dtype != torch.float64 else 1e-12)
+
+
+def _tp_case(lmax, layer, L, U, coupling, dtype, seed=0):
+    """Build the oracle Contracter of Allegro layer `layer` and matching kernel tables."""
+    sh = o3_ref.Irreps.spherical_harmonics(lmax)
+    allowed = o3_ref.Irreps([(1, (l, p)) for l in range(lmax + 1) for p in (1, -1)])
+    ins, outs = R.allegro_layer_irreps(sh, allowed, L)
+    torch.manual_seed(seed)
+    prev = torch.get_default_dtype()
+    torch.set_default_dtype(torch.float64)
+    try:
+        c = R.Contracter(ins[layer], sh, outs[layer], mul=U, path_channel_coupling=coupling, scatter_factor=None)
+        b = B200Contracter(repr(ins[layer]), repr(sh), repr(outs[layer]), mul=U, path_channel_coupling=coupling)
+    finally:
+        torch.set_default_dtype(prev)
+    b.load_state_dict(c.state_dict())
+    return c, b
+
+
+@pytest.mark.parametrize("case", [(1, 0, 1), (2, 0, 2), (2, 1, 2), (3, 0, 3), (3, 1, 3), (3, 2, 3), (1, 0, 2)])
+@pytest.mark.parametrize("coupling", [True, False])
+@pytest.mark.parametrize("dtype", [torch.float64, torch.float32, torch.bfloat16])
+def test_tp_fwd_bwd_explicit(case, coupling, dtype):
+    lmax, layer, L = case
+    U, N, E = 8, 23, 300
+    c, b = _tp_case(lmax, layer, L, U, coupling, dtype)
+    csr, ctr = _csr_random(N, E, seed=layer)
+    acc = _lib.ACC_DTYPE[dtype]
+    g = torch.Generator().manual_seed(5)
+    d_in, d_out, Dd = c.base_dim1, c.base_dim_out, (lmax + 1) ** 2
+    V = torch.randn(E, U, d_in, generator=g, dtype=torch.float64).to(dtype).double()
+    gam = torch.randn(N, U, Dd, generator=g, dtype=torch.float64).to(acc).double()
+    gout = torch.randn(E, U, d_out, generator=g, dtype=torch.float64).to(dtype).double()
+    Vt, gt = V.clone().requires_grad_(True), gam.clone().requires_grad_(True)
+    out_ref = c._contract(Vt, gt[ctr])
+    gV_ref, ggam_ref = torch.autograd.grad((out_ref * gout).sum(), (Vt, gt))
+    ijk, _, _ = b.sparse_table()
+    tab, cgw = ijk.to(DEV), b.cgw(acc, DEV)
+    Vi = V.transpose(1, 2).contiguous().to(DEV, dtype)
+    gi = gam.transpose(1, 2).contiguous().to(DEV, acc)
+    Vout = torch.empty(E, d_out, U, device=DEV, dtype=dtype)
+    _lib.tp_fwd(dtype, lmax, N, E, U, d_in, d_out, tab, cgw, csr.row_ptr, csr.ctr, gi, Vi, None, None, Vout)
+    tol = {torch.float64: 1e-12, torch.float32: 2e-5, torch.bfloat16: 1e-2}[dtype]
+    assert _rel(Vout.transpose(1, 2), out_ref.detach()) < tol
+    gVin = torch.empty(E, d_in, U, device=DEV, dtype=dtype)
+    ggam = torch.empty(N, Dd, U, device=DEV, dtype=acc)
+    _lib.tp_bwd(dtype, lmax, N, E, U, d_in, d_out, tab, cgw, csr.row_ptr, csr.ctr, gi, Vi, None, None,
+                gout.transpose(1, 2).contiguous().to(DEV, dtype), gVin, None, None, ggam)
+    assert _rel(gVin.transpose(1, 2), gV_ref) < tol
+    assert _rel(ggam.transpose(1, 2), ggam_ref) < (tol if dtype != torch.bfloat16 else 1e-5)
+
+
+@pytest.mark.parametrize("lmax", [1, 2, 3])
+@pytest.mark.parametrize("dtype", [torch.float64, torch.float32, torch.bfloat16])
+def test_tp_fwd_bwd_implicit_v0(lmax, dtype):
+    """Layer 0 with Vin = Y (x) w0 formed on the fly (tensorembed.py:95)."""
+    U, N, E, L = 8, 19, 250, 2
+    c, b = _tp_case(lmax, 0, L, U, True, dtype)
+    csr, ctr = _csr_random(N, E, seed=3)
+    acc = _lib.ACC_DTYPE[dtype]
+    g = torch.Generator().manual_seed(9)
+    Dd, n_ir, d_out = (lmax + 1) ** 2, lmax + 1, c.base_dim_out
+    Y = torch.randn(E, Dd, generator=g, dtype=torch.float64).to(acc).double()
+    w0 = torch.randn(E, n_ir * U, generator=g, dtype=torch.float64).to(dtype).double()  # internal [r][u]
+    gam = torch.randn(N, U, Dd, generator=g, dtype=torch.float64).to(acc).double()
+    gout = torch.randn(E, U, d_out, generator=g, dtype=torch.float64).to(dtype).double()
+    m = R.MakeWeightedChannels(o3_ref.Irreps.spherical_harmonics(lmax), U)
+    Yt, wt, gt = Y.clone().requires_grad_(True), w0.clone().requires_grad_(True), gam.clone().requires_grad_(True)
+    V0 = m(Yt, wt.view(E, n_ir, U).transpose(1, 2).reshape(E, -1))
+    out_ref = c._contract(V0, gt[ctr])
+    gY_ref, gw_ref, ggam_ref = torch.autograd.grad((out_ref * gout).sum(), (Yt, wt, gt))
+    ijk, _, _ = b.sparse_table()
+    tab, cgw = ijk.to(DEV), b.cgw(acc, DEV)
+    gi = gam.transpose(1, 2).contiguous().to(DEV, acc)
+    Yd, wd = Y.to(DEV, acc), w0.to(DEV, dtype)
+    Vout = torch.empty(E, d_out, U, device=DEV, dtype=dtype)
+    _lib.tp_fwd(dtype, lmax, N, E, U, Dd, d_out, tab, cgw, csr.row_ptr, csr.ctr, gi, None, Yd, wd, Vout)
+    tol = {torch.float64: 1e-12, torch.float32: 2e-5, torch.bfloat16: 1e-2}[dtype]
+    assert _rel(Vout.transpose(1, 2), out_ref.detach()) < tol
+    gw0 = torch.empty(E, n_ir * U, device=DEV, dtype=dtype)
+    gY = torch.zeros(E, Dd, device=DEV, dtype=acc)
+    ggam = torch.empty(N, Dd, U, device=DEV, dtype=acc)
+    _lib.tp_bwd(dtype, lmax, N, E, U, Dd, d_out, tab, cgw, csr.row_ptr, csr.ctr, gi, None, Yd, wd,
+                gout.transpose(1, 2).contiguous().to(DEV, dtype), None, gw0, gY, ggam)
+    assert _rel(gw0, gw_ref) < tol
+    assert _rel(gY, gY_ref) < (tol if dtype != torch.bfloat16 else 1e-5)
+    assert _rel(ggam.transpose(1, 2), ggam_ref) < (tol if dtype != torch.bfloat16 else 1e-5)
+
+
+def test_edge_sum_force_scatter_transpose():
+    N, E = 50, 900
+    csr, ctr = _csr_random(N, E, seed=1)
+    g = torch.Generator().manual_seed(2)
+    for dtype in (torch.float64, torch.float32):
+        Ez = torch.randn(E, generator=g, dtype=torch.float64)
+        Ei = _lib.edge_sum(Ez.to(DEV, dtype), csr.row_ptr, 0.25)
+        ref = torch.zeros(N, dtype=torch.float64).index_add_(0, ctr, 0.25 * Ez)
+        assert _rel(Ei, ref) < TOL[dtype]
+        gEi = torch.randn(N, generator=g, dtype=torch.float64)
+        gEz = _lib.edge_sum_bwd(gEi.to(DEV, dtype), csr.ctr, 0.25)
+        assert _rel(gEz, 0.25 * gEi[ctr]) < TOL[dtype]
+        gv = torch.randn(E, 3, generator=g, dtype=torch.float64)
+        F = _lib.force_scatter(gv.to(DEV, dtype), csr.row_ptr, csr.nbr, N)
+        Fr = torch.zeros(N, 3, dtype=torch.float64).index_add_(0, ctr, gv).index_add_(0, csr.nbr.long().cpu(), -gv)
+        assert _rel(F, Fr) < TOL[dtype] * 10
+    x = torch.randn(33, 5, 7, generator=g).to(DEV)
+    xi = _lib.transpose_ui(x, True)
+    assert torch.equal(xi, x.transpose(1, 2).contiguous())
+    assert torch.equal(_lib.transpose_ui(xi, False), x)
+
+
+# --------------------------------------------------------------------------- #
+# operator level: the reference's test_contract_kernels.py grid
+# --------------------------------------------------------------------------- #
+@pytest.mark.parametrize("irreps_in1", ["0e + 0o + 1e + 1o", "2o + 1e + 0e"])
+@pytest.mark.parametrize("irreps_in2", ["0e + 0o + 1e + 1o"])
+@pytest.mark.parametrize("irreps_out", ["0e + 0o + 1e + 1o", "1o + 2e"])
+@pytest.mark.parametrize("coupling", [True, False])
+@pytest.mark.parametrize("mul", [3, 8])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float64])
+def test_contract_kernel_vs_base(irreps_in1, irreps_in2, irreps_out, coupling, mul, dtype):
+    """tests/nn/test_contract_kernels.py:31-134: forward and grads wrt x1, x2 equal the base
+    (here: oracle) Contracter; 17 edges -> 5 atoms, random scatter idxs."""
+    prev = torch.get_default_dtype()
+    torch.set_default_dtype(dtype)
+    try:
+        torch.manual_seed(0)
+        i1, i2, io = o3_ref.Irreps(irreps_in1), o3_ref.Irreps(irreps_in2), o3_ref.Irreps(irreps_out)
+        c_base = R.Contracter(i1, i2, io, mul=mul, path_channel_coupling=coupling)
+        c_k = B200Contracter(irreps_in1, irreps_in2, irreps_out, mul=mul, instructions=c_base.instructions,
+                             path_channel_coupling=coupling).to(DEV)
+        c_k.load_state_dict(c_base.state_dict())
+        E, N = 17, 5
+        idx = torch.randint(0, N, (E,))
+        x1, x2 = torch.randn(E, mul, i1.dim), torch.randn(E, mul, i2.dim)
+        tol = {torch.float32: 1e-5, torch.float64: 1e-10}[dtype]
+        for arg in (0, 1):
+            a = [x1.clone(), x2.clone()]
+            a[arg].requires_grad_(True)
+            out_o = c_base(a[0], a[1], idx, torch.tensor([N]))
+            go = torch.randn_like(out_o)
+            (g_o,) = torch.autograd.grad(out_o, [a[arg]], go)
+            b = [x1.clone().to(DEV), x2.clone().to(DEV)]
+            b[arg].requires_grad_(True)
+            out_k = c_k(b[0], b[1], idx.to(DEV), torch.tensor([N], device=DEV))
+            (g_k,) = torch.autograd.grad(out_k, [b[arg]], go.to(DEV))
+            torch.testing.assert_close(out_k.cpu(), out_o.detach(), atol=tol, rtol=tol)
+            torch.testing.assert_close(g_k.cpu(), g_o, atol=tol, rtol=tol)
+    finally:
+        torch.set_default_dtype(prev)
+
+
+def test_contracter_scatter_factor_and_equivariance():
+    prev = torch.get_default_dtype()
+    torch.set_default_dtype(torch.float64)
+    try:
+        torch.manual_seed(3)
+        irr = "0e+1o+2e"
+        i = o3_ref.Irreps(irr)
+        c_base = R.Contracter(i, i, i, mul=4, scatter_factor=0.21)
+        c_k = B200Contracter(irr, irr, irr, mul=4, scatter_factor=0.21).to(DEV)
+        c_k.load_state_dict(c_base.state_dict())
+        E, N = 40, 7
+        idx = torch.randint(0, N, (E,))
+        x1, x2 = torch.randn(E, 4, 9), torch.randn(E, 4, 9)
+        out = c_k(x1.to(DEV), x2.to(DEV), idx.to(DEV), N).cpu()
+        assert (out - c_base(x1, x2, idx, N).detach()).abs().max() < 1e-12
+        Rm = o3_ref.random_rotation(4)
+        Dm = torch.block_diag(*[o3_ref.wigner_D_from_rotation(l, Rm) for l in (0, 1, 2)])
+        out_r = c_k((x1 @ Dm.T).to(DEV), (x2 @ Dm.T).to(DEV), idx.to(DEV), N).cpu()
+        assert (out_r - out @ Dm.T).abs().max() < 1e-9
+        with pytest.raises(RuntimeError):
+            c_k.cpu()(x1, x2, idx, N)  # no CPU path
+    finally:
+        torch.set_default_dtype(prev)
