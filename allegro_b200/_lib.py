@@ -78,6 +78,53 @@ def load() -> C.CDLL:
     return lib
 
 
+class _Prof:
+    """Launch counter + optional per-kernel CUDA-event timing (bench.py's roofline leg).
+    Events are recorded on the launching stream (torch's current stream)."""
+
+    def __init__(self):
+        self.launches = 0
+        self.enabled = False
+        self.records = {}
+
+    def reset(self):
+        self.launches = 0
+        self.records = {}
+
+    def times_ms(self):
+        torch.cuda.synchronize()
+        return {k: [a.elapsed_time(b) for a, b in v] for k, v in self.records.items()}
+
+
+PROF = _Prof()
+_TAG = [""]
+
+
+def set_tag(tag: str):
+    """Label subsequent kernel calls (only used to name bench.py's per-kernel timings)."""
+    _TAG[0] = tag
+
+
+class _timed:
+    __slots__ = ("name", "n", "ev")
+
+    def __init__(self, name: str, n_kernels: int = 1):
+        self.name, self.n = name, n_kernels
+
+    def __enter__(self):
+        PROF.launches += self.n
+        if PROF.enabled:
+            self.ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+            self.ev[0].record()
+        return self
+
+    def __exit__(self, *a):
+        if PROF.enabled:
+            self.ev[1].record()
+            PROF.records.setdefault(self.name + "@" + _TAG[0], []).append(self.ev)
+        return False
+
+
 def _check(rc: int):
     if rc != 0:
         msg = load().ab2_last_error()
@@ -115,7 +162,8 @@ def _row_strided(t: torch.Tensor, name: str):
 def sh_fwd(vec: torch.Tensor, lmax: int) -> torch.Tensor:
     E = vec.shape[0]
     Y = torch.empty(E, (lmax + 1) ** 2, dtype=vec.dtype, device=vec.device)
-    _check(load().ab2_sh_fwd(DTYPE_ENUM[vec.dtype], lmax, E, _ptr(_contig(vec, "vec")), _ptr(Y), _stream()))
+    with _timed("sh_fwd"):
+        _check(load().ab2_sh_fwd(DTYPE_ENUM[vec.dtype], lmax, E, _ptr(_contig(vec, "vec")), _ptr(Y), _stream()))
     return Y
 
 
@@ -124,7 +172,8 @@ def sh_bwd(vec: torch.Tensor, gY: torch.Tensor, lmax: int, out: Optional[torch.T
     if out is None:
         out = torch.empty_like(vec)
         accumulate = False
-    _check(load().ab2_sh_bwd(DTYPE_ENUM[vec.dtype], lmax, E, _ptr(_contig(vec, "vec")), _ptr(_contig(gY, "gY")), _ptr(out), int(accumulate), _stream()))
+    with _timed("sh_bwd"):
+        _check(load().ab2_sh_bwd(DTYPE_ENUM[vec.dtype], lmax, E, _ptr(_contig(vec, "vec")), _ptr(_contig(gY, "gY")), _ptr(out), int(accumulate), _stream()))
     return out
 
 
@@ -164,12 +213,13 @@ def linear(
     if aux is not None:
         aux, aux_ld = _row_strided(aux, "aux")
         assert aux.dtype == dt
-    _check(
-        load().ab2_linear(
-            DTYPE_ENUM[dt], M, K, N, na, a_ptr, a_ld, a_w, act, _ptr(_contig(W, "W")), no, o_ptr, o_ld, o_w, o_acc, epi,
-            _ptr(aux), aux_ld, _stream(),
+    with _timed("linear", 1):
+        _check(
+            load().ab2_linear(
+                DTYPE_ENUM[dt], M, K, N, na, a_ptr, a_ld, a_w, act, _ptr(_contig(W, "W")), no, o_ptr, o_ld, o_w, o_acc, epi,
+                _ptr(aux), aux_ld, _stream(),
+            )
         )
-    )
 
 
 def env_sum(dtype, lmax: int, N: int, U: int, row_ptr, Y, w: torch.Tensor, sf: float, out: Optional[torch.Tensor] = None):
@@ -177,7 +227,8 @@ def env_sum(dtype, lmax: int, N: int, U: int, row_ptr, Y, w: torch.Tensor, sf: f
     D = (lmax + 1) ** 2
     if out is None:
         out = torch.empty(N, D, U, dtype=ACC_DTYPE[dtype], device=Y.device)
-    _check(load().ab2_env_sum(DTYPE_ENUM[dtype], lmax, N, U, _ptr(row_ptr), _ptr(_contig(Y, "Y")), _ptr(w), w_ld, float(sf), _ptr(out), _stream()))
+    with _timed("env_sum"):
+        _check(load().ab2_env_sum(DTYPE_ENUM[dtype], lmax, N, U, _ptr(row_ptr), _ptr(_contig(Y, "Y")), _ptr(w), w_ld, float(sf), _ptr(out), _stream()))
     return out
 
 
@@ -185,12 +236,13 @@ def env_bwd(dtype, lmax: int, U: int, ctr, Y, w: torch.Tensor, ggamma, sf: float
     w, w_ld = _row_strided(w, "w")
     gw, gw_ld = _row_strided(gw, "gw")
     E = Y.shape[0]
-    _check(
-        load().ab2_env_bwd(
-            DTYPE_ENUM[dtype], lmax, E, U, _ptr(ctr), _ptr(_contig(Y, "Y")), _ptr(w), w_ld, _ptr(_contig(ggamma, "ggamma")), float(sf),
-            _ptr(gw), gw_ld, _ptr(_contig(gY, "gY")), _stream(),
+    with _timed("env_bwd", 1):
+        _check(
+            load().ab2_env_bwd(
+                DTYPE_ENUM[dtype], lmax, E, U, _ptr(ctr), _ptr(_contig(Y, "Y")), _ptr(w), w_ld, _ptr(_contig(ggamma, "ggamma")), float(sf),
+                _ptr(gw), gw_ld, _ptr(_contig(gY, "gY")), _stream(),
+            )
         )
-    )
 
 
 def tp_fwd(dtype, lmax, N, E, U, d_in, d_out, tab, cgw, row_ptr, ctr, gamma, Vin, Y, w0, Vout):
@@ -198,12 +250,13 @@ def tp_fwd(dtype, lmax, N, E, U, d_in, d_out, tab, cgw, row_ptr, ctr, gamma, Vin
     w0_ld = 0
     if implicit:
         w0, w0_ld = _row_strided(w0, "w0")
-    _check(
-        load().ab2_tp_fwd(
-            DTYPE_ENUM[dtype], lmax, N, E, U, d_in, d_out, tab.shape[0], _ptr(tab), _ptr(cgw), _ptr(row_ptr), _ptr(ctr), _ptr(gamma),
-            _ptr(Vin), int(implicit), _ptr(Y), _ptr(w0) if implicit else None, w0_ld, _ptr(Vout), _stream(),
+    with _timed("tp_fwd", 1):
+        _check(
+            load().ab2_tp_fwd(
+                DTYPE_ENUM[dtype], lmax, N, E, U, d_in, d_out, tab.shape[0], _ptr(tab), _ptr(cgw), _ptr(row_ptr), _ptr(ctr), _ptr(gamma),
+                _ptr(Vin), int(implicit), _ptr(Y), _ptr(w0) if implicit else None, w0_ld, _ptr(Vout), _stream(),
+            )
         )
-    )
 
 
 def tp_bwd(dtype, lmax, N, E, U, d_in, d_out, tab, cgw, row_ptr, ctr, gamma, Vin, Y, w0, gVout, gVin, gw0, gY, ggamma):
@@ -212,26 +265,29 @@ def tp_bwd(dtype, lmax, N, E, U, d_in, d_out, tab, cgw, row_ptr, ctr, gamma, Vin
     if implicit:
         w0, w0_ld = _row_strided(w0, "w0")
         gw0, gw0_ld = _row_strided(gw0, "gw0")
-    _check(
-        load().ab2_tp_bwd(
-            DTYPE_ENUM[dtype], lmax, N, E, U, d_in, d_out, tab.shape[0], _ptr(tab), _ptr(cgw), _ptr(row_ptr), _ptr(ctr), _ptr(gamma),
-            _ptr(Vin), int(implicit), _ptr(Y), _ptr(w0) if implicit else None, w0_ld, _ptr(gVout), _ptr(gVin),
-            _ptr(gw0) if implicit else None, gw0_ld, _ptr(gY) if implicit else None, _ptr(ggamma), _stream(),
+    with _timed("tp_bwd", 2):
+        _check(
+            load().ab2_tp_bwd(
+                DTYPE_ENUM[dtype], lmax, N, E, U, d_in, d_out, tab.shape[0], _ptr(tab), _ptr(cgw), _ptr(row_ptr), _ptr(ctr), _ptr(gamma),
+                _ptr(Vin), int(implicit), _ptr(Y), _ptr(w0) if implicit else None, w0_ld, _ptr(gVout), _ptr(gVin),
+                _ptr(gw0) if implicit else None, gw0_ld, _ptr(gY) if implicit else None, _ptr(ggamma), _stream(),
+            )
         )
-    )
 
 
 def edge_sum(Ez: torch.Tensor, row_ptr: torch.Tensor, factor: float) -> torch.Tensor:
     N = row_ptr.shape[0] - 1
     Ei = torch.empty(N, dtype=Ez.dtype, device=Ez.device)
-    _check(load().ab2_edge_sum(DTYPE_ENUM[Ez.dtype], N, _ptr(row_ptr), _ptr(_contig(Ez, "Ez")), float(factor), _ptr(Ei), _stream()))
+    with _timed("edge_sum"):
+        _check(load().ab2_edge_sum(DTYPE_ENUM[Ez.dtype], N, _ptr(row_ptr), _ptr(_contig(Ez, "Ez")), float(factor), _ptr(Ei), _stream()))
     return Ei
 
 
 def edge_sum_bwd(gEi: torch.Tensor, ctr: torch.Tensor, factor: float) -> torch.Tensor:
     E = ctr.shape[0]
     gEz = torch.empty(E, dtype=gEi.dtype, device=gEi.device)
-    _check(load().ab2_edge_sum_bwd(DTYPE_ENUM[gEi.dtype], E, _ptr(ctr), _ptr(_contig(gEi, "gEi")), float(factor), _ptr(gEz), _stream()))
+    with _timed("edge_sum_bwd"):
+        _check(load().ab2_edge_sum_bwd(DTYPE_ENUM[gEi.dtype], E, _ptr(ctr), _ptr(_contig(gEi, "gEi")), float(factor), _ptr(gEz), _stream()))
     return gEz
 
 
@@ -239,7 +295,8 @@ def force_scatter(gvec: torch.Tensor, row_ptr: torch.Tensor, nbr: torch.Tensor, 
     N = row_ptr.shape[0] - 1
     E = nbr.shape[0]
     F = torch.zeros(num_atoms_total, 3, dtype=gvec.dtype, device=gvec.device)
-    _check(load().ab2_force_scatter(DTYPE_ENUM[gvec.dtype], N, E, _ptr(row_ptr), _ptr(nbr), _ptr(_contig(gvec, "gvec")), _ptr(F), _stream()))
+    with _timed("force_scatter"):
+        _check(load().ab2_force_scatter(DTYPE_ENUM[gvec.dtype], N, E, _ptr(row_ptr), _ptr(nbr), _ptr(_contig(gvec, "gvec")), _ptr(F), _stream()))
     return F
 
 
@@ -248,7 +305,8 @@ def transpose_ui(x: torch.Tensor, to_internal: bool) -> torch.Tensor:
     E, a, b = x.shape
     U, d = (a, b) if to_internal else (b, a)
     out = torch.empty(E, d, U, dtype=x.dtype, device=x.device) if to_internal else torch.empty(E, U, d, dtype=x.dtype, device=x.device)
-    _check(load().ab2_transpose_ui(DTYPE_ENUM[x.dtype], E, U, d, _ptr(_contig(x, "x")), _ptr(out), int(to_internal), _stream()))
+    with _timed("transpose_ui"):
+        _check(load().ab2_transpose_ui(DTYPE_ENUM[x.dtype], E, U, d, _ptr(_contig(x, "x")), _ptr(out), int(to_internal), _stream()))
     return out
 
 
@@ -256,7 +314,8 @@ def op_scatter_env(x2: torch.Tensor, idxs: torch.Tensor, n: int, sf: float) -> t
     E = x2.shape[0]
     row = x2[0].numel() if E else 0
     gamma = torch.zeros((n,) + tuple(x2.shape[1:]), dtype=x2.dtype, device=x2.device)
-    _check(load().ab2_op_scatter_env(DTYPE_ENUM[x2.dtype], E, row, float(sf), _ptr(_contig(x2, "x2")), _ptr(_contig(idxs, "idxs")), _ptr(gamma), _stream()))
+    with _timed("op_scatter_env"):
+        _check(load().ab2_op_scatter_env(DTYPE_ENUM[x2.dtype], E, row, float(sf), _ptr(_contig(x2, "x2")), _ptr(_contig(idxs, "idxs")), _ptr(gamma), _stream()))
     return gamma
 
 
@@ -264,16 +323,18 @@ def op_gather_rows(src: torch.Tensor, idxs: torch.Tensor, sf: float) -> torch.Te
     E = idxs.shape[0]
     row = src[0].numel()
     out = torch.empty((E,) + tuple(src.shape[1:]), dtype=src.dtype, device=src.device)
-    _check(load().ab2_op_gather_rows(DTYPE_ENUM[src.dtype], E, row, float(sf), _ptr(_contig(src, "src")), _ptr(_contig(idxs, "idxs")), _ptr(out), _stream()))
+    with _timed("op_gather_rows"):
+        _check(load().ab2_op_gather_rows(DTYPE_ENUM[src.dtype], E, row, float(sf), _ptr(_contig(src, "src")), _ptr(_contig(idxs, "idxs")), _ptr(out), _stream()))
     return out
 
 
 def op_contract(mode: int, U, d1, d2, dout, tab, cgw, a, b, idxs, out):
     E = idxs.shape[0]
-    _check(
-        load().ab2_op_contract(
-            DTYPE_ENUM[a.dtype], mode, E, U, d1, d2, dout, tab.shape[0], _ptr(tab), _ptr(cgw), _ptr(_contig(a, "a")), _ptr(_contig(b, "b")),
-            _ptr(_contig(idxs, "idxs")), _ptr(out), _stream(),
+    with _timed("op_contract", 1):
+        _check(
+            load().ab2_op_contract(
+                DTYPE_ENUM[a.dtype], mode, E, U, d1, d2, dout, tab.shape[0], _ptr(tab), _ptr(cgw), _ptr(_contig(a, "a")), _ptr(_contig(b, "b")),
+                _ptr(_contig(idxs, "idxs")), _ptr(out), _stream(),
+            )
         )
-    )
     return out

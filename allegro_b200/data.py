@@ -74,25 +74,27 @@ def _brute_force(pos, cell, pbc, r_max):
     return torch.cat(ei, dim=1), torch.cat(sh, dim=0)
 
 
-def _cell_list(pos, box, r_max, chunk: int = 1 << 22):
-    """Orthorhombic fully periodic box with >= 3 cells per axis."""
+def _cell_list(pos, box, r_max, pbc=(True, True, True), origin=None):
+    """Orthorhombic box, per-axis periodicity.  Periodic axes need >= 3 cells; on a
+    non-periodic axis the grid spans [origin, origin+box) and nothing wraps."""
     dev = pos.device
     n = pos.shape[0]
+    pbc_t = torch.tensor([bool(p) for p in pbc], device=dev)
+    if origin is None:
+        origin = torch.zeros(3, dtype=pos.dtype, device=dev)
     ncell = torch.floor(box / r_max).to(torch.long).clamp(min=1)
-    assert int(ncell.min()) >= 3, "cell list needs box >= 3 r_max on every axis"
-    frac = pos / box
-    frac = frac - torch.floor(frac)
-    cidx3 = torch.minimum((frac * ncell).to(torch.long), ncell - 1)
+    assert int(ncell[pbc_t].min() if bool(pbc_t.any()) else 3) >= 3, "cell list needs box >= 3 r_max on every periodic axis"
+    rel = pos - origin
+    img0 = torch.where(pbc_t, torch.floor(rel / box), torch.zeros_like(rel)).to(torch.long)  # image index of the raw position
+    wrapped = rel - img0.to(pos.dtype) * box
+    cidx3 = torch.minimum(torch.clamp((wrapped / box * ncell).to(torch.long), min=0), ncell - 1)
     nc = [int(v) for v in ncell]
     cid = (cidx3[:, 0] * nc[1] + cidx3[:, 1]) * nc[2] + cidx3[:, 2]
     order = torch.argsort(cid, stable=True)
-    cid_sorted = cid[order]
     ncells = nc[0] * nc[1] * nc[2]
-    counts = torch.bincount(cid_sorted, minlength=ncells)
+    counts = torch.bincount(cid, minlength=ncells)
     starts = torch.cumsum(counts, 0) - counts
     ei, sh = [], []
-    wrapped = pos - torch.floor(pos / box) * box  # positions folded into the box
-    base_shift = torch.floor(pos / box).to(torch.long)  # image index of the raw position
     ar = torch.arange(n, device=dev)
     for dx in (-1, 0, 1):
         for dy in (-1, 0, 1):
@@ -100,9 +102,12 @@ def _cell_list(pos, box, r_max, chunk: int = 1 << 22):
                 d = torch.tensor([dx, dy, dz], device=dev)
                 c3 = cidx3 + d
                 img = torch.div(c3, ncell, rounding_mode="floor")  # -1, 0, +1
-                c3w = c3 - img * ncell
+                valid = (pbc_t | (img == 0)).all(-1)
+                img = torch.where(pbc_t, img, torch.zeros_like(img))
+                c3w = torch.clamp(c3 - img * ncell, min=0)
+                c3w = torch.minimum(c3w, ncell - 1)
                 ncid = (c3w[:, 0] * nc[1] + c3w[:, 1]) * nc[2] + c3w[:, 2]
-                cnt = counts[ncid]
+                cnt = counts[ncid] * valid
                 tot = int(cnt.sum())
                 if tot == 0:
                     continue
@@ -114,7 +119,7 @@ def _cell_list(pos, box, r_max, chunk: int = 1 << 22):
                 keep = (rij.norm(dim=-1) < r_max) & ~((i_rep == j_rep) & (img_rep == 0).all(-1))
                 i_k, j_k = i_rep[keep], j_rep[keep]
                 # shift relative to the *raw* positions: r = pos[j] + shift*box - pos[i]
-                s = img_rep[keep] - base_shift[j_k] + base_shift[i_k]
+                s = img_rep[keep] - img0[j_k] + img0[i_k]
                 ei.append(torch.stack([i_k, j_k]))
                 sh.append(s)
     return torch.cat(ei, dim=1), torch.cat(sh, dim=0)
@@ -133,10 +138,19 @@ def neighbor_list(
     ortho = cell is not None and bool((cell.view(3, 3) - torch.diag(torch.diagonal(cell.view(3, 3)))).abs().max() == 0)
     if method == "auto":
         big = pos.shape[0] > 3000
-        can = cell is not None and ortho and all(pbc) and float(torch.diagonal(cell.view(3, 3)).min()) >= 3 * r_max
+        can = cell is not None and ortho and all(
+            (not p) or float(cell.view(3, 3)[a, a]) >= 3 * r_max for a, p in enumerate(pbc)
+        )
         method = "cell" if (big and can) else "brute"
     if method == "cell":
-        ei, sh = _cell_list(pos, torch.diagonal(cell.view(3, 3)).to(pos.dtype), float(r_max))
+        box = torch.diagonal(cell.view(3, 3)).to(pos.dtype).clone()
+        origin = torch.zeros(3, dtype=pos.dtype, device=pos.device)
+        for a, p in enumerate(pbc):
+            if not p:  # non-periodic axis: grid over the occupied extent
+                lo, hi = pos[:, a].min(), pos[:, a].max()
+                origin[a] = lo
+                box[a] = (hi - lo) * (1 + 1e-9) + 1e-6
+        ei, sh = _cell_list(pos, box, float(r_max), pbc, origin)
     else:
         ei, sh = _brute_force(pos, cell, pbc, float(r_max))
     n = pos.shape[0]

@@ -93,6 +93,7 @@ class AllegroCore:
         assert vec.dtype == self.acc and x_emb.dtype == dt
         sv = _Saved()
         sv.csr, sv.vec = csr, vec
+        _lib.set_tag("fwd.embed")
         Y = _lib.sh_fwd(vec, self.lmax)
         X = torch.empty(E, S * (L + 1), dtype=dt, device=dev)
         w0 = torch.empty(E, self.nw, dtype=dt, device=dev)
@@ -101,6 +102,7 @@ class AllegroCore:
         V: List[Optional[torch.Tensor]] = [None]
         gammas, pre_lat = [], []
         for l, ly in enumerate(self.layers):
+            _lib.set_tag(f"fwd.L{l}")
             gamma = _lib.env_sum(dt, self.lmax, N, U, csr.row_ptr, Y, omega[l], self.sf)
             Vn = torch.empty(E, ly["d_out"], U, dtype=dt, device=dev)
             _lib.tp_fwd(dt, self.lmax, N, E, U, ly["d_in"], ly["d_out"], ly["tab"], ly["cgw"], csr.row_ptr, csr.ctr, gamma,
@@ -113,6 +115,7 @@ class AllegroCore:
             pre_lat.append(ly["mlp"].forward([X[:, : S * (l + 1)], s], outs))
             V.append(Vn)
             gammas.append(gamma)
+        _lib.set_tag("fwd.readout")
         Ez = torch.empty(E, 1, dtype=dt, device=dev)
         pre_read = self.readout.forward([X], [Ez])
         Ei = _lib.edge_sum(Ez.view(E).to(self.acc), csr.row_ptr, self.factor)
@@ -125,6 +128,7 @@ class AllegroCore:
         csr = sv.csr
         E, N, U, S, L, D = csr.num_edges, csr.num_atoms, self.U, self.S, self.L, self.D
         dt, dev = self.dtype, self.device
+        _lib.set_tag("bwd.readout")
         gEz = _lib.edge_sum_bwd(gEi.contiguous(), csr.ctr, self.factor).to(dt).view(E, 1)
         gX = torch.empty(E, S * (L + 1), dtype=dt, device=dev)
         self.readout.backward([gEz], sv.pre_read, [gX], [False])
@@ -134,6 +138,7 @@ class AllegroCore:
         gw0 = None
         for l in range(L - 1, -1, -1):
             ly = self.layers[l]
+            _lib.set_tag(f"bwd.L{l}")
             if ly["last"]:
                 gV_next = torch.empty(E, ly["d_out"], U, dtype=dt, device=dev)
                 if ly["d_out"] > 1:
@@ -159,6 +164,7 @@ class AllegroCore:
             gomega = torch.empty(E, self.nw, dtype=dt, device=dev)
             _lib.env_bwd(dt, self.lmax, U, csr.ctr, sv.Y, sv.omega[l], ggamma, self.sf, gomega, gY)
             gV_next, gomega_next = gV_in, gomega
+        _lib.set_tag("bwd.embed")
         gx_emb = torch.empty(E, self.S_in, dtype=dt, device=dev)
         self.embed.backward([gw0, gX[:, :S], gomega_next], [], [gx_emb], [False])
         gvec = _lib.sh_bwd(sv.vec, gY, self.lmax)

@@ -1,0 +1,310 @@
+#!/usr/bin/env python
+"""bench.py -- atom-steps/s (energy + forces) of the Allegro hot path on B200.
+
+    python bench.py --gpus N --steps K --warmup W            # this framework
+    python bench.py --impl reference --gpus N --steps K ...  # CPU reference arm (oracle port)
+
+One "step" = one energy+forces evaluation of the configured model on one synthetic frame
+(neighbour list given, built outside the timed region).  N=1 workload: BASELINE.json
+configs[1] (c2: 10 976-atom Cu FCC, l_max=2, 2 layers, 64 features, r_max=5.0).
+Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+METRIC = "atom-steps/sec (energy+forces)"
+UNIT = "atom-steps/s"
+
+
+# --------------------------------------------------------------------------------------
+# clocks sampling (nvidia-smi during the timed region)
+# --------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.rows = []
+        self._stop = threading.Event()
+        self._t = None
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def start(self):
+        self._t = threading.Thread(target=self._run, daemon=True)
+        self._t.start()
+
+    def stop(self):
+        self._stop.set()
+        if self._t:
+            self._t.join(timeout=6)
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx.append(float(r[1]))
+            except Exception:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------------------
+# workload
+# --------------------------------------------------------------------------------------
+def build_workload(cfg: str, dtype: str, device, scale=None):
+    from allegro_b200 import data as D
+    from allegro_b200 import systems
+    from allegro_b200.model import AllegroModel
+
+    d = systems.make_system(cfg, scale)
+    n, e = d[D.POSITIONS_KEY].shape[0], d[D.EDGE_INDEX_KEY].shape[1]
+    kw = systems.model_kwargs(cfg, e / n, dtype)
+    model = AllegroModel(**kw).to(device)
+    data = {k: v.to(device) for k, v in d.items()}
+    return model, data, d, kw, n, e
+
+
+def algorithmic_bytes_per_edge(name: str, core) -> float:
+    """Bytes that must cross HBM per edge for each kernel of the current (per-kernel) pipeline
+    (DESIGN.md section 4); b = bytes per activation element, 4 = fp32 accumulate-type element."""
+    b = {torch.float64: 8, torch.float32: 4, torch.bfloat16: 2}[core.dtype]
+    a = 8 if core.dtype == torch.float64 else 4
+    U, S, D, nw, L = core.U, core.S, core.D, core.nw, core.L
+    kern, _, tag = name.partition("@")
+    layer = int(tag.split("L")[1]) if ".L" in tag else None
+    if kern == "tp_fwd":
+        ly = core.layers[layer]
+        vin = (b * nw + a * D) if layer == 0 else b * U * ly["d_in"]
+        return vin + 4 + b * U * ly["d_out"]
+    if kern == "tp_bwd":
+        ly = core.layers[layer]
+        vin = (b * nw + a * D) if layer == 0 else b * U * ly["d_in"]
+        gin = (b * nw + 2 * a * D) if layer == 0 else b * U * ly["d_in"]
+        return vin + 4 + b * U * ly["d_out"] + gin
+    if kern == "env_sum":
+        return b * nw + a * D
+    if kern == "env_bwd":
+        return 2 * b * nw + 3 * a * D + 4
+    return float("nan")
+
+
+def run_ours(args, rank: int, world: int):
+    from allegro_b200 import _lib
+    from allegro_b200 import data as D
+
+    if world > 1:
+        from allegro_b200 import halo  # noqa: F401  (spatial decomposition; see bench_multi)
+
+        return run_ours_multi(args, rank, world)
+    dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", 0)))
+    torch.cuda.set_device(dev)
+    cfg = args.config
+    from allegro_b200 import systems
+
+    dtype = args.dtype or systems.CONFIGS[cfg]["dtype"]
+    model, data, d_cpu, kw, n_atoms, n_edges = build_workload(cfg, dtype, dev)
+    K, W = args.steps, args.warmup
+
+    def step():
+        return model(data)
+
+    for _ in range(W):
+        out = step()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(dev.index or 0)
+    sampler.start()
+    # ---- leg 1: inputs resident in HBM, device-timed ----
+    _lib.PROF.reset()
+    _lib.PROF.enabled = False
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    t0.record()
+    for _ in range(K):
+        out = step()
+    t1.record()
+    torch.cuda.synchronize()
+    ms = t0.elapsed_time(t1) / K
+    launches = _lib.PROF.launches
+    # ---- leg 2: same K steps with per-kernel CUDA events (roofline of the dominant kernel) ----
+    _lib.PROF.reset()
+    _lib.PROF.enabled = True
+    for _ in range(K):
+        out = step()
+    times = _lib.PROF.times_ms()
+    _lib.PROF.enabled = False
+    # ---- leg 3: end to end through the public API with HOST buffers ----
+    pos_host = d_cpu[D.POSITIONS_KEY].clone().pin_memory()
+    f_host = torch.empty(n_atoms, 3, dtype=out[D.FORCE_KEY].dtype).pin_memory()
+    e_host = torch.empty(1, 1, dtype=out[D.TOTAL_ENERGY_KEY].dtype).pin_memory()
+    data_e2e = dict(data)
+
+    def step_e2e():
+        data_e2e[D.POSITIONS_KEY] = pos_host.to(dev, non_blocking=True)
+        o = model(data_e2e)
+        f_host.copy_(o[D.FORCE_KEY], non_blocking=True)
+        e_host.copy_(o[D.TOTAL_ENERGY_KEY], non_blocking=True)
+
+    for _ in range(2):
+        step_e2e()
+    torch.cuda.synchronize()
+    t0.record()
+    for _ in range(K):
+        step_e2e()
+    t1.record()
+    torch.cuda.synchronize()
+    ms_e2e = t0.elapsed_time(t1) / K
+    clocks = sampler.stop()
+
+    core = model.model.core()
+    per_kernel = {k: sum(v) / K for k, v in times.items()}  # ms per step
+    kernel_total = sum(per_kernel.values())
+    dom = max(per_kernel, key=per_kernel.get)
+    # the roofline is quoted for the dominant tensor-product kernel (the path's named hot loop)
+    tp_like = {k: v for k, v in per_kernel.items() if k.split("@")[0] in ("tp_fwd", "tp_bwd", "env_sum", "env_bwd")}
+    dom_tp = max(tp_like, key=tp_like.get)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    n_l = len(times[dom_tp]) / K
+    avg_ms = per_kernel[dom_tp] / n_l
+    bpe = algorithmic_bytes_per_edge(dom_tp, core)
+    achieved = bpe * n_edges / (avg_ms * 1e-3) / 1e9
+    roofline = {
+        "kernel": dom_tp, "bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
+        "frac": round(achieved / peak, 4), "traffic": None, "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 (of fallback)",
+        "algorithmic_bytes_per_edge": bpe, "avg_launch_ms": round(avg_ms, 5), "share_of_kernel_time": round(per_kernel[dom_tp] / kernel_total, 4),
+    }
+    res = {
+        "metric": METRIC, "value": n_atoms * 1e3 / ms, "unit": UNIT, "n_gpus": 1, "steps": K, "warmup": W, "ms_per_step": ms,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": {"float64": "f64", "float32": "f32", "bfloat16": "bf16"}[dtype], "data": "synthetic",
+        "config": {"workload": f"{cfg}: {systems.CONFIGS[cfg]['system']}, {n_atoms} atoms, {n_edges} edges, l_max={kw['l_max']}, "
+                               f"n_layers={kw['num_layers']}, S={kw['num_scalar_features']}, U={kw['num_tensor_features']}, r_max={kw['r_max']}",
+                   "global_atoms": n_atoms, "parallelism": "1 GPU", "timing": "CUDA events, inputs larger than L2 (per-step working set "
+                   f"~{n_edges * 5e3 / 1e9:.1f} GB >> 126 MB L2), neighbour list resident"},
+        "ns_per_day_at_1fs": 1e3 / ms * 0.0864,
+        "clocks": clocks,
+        "e2e": {"value": n_atoms * 1e3 / ms_e2e, "unit": UNIT, "ms_per_step": ms_e2e,
+                "h2d_bytes_per_step": pos_host.numel() * pos_host.element_size(),
+                "d2h_bytes_per_step": f_host.numel() * f_host.element_size() + e_host.numel() * e_host.element_size()},
+        "gpu_launches": launches,
+        "roofline": roofline,
+        "kernels_ms_per_step": {k: round(v, 4) for k, v in sorted(per_kernel.items(), key=lambda kv: -kv[1])},
+        "kernel_time_ms_per_step": round(kernel_total, 4),
+        "dominant_kernel": dom,
+    }
+    if not args.no_cpu_baseline:
+        res["cpu_baseline"] = cpu_baseline(cfg, steps=3)
+    print(json.dumps(res))
+
+
+def run_ours_multi(args, rank, world):
+    raise NotImplementedError("multi-GPU bench leg not wired yet")
+
+
+# --------------------------------------------------------------------------------------
+# CPU reference arm / baseline: the oracle port on the host cores
+# --------------------------------------------------------------------------------------
+def _oracle_setup(cfg: str, scale: int):
+    from allegro_b200 import data as D
+    from allegro_b200 import systems
+    from oracle.model_ref import AllegroOracle
+
+    d = systems.make_system(cfg, scale)
+    n, e = d[D.POSITIONS_KEY].shape[0], d[D.EDGE_INDEX_KEY].shape[1]
+    kw = systems.model_kwargs(cfg, e / n, "float32")
+    return AllegroOracle(**kw), d, n, e, kw
+
+
+def cpu_baseline(cfg: str, steps: int = 3, scale: int = 3):
+    oracle, d, n, e, _ = _oracle_setup(cfg, scale)
+    oracle(d)
+    t = time.perf_counter()
+    for _ in range(steps):
+        oracle(d)
+    dt = (time.perf_counter() - t) / steps
+    return {"value": n / dt, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"{cfg} architecture (fp32 eager PyTorch oracle, edge-chunked dense contraction) on a {scale}^3 supercell: "
+                      f"{n} atoms, {e} edges, {steps} evaluations of {dt:.2f} s; cost is linear in edges",
+            "host_cpus": os.cpu_count()}
+
+
+def run_reference(args, rank: int, world: int):
+    if rank != 0:
+        return
+    cfg = args.config
+    K, W = args.steps, args.warmup
+    scale = 3 if K + W > 12 else 4
+    oracle, d, n, e, kw = _oracle_setup(cfg, scale)
+    for _ in range(max(W, 1)):
+        oracle(d)
+    t = time.perf_counter()
+    for _ in range(K):
+        oracle(d)
+    dt = (time.perf_counter() - t) / K
+    val = n / dt
+    from allegro_b200 import systems
+
+    res = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": K, "warmup": W,
+        "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{cfg}: {systems.CONFIGS[cfg]['system']} architecture l_max={kw['l_max']}, n_layers={kw['num_layers']}, "
+                               f"S={kw['num_scalar_features']}, U={kw['num_tensor_features']}; bounded sample {n} atoms / {e} edges per step",
+                   "note": "plain-PyTorch restatement of the reference (nequip/e3nn are not installable here), CPU, all host threads"},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+                         "sample": f"{scale}^3 supercell, {n} atoms, {e} edges per step"},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(res))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="c2")
+    ap.add_argument("--dtype", default=None, choices=[None, "float64", "float32", "bfloat16"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    if args.impl == "reference":
+        return run_reference(args, rank, world)
+    return run_ours(args, rank, world)
+
+
+if __name__ == "__main__":
+    main()
