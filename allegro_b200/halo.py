@@ -1,0 +1,187 @@
+"""Spatial domain decomposition with a single-r_max halo.
+
+Allegro is strictly local: E_i depends only on atoms within r_max of i
+(/root/reference/tests/model/test_allegro.py:68-70; the environment sum only runs over edges
+centred on i, allegro/nn/_strided/_contract.py:199-205).  So atoms are split into 1-D slabs
+along x, one per rank / GPU; each rank evaluates the edges of its OWNED centres, with
+neighbours taken from owned + ghost atoms in exactly the reference's ghost-atom data format
+(ghosts appended after the locals, neighbour index >= N_local,
+/root/reference/allegro/_compile.py:41-61).
+
+Per force evaluation the only communication is
+  1. forward halo : positions of boundary atoms -> neighbouring slabs' ghosts
+  2. reverse halo : dE/dpos accumulated on ghosts -> added on the owning rank
+  3. one all-reduce of the scalar total energy
+through torch.distributed point-to-point ops (NCCL over NVLink on the GPU box, gloo in the
+CPU tests).  There is no reference counterpart (the reference delegates this to LAMMPS' MPI).
+
+The decomposition itself is set up from the global synthetic frame, which every rank can
+generate deterministically, so set-up needs no communication.
+"""
+from __future__ import annotations
+
+from typing import Callable, Dict, List, Optional, Tuple
+
+import torch
+import torch.distributed as dist
+
+from . import data as D
+
+
+class SlabDecomposition:
+    """Static exchange plan of one rank (valid as long as the neighbour list is)."""
+
+    def __init__(self, pos: torch.Tensor, cell: torch.Tensor, types: torch.Tensor, r_max: float, rank: int, world: int):
+        assert world >= 2, "use the plain periodic path on one rank"
+        cell = cell.view(3, 3)
+        assert bool((cell - torch.diag(torch.diagonal(cell))).abs().max() == 0), "slab decomposition needs an orthorhombic box"
+        Lx = float(cell[0, 0])
+        width = Lx / world
+        assert width >= r_max, "slab thinner than r_max: neighbours beyond the adjacent slab"
+        self.rank, self.world, self.r_max, self.Lx = rank, world, float(r_max), Lx
+        x = pos[:, 0] - torch.floor(pos[:, 0] / Lx) * Lx
+        slab = torch.clamp((x / width).long(), max=world - 1)
+
+        def owned_of(r):
+            return torch.nonzero(slab == r).squeeze(-1)
+
+        def send_lists(r):
+            ids = owned_of(r)
+            xr = x[ids]
+            lo, hi = r * width, (r + 1) * width
+            return ids[xr >= hi - r_max], ids[xr < lo + r_max]  # (to the right neighbour, to the left neighbour)
+
+        self.left, self.right = (rank - 1) % world, (rank + 1) % world
+        self.owned = owned_of(rank)
+        self.n_owned = int(self.owned.shape[0])
+        my_to_right, my_to_left = send_lists(rank)
+        # positions in the local owned array
+        inv = torch.full((pos.shape[0],), -1, dtype=torch.long)
+        inv[self.owned] = torch.arange(self.n_owned)
+        self.send_right_idx = inv[my_to_right]
+        self.send_left_idx = inv[my_to_left]
+        # what arrives: left neighbour's "to the right" list, right neighbour's "to the left" list
+        left_ids = send_lists(self.left)[0]
+        right_ids = send_lists(self.right)[1]
+        self.n_ghost_left, self.n_ghost_right = int(left_ids.shape[0]), int(right_ids.shape[0])
+        self.ghost_global = torch.cat([left_ids, right_ids])
+        self.n_ghost = self.n_ghost_left + self.n_ghost_right
+        # periodic wrap of the ghost images along x
+        self.shift_left = -Lx if rank == 0 else 0.0
+        self.shift_right = Lx if rank == world - 1 else 0.0
+        self.types_local = torch.cat([types[self.owned], types[self.ghost_global]])
+        self.global_ids_local = torch.cat([self.owned, self.ghost_global])
+        # local periodic cell: x is open (ghosts cover it), y and z stay periodic
+        self.cell = cell.clone()
+        self.pbc = (False, True, True)
+        # unwrapped x so that slab + ghosts form one contiguous block along x
+        pos_local = self.local_positions_from_global(pos)
+        ei, sh = D.neighbor_list(pos_local, r_max, self.cell, self.pbc)
+        keep = ei[0] < self.n_owned  # edges of owned centres only
+        self.edge_index = ei[:, keep].contiguous()
+        self.edge_cell_shift = sh[keep].contiguous()
+
+    # positions of owned + ghost atoms taken from a global frame (set-up / tests)
+    def local_positions_from_global(self, pos: torch.Tensor) -> torch.Tensor:
+        Lx = self.Lx
+        p = pos.clone()
+        p[:, 0] = p[:, 0] - torch.floor(p[:, 0] / Lx) * Lx
+        gl = p[self.ghost_global[: self.n_ghost_left]].clone()
+        gr = p[self.ghost_global[self.n_ghost_left :]].clone()
+        gl[:, 0] += self.shift_left
+        gr[:, 0] += self.shift_right
+        return torch.cat([p[self.owned], gl, gr], 0)
+
+    def to(self, device) -> "SlabDecomposition":
+        for k in ("owned", "send_right_idx", "send_left_idx", "ghost_global", "types_local", "global_ids_local", "cell",
+                  "edge_index", "edge_cell_shift"):
+            setattr(self, k, getattr(self, k).to(device))
+        return self
+
+    # ---- communication --------------------------------------------------------------------
+    def _peers(self):
+        """-> list of (peer, [send segments], [recv segment sizes]) in a canonical order that
+        both sides agree on (right-going list first, then left-going)."""
+        if self.left == self.right:  # world == 2: both neighbours are the same rank
+            return [(self.left, ["right", "left"], ["from_left", "from_right"])]
+        return [(self.right, ["right"], ["from_right"]), (self.left, ["left"], ["from_left"])]
+
+    def exchange_forward(self, pos_owned: torch.Tensor) -> torch.Tensor:
+        """positions of owned atoms [n_owned,3] -> ghost positions [n_ghost,3] (wrap applied)."""
+        seg = {"right": pos_owned.index_select(0, self.send_right_idx), "left": pos_owned.index_select(0, self.send_left_idx)}
+        n_in = {"from_left": self.n_ghost_left, "from_right": self.n_ghost_right}
+        ops, bufs = [], []
+        for peer, sends, recvs in self._peers():
+            sbuf = torch.cat([seg[s] for s in sends], 0).contiguous()
+            rbuf = torch.empty(sum(n_in[r] for r in recvs), 3, dtype=pos_owned.dtype, device=pos_owned.device)
+            ops += [dist.P2POp(dist.isend, sbuf, peer), dist.P2POp(dist.irecv, rbuf, peer)]
+            bufs.append((recvs, rbuf, sbuf))
+        for w in dist.batch_isend_irecv(ops):
+            w.wait()
+        got = {}
+        for recvs, rbuf, _ in bufs:
+            o = 0
+            for r in recvs:
+                got[r] = rbuf[o : o + n_in[r]]
+                o += n_in[r]
+        gl, gr = got["from_left"].clone(), got["from_right"].clone()
+        gl[:, 0] += self.shift_left
+        gr[:, 0] += self.shift_right
+        return torch.cat([gl, gr], 0)
+
+    def exchange_reverse(self, g_ghost: torch.Tensor, g_owned: torch.Tensor) -> torch.Tensor:
+        """add the gradient accumulated on ghosts [n_ghost,3] onto the owners; returns g_owned."""
+        seg = {"from_left": g_ghost[: self.n_ghost_left], "from_right": g_ghost[self.n_ghost_left :]}
+        n_out = {"right": int(self.send_right_idx.shape[0]), "left": int(self.send_left_idx.shape[0])}
+        ops, bufs = [], []
+        for peer, sends, recvs in self._peers():
+            # mirror of the forward plan: what I received from `peer` goes back to it
+            sbuf = torch.cat([seg[r] for r in recvs], 0).contiguous()
+            rbuf = torch.empty(sum(n_out[s] for s in sends), 3, dtype=g_ghost.dtype, device=g_ghost.device)
+            ops += [dist.P2POp(dist.isend, sbuf, peer), dist.P2POp(dist.irecv, rbuf, peer)]
+            bufs.append((sends, rbuf, sbuf))
+        for w in dist.batch_isend_irecv(ops):
+            w.wait()
+        idx = {"right": self.send_right_idx, "left": self.send_left_idx}
+        for sends, rbuf, _ in bufs:
+            o = 0
+            for s in sends:
+                g_owned.index_add_(0, idx[s], rbuf[o : o + n_out[s]])
+                o += n_out[s]
+        return g_owned
+
+    def halo_bytes_per_step(self, itemsize: int) -> int:
+        n = int(self.send_right_idx.shape[0]) + int(self.send_left_idx.shape[0]) + self.n_ghost
+        return n * 3 * itemsize
+
+
+class DistributedAllegro:
+    """Energy + forces of a slab-decomposed frame.  ``energy_model(data) -> data`` must write
+    ``atomic_energy`` for the local atoms (owned first) and be differentiable w.r.t. ``pos``
+    (FusedAllegroEnergy on the GPU; any stand-in in the CPU tests)."""
+
+    def __init__(self, energy_model: Callable[[D.Type], D.Type], dec: SlabDecomposition):
+        self.model, self.dec = energy_model, dec
+
+    def __call__(self, pos_owned: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+        """-> (total energy [all ranks], forces on owned atoms [n_owned,3], owned atomic energies)."""
+        dec = self.dec
+        ghosts = dec.exchange_forward(pos_owned.detach())
+        pos_local = torch.cat([pos_owned.detach(), ghosts], 0).requires_grad_(True)
+        data = {
+            D.POSITIONS_KEY: pos_local,
+            D.ATOM_TYPE_KEY: dec.types_local,
+            D.EDGE_INDEX_KEY: dec.edge_index,
+            D.EDGE_CELL_SHIFT_KEY: dec.edge_cell_shift,
+            D.CELL_KEY: dec.cell,
+        }
+        with torch.enable_grad():
+            out = self.model(data)
+            e_atoms = out[D.PER_ATOM_ENERGY_KEY][: dec.n_owned]
+            e_local = e_atoms.sum()
+            (g,) = torch.autograd.grad(e_local, pos_local)
+        g_owned = g[: dec.n_owned].clone()
+        dec.exchange_reverse(g[dec.n_owned :].contiguous(), g_owned)
+        e_tot = e_local.detach().double().clone().reshape(1)
+        dist.all_reduce(e_tot)
+        return e_tot, -g_owned, e_atoms.detach()

@@ -40,34 +40,35 @@ CONFIGS: Dict[str, Dict] = {
 }
 
 
-def make_positions(name: str, scale: Optional[int] = None, seed: int = 1234):
+def make_positions(name: str, scale=None, seed: int = 1234):
     """-> pos [N,3] fp64, cell [3,3] fp64, atom_types [N] int64."""
     gen = torch.Generator().manual_seed(seed)
+
+    def _reps(default):
+        if scale is None:
+            return (default,) * 3
+        return tuple(scale) if isinstance(scale, (tuple, list)) else (scale,) * 3
+
     if name == "c1":
-        n = scale or 2
-        pos, cell = _lattice(_DIAMOND, 5.431, (n, n, n), 0.05, gen)
+        pos, cell = _lattice(_DIAMOND, 5.431, _reps(2), 0.05, gen)
         types = torch.zeros(pos.shape[0], dtype=torch.long)
     elif name == "c2":
-        n = scale or 14
-        pos, cell = _lattice(_FCC, 3.615, (n, n, n), 0.05, gen)
+        pos, cell = _lattice(_FCC, 3.615, _reps(14), 0.05, gen)
         types = torch.zeros(pos.shape[0], dtype=torch.long)
     elif name == "c5":
-        n = scale or 14
-        pos, cell = _lattice(_FCC, 3.6, (n, n, n), 0.05, gen)
+        pos, cell = _lattice(_FCC, 3.6, _reps(14), 0.05, gen)
         types = torch.randint(0, 5, (pos.shape[0],), generator=gen)
     elif name == "c3":
         # jittered simple-cubic lattice at number density 0.050 A^-3 (spacing 2.714 A);
         # jitter 0.3 A keeps min distance > 1.8 A.  Li:P:S = 3:1:4.
-        n_side = scale or 46  # 46^3 = 97 336 ~ 100k
-        a = (1.0 / 0.050) ** (1.0 / 3.0)
-        pos, cell = _lattice(torch.zeros(1, 3, dtype=torch.float64), a, (n_side,) * 3, 0.3, gen)
+        a = (1.0 / 0.050) ** (1.0 / 3.0)  # 46^3 = 97 336 ~ 100k
+        pos, cell = _lattice(torch.zeros(1, 3, dtype=torch.float64), a, _reps(46), 0.3, gen)
         r = torch.rand(pos.shape[0], generator=gen)
         types = torch.where(r < 3 / 8, 0, torch.where(r < 4 / 8, 1, 2)).long()
     elif name == "c4":
         # O on a jittered cubic lattice at 0.0334 A^-3 + 2 H at 0.96 A in random directions
-        n_side = scale or 69  # 69^3 = 328 509 O -> 985 527 atoms
-        a = (1.0 / 0.0334) ** (1.0 / 3.0)
-        o, cell = _lattice(torch.zeros(1, 3, dtype=torch.float64), a, (n_side,) * 3, 0.2, gen)
+        a = (1.0 / 0.0334) ** (1.0 / 3.0)  # 69^3 = 328 509 O -> 985 527 atoms
+        o, cell = _lattice(torch.zeros(1, 3, dtype=torch.float64), a, _reps(69), 0.2, gen)
         d1 = torch.randn(o.shape, generator=gen, dtype=torch.float64)
         d1 = d1 / d1.norm(dim=-1, keepdim=True)
         d2 = torch.randn(o.shape, generator=gen, dtype=torch.float64)
@@ -83,7 +84,7 @@ def make_positions(name: str, scale: Optional[int] = None, seed: int = 1234):
     return pos, cell, types
 
 
-def make_system(name: str, scale: Optional[int] = None, seed: int = 1234, device="cpu") -> D.Type:
+def make_system(name: str, scale=None, seed: int = 1234, device="cpu") -> D.Type:
     cfg = CONFIGS[name]
     pos, cell, types = make_positions(name, scale, seed)
     pos, cell, types = pos.to(device), cell.to(device), types.to(device)

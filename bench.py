@@ -121,8 +121,6 @@ def run_ours(args, rank: int, world: int):
     from allegro_b200 import data as D
 
     if world > 1:
-        from allegro_b200 import halo  # noqa: F401  (spatial decomposition; see bench_multi)
-
         return run_ours_multi(args, rank, world)
     dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", 0)))
     torch.cuda.set_device(dev)
@@ -230,7 +228,100 @@ def run_ours(args, rank: int, world: int):
 
 
 def run_ours_multi(args, rank, world):
-    raise NotImplementedError("multi-GPU bench leg not wired yet")
+    """N>1: weak scaling by spatial domain decomposition.  The c2 crystal is
+    replicated `world` times along x; each rank owns one 14x14x14-cell slab (fixed per-GPU
+    work) and exchanges a single-r_max halo with its two neighbours over NCCL every step:
+    positions forward, ghost gradients back, one scalar all-reduce."""
+    import torch.distributed as dist
+
+    from allegro_b200 import _lib, systems
+    from allegro_b200 import data as D
+    from allegro_b200.halo import DistributedAllegro, SlabDecomposition
+    from allegro_b200.model import AllegroModel
+
+    local = int(os.environ.get("LOCAL_RANK", rank))
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    cfg = args.config
+    dtype = args.dtype or systems.CONFIGS[cfg]["dtype"]
+    base = {"c1": 2, "c2": 14, "c5": 14, "c3": 46, "c4": 69}[cfg]
+    reps = (base * world, base, base)
+    pos, cell, types = systems.make_positions(cfg, reps)
+    n_global = pos.shape[0]
+    dec = SlabDecomposition(pos, cell, types, systems.CONFIGS[cfg]["r_max"], rank, world)
+    n_edges = dec.edge_index.shape[1]
+    kw = systems.model_kwargs(cfg, n_edges / dec.n_owned, dtype)
+    model = AllegroModel(**kw).to(dev).model  # energy model; forces via the halo-aware runner
+    pos_owned = dec.local_positions_from_global(pos)[: dec.n_owned].to(dev)
+    dec.to(dev)
+    runner = DistributedAllegro(model, dec)
+    K, W = args.steps, args.warmup
+    for _ in range(W):
+        e, f, _ = runner(pos_owned)
+    sampler = ClockSampler(dev.index or 0)
+    if rank == 0:
+        sampler.start()
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    _lib.PROF.reset()
+    dist.barrier()
+    torch.cuda.synchronize()
+    t0.record()
+    for _ in range(K):
+        e, f, _ = runner(pos_owned)
+    t1.record()
+    torch.cuda.synchronize()
+    dist.barrier()
+    ms_t = torch.tensor([t0.elapsed_time(t1) / K], device=dev, dtype=torch.float64)
+    dist.all_reduce(ms_t, op=dist.ReduceOp.MAX)
+    ms = float(ms_t)
+    launches = _lib.PROF.launches
+    # end to end: owned positions from pinned host memory, forces + energy back to the host
+    pos_host = pos_owned.cpu().pin_memory()
+    f_host = torch.empty(dec.n_owned, 3, dtype=f.dtype).pin_memory()
+    e_host = torch.empty(1, dtype=e.dtype).pin_memory()
+
+    def step_e2e():
+        p = pos_host.to(dev, non_blocking=True)
+        ee, ff, _ = runner(p)
+        f_host.copy_(ff, non_blocking=True)
+        e_host.copy_(ee, non_blocking=True)
+
+    step_e2e()
+    dist.barrier()
+    torch.cuda.synchronize()
+    t0.record()
+    for _ in range(K):
+        step_e2e()
+    t1.record()
+    torch.cuda.synchronize()
+    dist.barrier()
+    ms_e = torch.tensor([t0.elapsed_time(t1) / K], device=dev, dtype=torch.float64)
+    dist.all_reduce(ms_e, op=dist.ReduceOp.MAX)
+    ms_e2e = float(ms_e)
+    ghosts = torch.tensor([dec.n_ghost], device=dev)
+    dist.all_reduce(ghosts, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        clocks = sampler.stop()
+        res = {
+            "metric": METRIC, "value": n_global * 1e3 / ms, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": {"float64": "f64", "float32": "f32", "bfloat16": "bf16"}[dtype], "data": "synthetic",
+            "config": {"workload": f"{cfg} replicated x{world} along x: {n_global} atoms, {dec.n_owned} owned + <= {int(ghosts)} ghost atoms and "
+                                   f"{n_edges} edges per GPU, l_max={kw['l_max']}, n_layers={kw['num_layers']}, S={kw['num_scalar_features']}, "
+                                   f"U={kw['num_tensor_features']}, r_max={kw['r_max']}",
+                       "global_atoms": n_global, "parallelism": f"spatial slab decomposition x{world}, NCCL halo (positions fwd, gradients rev) "
+                       "+ 1 scalar all-reduce per step", "timing": "CUDA events, barrier + synchronize both sides, max over ranks; per-step working set >> L2",
+                       "halo_bytes_per_step_per_gpu": dec.halo_bytes_per_step(8)},
+            "ns_per_day_at_1fs": 1e3 / ms * 0.0864,
+            "clocks": clocks,
+            "e2e": {"value": n_global * 1e3 / ms_e2e, "unit": UNIT, "ms_per_step": ms_e2e,
+                    "h2d_bytes_per_step": pos_host.numel() * 8 * world, "d2h_bytes_per_step": (f_host.numel() * f_host.element_size() + 8) * world},
+            "gpu_launches": launches,
+        }
+        print(json.dumps(res))
+    dist.destroy_process_group()
 
 
 # --------------------------------------------------------------------------------------
