@@ -29,12 +29,15 @@ _SIGNATURES = {
     "ab2_version": ([], C.c_int),
     "ab2_device_ok": ([], C.c_int),
     "ab2_last_error": ([], C.c_char_p),
+    "ab2_set_option": ([C.c_char_p, _i32], C.c_int),
     "ab2_op_scatter_env": ([_i32, _i64, _i64, _dbl, _vp, _vp, _vp, _vp], C.c_int),
     "ab2_op_contract": ([_i32, _i32, _i64, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp], C.c_int),
     "ab2_op_gather_rows": ([_i32, _i64, _i64, _dbl, _vp, _vp, _vp, _vp], C.c_int),
     "ab2_sh_fwd": ([_i32, _i32, _i64, _vp, _vp, _vp], C.c_int),
     "ab2_sh_bwd": ([_i32, _i32, _i64, _vp, _vp, _vp, _i32, _vp], C.c_int),
-    "ab2_linear": ([_i32, _i64, _i32, _i32, _i32, _vp, _vp, _vp, _i32, _vp, _i32, _vp, _vp, _vp, _vp, _i32, _vp, _i64, _vp], C.c_int),
+    "ab2_linear": ([_i32, _i64, _i32, _i32, _i32, _vp, _vp, _vp, _i32, _vp, _vp, _i32, _vp, _vp, _vp, _vp, _i32, _vp, _i64, _vp], C.c_int),
+    "ab2_linear_packed_bytes": ([_i32, _i32, _i32], C.c_int64),
+    "ab2_linear_pack": ([_i32, _i32, _i32, _vp, _vp, _vp], C.c_int),
     "ab2_env_sum": ([_i32, _i32, _i64, _i32, _vp, _vp, _vp, _i64, _dbl, _vp, _vp], C.c_int),
     "ab2_env_bwd": ([_i32, _i32, _i64, _i32, _vp, _vp, _vp, _i64, _vp, _dbl, _vp, _i64, _vp, _vp], C.c_int),
     "ab2_tp_fwd": ([_i32, _i32, _i64, _i64, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _i64, _vp, _vp], C.c_int),
@@ -125,6 +128,10 @@ class _timed:
         return False
 
 
+def set_option(key: str, value: int):
+    _check(load().ab2_set_option(key.encode(), int(value)))
+
+
 def _check(rc: int):
     if rc != 0:
         msg = load().ab2_last_error()
@@ -185,8 +192,10 @@ def linear(
     act: int = ACT_NONE,
     epi: int = EPI_NONE,
     aux: Optional[torch.Tensor] = None,
+    W_packed: Optional[torch.Tensor] = None,
 ):
-    """Out (+)= epi(act(cat(a_segs, -1)) @ W); a_segs / o_segs are 2-D row-strided views."""
+    """Out (+)= epi(act(cat(a_segs, -1)) @ W); a_segs / o_segs are 2-D row-strided views.
+    ``W_packed`` (from ``linear_pack``) enables the tcgen05 tensor-core path."""
     M = a_segs[0].shape[0]
     K, N = W.shape
     dt = W.dtype
@@ -216,10 +225,21 @@ def linear(
     with _timed("linear", 1):
         _check(
             load().ab2_linear(
-                DTYPE_ENUM[dt], M, K, N, na, a_ptr, a_ld, a_w, act, _ptr(_contig(W, "W")), no, o_ptr, o_ld, o_w, o_acc, epi,
+                DTYPE_ENUM[dt], M, K, N, na, a_ptr, a_ld, a_w, act, _ptr(_contig(W, "W")), _ptr(W_packed), no, o_ptr, o_ld, o_w, o_acc, epi,
                 _ptr(aux), aux_ld, _stream(),
             )
         )
+
+
+def linear_pack(W: torch.Tensor) -> Optional[torch.Tensor]:
+    """Packed bf16 (hi, lo) image of W[K][N] for the tensor-core path, or None if not eligible."""
+    K, N = W.shape
+    nbytes = int(load().ab2_linear_packed_bytes(DTYPE_ENUM[W.dtype], K, N))
+    if nbytes == 0:
+        return None
+    packed = torch.empty(nbytes, dtype=torch.uint8, device=W.device)
+    _check(load().ab2_linear_pack(DTYPE_ENUM[W.dtype], K, N, _ptr(_contig(W, "W")), _ptr(packed), _stream()))
+    return packed
 
 
 def env_sum(dtype, lmax: int, N: int, U: int, row_ptr, Y, w: torch.Tensor, sf: float, out: Optional[torch.Tensor] = None):

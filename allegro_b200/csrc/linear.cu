@@ -129,10 +129,14 @@ __global__ void __launch_bounds__(256) linear_kernel(const LinParams p) {
     }
 }
 
+int ab2_linear_tc_try(int dtype, int64_t M, int K, int N, int n_a, const void* const* a_ptr, const int64_t* a_ld,
+                      const int32_t* a_width, int act, const void* Wpacked, int n_o, void* const* o_ptr, const int64_t* o_ld,
+                      const int32_t* o_width, const int32_t* o_accum, int epi, const void* aux, int64_t aux_ld, cudaStream_t st);
+
 extern "C" int ab2_linear(int dtype, int64_t M, int K, int N, int n_a, const void* const* a_ptr, const int64_t* a_ld,
-                          const int32_t* a_width, int act, const void* W, int n_o, void* const* o_ptr, const int64_t* o_ld,
-                          const int32_t* o_width, const int32_t* o_accum, int epi, const void* aux, int64_t aux_ld,
-                          void* stream) {
+                          const int32_t* a_width, int act, const void* W, const void* Wpacked, int n_o, void* const* o_ptr,
+                          const int64_t* o_ld, const int32_t* o_width, const int32_t* o_accum, int epi, const void* aux,
+                          int64_t aux_ld, void* stream) {
     if (M == 0) return 0;
     AB2_CHECK_ARG(n_a >= 1 && n_a <= AB2_MAX_SEG && n_o >= 1 && n_o <= AB2_MAX_SEG, "segment count");
     AB2_CHECK_ARG(K > 0 && N > 0 && W, "shape");
@@ -152,8 +156,13 @@ extern "C" int ab2_linear(int dtype, int64_t M, int K, int N, int n_a, const voi
     }
     AB2_CHECK_ARG(ks == K, "A segment widths must sum to K");
     AB2_CHECK_ARG(ns == N, "output segment widths must sum to N");
-    dim3 grid(ab2_blocks(M, 64), (unsigned)((N + 63) / 64));
     cudaStream_t st = (cudaStream_t)stream;
+    if (Wpacked && ab2_linear_tc_try(dtype, M, K, N, n_a, a_ptr, a_ld, a_width, act, Wpacked, n_o, o_ptr, o_ld, o_width, o_accum, epi,
+                                     aux, aux_ld, st) == 0) {
+        AB2_CUDA_LAUNCH_CHECK();
+        return 0;
+    }
+    dim3 grid(ab2_blocks(M, 64), (unsigned)((N + 63) / 64));
     AB2_DISPATCH_DTYPE(dtype, linear_kernel<TAct, TAcc><<<grid, 256, 0, st>>>(p));
     AB2_CUDA_LAUNCH_CHECK();
     return 0;

@@ -1,0 +1,456 @@
+// tcgen05 (5th-gen tensor core) path of the fused linear layer -- same contract as linear.cu:
+//
+//   Out[M][N] (+)= epi( act([A_0 | A_1 | ...])[M][K] @ W[K][N] )
+//
+// M = number of edges (10^5..10^8), K,N <= 256: a tall-skinny GEMM that is HBM-bound once the
+// MACs run on tensor cores (12-25 KFLOP per ~0.5-1 KB row).  Structure (one persistent CTA per
+// SM, 9 warps, warp-specialised, all hand-written PTX):
+//
+//   warps 0-3  producers : coalesced global loads of the concatenated A row segments
+//                          (8 rows x 128 B per warp instruction), optional SiLU, split of the fp32
+//                          value into bf16 hi + bf16 lo, 16-byte st.shared into a ring of
+//                          128-row x 32-k stages in the UMMA canonical K-major (no-swizzle,
+//                          8x16B core matrix) layout; fence.proxy.async + mbarrier arrive.
+//   warp  4    MMA       : one elected lane issues tcgen05.mma.cta_group::1.kind::f16
+//                          (M=128, N<=256, K=16) from shared-memory descriptors into one of two
+//                          TMEM accumulators; fp32 storage uses the 3-term split
+//                          A_hi W_hi + A_lo W_hi + A_hi W_lo (~2^-16 relative, fp32 accumulate);
+//                          tcgen05.commit releases ring slots / publishes the accumulator.
+//   warps 5-8  epilogue  : tcgen05.ld 32x32b (lane = row), silu' / accumulate epilogue, split
+//                          into the output column segments, vectorised global stores.
+//
+// W (all of it: <= 128 KB as bf16 hi+lo) is staged once per CTA from a pre-packed image
+// (ab2_linear_pack) and stays resident in shared memory.
+#include "common.cuh"
+
+extern int g_ab2_opt_linear_tc;
+
+namespace {
+
+constexpr int BM = 128;       // rows per tile = UMMA M
+constexpr int KC = 32;        // k per ring stage
+constexpr int NSTAGE = 6;
+constexpr int STAGE_HALF = BM * KC * 2;  // bytes of one bf16 [128][32] operand image (8 KB)
+constexpr int NTHREADS = 288;
+constexpr int MAX_W_BYTES = 128 * 1024;
+
+struct TcSeg {
+    const void* ptr;
+    int64_t ld;
+    int width;
+    int accum;
+};
+
+struct TcParams {
+    int64_t M;
+    int K, N, Npad;
+    int n_a;
+    TcSeg a[AB2_MAX_SEG];
+    int act;
+    const void* Wpacked;  // [hi image | lo image], each Npad*K bf16 in canonical layout
+    int n_o;
+    TcSeg o[AB2_MAX_SEG];
+    int epi;
+    const void* aux;
+    int64_t aux_ld;
+    int64_t num_tiles;
+};
+
+// ---- PTX wrappers ---------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra WAIT_DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "WAIT_DONE:\n\t"
+        "}" ::"r"(bar),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// D[tmem] (+)= A[smem desc] * B[smem desc], bf16 inputs, fp32 accumulate
+__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(d_tmem),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// shared-memory matrix descriptor: K-major, SWIZZLE_NONE, 8x16B core matrices.
+// canonical layout (16-byte units) ((8,n),2):((1,SBO),LBO): LBO = byte distance between core
+// matrices adjacent in K, SBO = between 8-row groups.
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+    d |= (uint64_t)1 << 46;  // descriptor version (Blackwell)
+    return d;                // base_offset = 0, lbo_mode = 0, layout_type = 0 (SWIZZLE_NONE)
+}
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
+    __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&v);
+}
+
+// load 8 consecutive concat columns [k, k+8) of row m (segment widths are multiples of 8)
+template <typename TSrc>
+__device__ __forceinline__ void load8(const TcParams& p, int64_t m, int k, float (&v)[8]) {
+#pragma unroll
+    for (int s = 0; s < AB2_MAX_SEG; ++s) {
+        if (s < p.n_a) {
+            if (k < p.a[s].width) {
+                if constexpr (sizeof(TSrc) == 4) {
+                    const float4* src = reinterpret_cast<const float4*>((const float*)p.a[s].ptr + m * p.a[s].ld + k);
+                    const float4 x = __ldg(src), y = __ldg(src + 1);
+                    v[0] = x.x; v[1] = x.y; v[2] = x.z; v[3] = x.w; v[4] = y.x; v[5] = y.y; v[6] = y.z; v[7] = y.w;
+                } else {
+                    const uint4 x = __ldg(reinterpret_cast<const uint4*>((const bf16*)p.a[s].ptr + m * p.a[s].ld + k));
+                    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&x);
+#pragma unroll
+                    for (int t = 0; t < 4; ++t) {
+                        const float2 f = __bfloat1622float2(h[t]);
+                        v[2 * t] = f.x; v[2 * t + 1] = f.y;
+                    }
+                }
+                return;
+            }
+            k -= p.a[s].width;
+        }
+    }
+#pragma unroll
+    for (int t = 0; t < 8; ++t) v[t] = 0.f;
+}
+
+template <typename TSrc, bool SPLIT>
+__global__ void __launch_bounds__(NTHREADS, 1) linear_tc_kernel(const TcParams p) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int w_half = p.Npad * p.K * 2;                     // bytes of one W image
+    const int w_bytes = SPLIT ? 2 * w_half : w_half;
+    uint8_t* sW = smem;
+    uint8_t* sA = smem + ((w_bytes + 127) & ~127);
+    const int stage_bytes = SPLIT ? 2 * STAGE_HALF : STAGE_HALF;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sA + NSTAGE * stage_bytes);
+    // bars: full[NSTAGE], empty[NSTAGE], tmem_full[2], tmem_empty[2]; then the TMEM base word
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NSTAGE + 4);
+    const uint32_t bar0 = smem_u32(bars);
+    auto full_bar = [&](int s) { return bar0 + 8u * s; };
+    auto empty_bar = [&](int s) { return bar0 + 8u * (NSTAGE + s); };
+    auto tfull_bar = [&](int a) { return bar0 + 8u * (2 * NSTAGE + a); };
+    auto tempty_bar = [&](int a) { return bar0 + 8u * (2 * NSTAGE + 2 + a); };
+
+    // ---- one-time setup ----
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < NSTAGE; ++s) {
+            mbar_init(full_bar(s), 128);
+            mbar_init(empty_bar(s), 1);
+        }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(tfull_bar(a), 1);
+            mbar_init(tempty_bar(a), 128);
+        }
+        fence_barrier_init();
+    }
+    if (warp == 4) tmem_alloc(smem_u32(tmem_slot), 512);
+    // stage W (pre-packed canonical image) with plain 16-byte copies
+    {
+        const uint4* src = reinterpret_cast<const uint4*>(p.Wpacked);
+        uint4* dst = reinterpret_cast<uint4*>(sW);
+        for (int e = threadIdx.x; e < w_bytes / 16; e += NTHREADS) dst[e] = __ldg(src + e);
+    }
+    fence_proxy_async();  // W was written through the generic proxy, tcgen05.mma reads via the async proxy
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int nkb = (p.K + KC - 1) / KC;
+    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.Npad >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+
+    if (warp < 4) {
+        // =============================== producers ===============================
+        const int r8 = lane & 7, kc = lane >> 3;
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int64_t tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+            const int64_t m0 = tile * BM;
+            for (int kb = 0; kb < nkb; ++kb) {
+                mbar_wait(empty_bar(stage), phase ^ 1);
+                uint8_t* st_hi = sA + stage * stage_bytes;
+                const int k = kb * KC + kc * 8;
+                float v[4][8];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int64_t m = m0 + (warp * 4 + i) * 8 + r8;
+                    if (m < p.M && k < p.K) {
+                        load8<TSrc>(p, m, k, v[i]);
+                    } else {
+#pragma unroll
+                        for (int t = 0; t < 8; ++t) v[i][t] = 0.f;
+                    }
+                }
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    if (p.act == AB2_ACT_SILU) {
+#pragma unroll
+                        for (int t = 0; t < 8; ++t) v[i][t] = silu_f(v[i][t]);
+                    }
+                    const int g = warp * 4 + i;
+                    const uint32_t off = g * (KC / 8) * 128 + kc * 128 + r8 * 16;
+                    uint32_t hi[4];
+                    float lo[8];
+#pragma unroll
+                    for (int t = 0; t < 4; ++t) {
+                        const __nv_bfloat16 h0 = __float2bfloat16_rn(v[i][2 * t]), h1 = __float2bfloat16_rn(v[i][2 * t + 1]);
+                        lo[2 * t] = v[i][2 * t] - __bfloat162float(h0);
+                        lo[2 * t + 1] = v[i][2 * t + 1] - __bfloat162float(h1);
+                        __nv_bfloat162 hh;
+                        hh.x = h0; hh.y = h1;
+                        hi[t] = *reinterpret_cast<uint32_t*>(&hh);
+                    }
+                    *reinterpret_cast<uint4*>(st_hi + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                    if constexpr (SPLIT) {
+                        *reinterpret_cast<uint4*>(st_hi + STAGE_HALF + off) =
+                            make_uint4(pack_bf16x2(lo[0], lo[1]), pack_bf16x2(lo[2], lo[3]), pack_bf16x2(lo[4], lo[5]), pack_bf16x2(lo[6], lo[7]));
+                    }
+                }
+                fence_proxy_async();
+                mbar_arrive(full_bar(stage));
+                if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp == 4) {
+        // =============================== MMA issuer ===============================
+        int stage = 0;
+        uint32_t phase = 0;
+        int64_t it = 0;
+        const uint32_t sW_u = smem_u32(sW);
+        const uint32_t w_sbo = (uint32_t)(p.K / 8) * 128;  // bytes between 8-column (n) groups of W
+        for (int64_t tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+            const int a = (int)(it & 1);
+            const uint32_t aphase = (uint32_t)((it >> 1) & 1);
+            mbar_wait(tempty_bar(a), aphase ^ 1);
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + (uint32_t)(a * 256);
+            for (int kb = 0; kb < nkb; ++kb) {
+                mbar_wait(full_bar(stage), phase);
+                tc_fence_after();
+                if (lane == 0) {
+                    const uint32_t a_hi = smem_u32(sA + stage * stage_bytes);
+                    const int ksteps = min(2, (p.K - kb * KC) / 16);
+                    for (int ks = 0; ks < ksteps; ++ks) {
+                        const uint64_t da_hi = make_desc(a_hi + ks * 256, 128, (KC / 8) * 128);
+                        const uint32_t wk = sW_u + (uint32_t)(kb * (KC / 8) + ks * 2) * 128;
+                        const uint64_t db_hi = make_desc(wk, 128, w_sbo);
+                        umma_bf16(d_tmem, da_hi, db_hi, idesc, (kb | ks) ? 1u : 0u);
+                        if constexpr (SPLIT) {
+                            const uint64_t da_lo = make_desc(a_hi + STAGE_HALF + ks * 256, 128, (KC / 8) * 128);
+                            const uint64_t db_lo = make_desc(wk + w_half, 128, w_sbo);
+                            umma_bf16(d_tmem, da_lo, db_hi, idesc, 1u);
+                            umma_bf16(d_tmem, da_hi, db_lo, idesc, 1u);
+                        }
+                    }
+                    umma_commit(empty_bar(stage));                  // ring slot free once these MMAs retire
+                    if (kb == nkb - 1) umma_commit(tfull_bar(a));   // accumulator complete
+                }
+                __syncwarp();
+                if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else {
+        // =============================== epilogue ===============================
+        const int q = warp & 3;  // TMEM lane quadrant this warp may access
+        int64_t it = 0;
+        for (int64_t tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+            const int a = (int)(it & 1);
+            const uint32_t aphase = (uint32_t)((it >> 1) & 1);
+            mbar_wait(tfull_bar(a), aphase);
+            tc_fence_after();
+            const int64_t m = tile * BM + q * 32 + lane;
+            const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * 256);
+            for (int c0 = 0; c0 < p.Npad; c0 += 16) {
+                uint32_t r[16];
+                tmem_ld16(t_row + c0, r);
+                if (m < p.M) {
+                    float v[16];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
+                    if (p.epi == AB2_EPI_MUL_DSILU) {
+                        const TSrc* ax = (const TSrc*)p.aux + m * p.aux_ld + c0;
+#pragma unroll
+                        for (int j = 0; j < 16; ++j)
+                            if (c0 + j < p.N) v[j] *= dsilu_f(to_acc<float>(ax[j]));
+                    }
+                    // scatter the 16 columns into the output segments
+                    int seg_lo = 0;
+#pragma unroll
+                    for (int s = 0; s < AB2_MAX_SEG; ++s) {
+                        if (s < p.n_o) {
+                            const int seg_hi = seg_lo + p.o[s].width;
+                            const int lo = max(seg_lo, c0), hi = min(seg_hi, min(c0 + 16, p.N));
+                            if (lo < hi) {
+                                TSrc* dst = (TSrc*)p.o[s].ptr + m * p.o[s].ld + (lo - seg_lo);
+                                const bool vec = (sizeof(TSrc) == 4) && (hi - lo == 16) && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0);
+                                if (vec) {
+                                    float4* d4 = reinterpret_cast<float4*>(dst);
+#pragma unroll
+                                    for (int t = 0; t < 4; ++t) {
+                                        float4 o4 = make_float4(v[4 * t], v[4 * t + 1], v[4 * t + 2], v[4 * t + 3]);
+                                        if (p.o[s].accum) {
+                                            const float4 old = d4[t];
+                                            o4.x += old.x; o4.y += old.y; o4.z += old.z; o4.w += old.w;
+                                        }
+                                        d4[t] = o4;
+                                    }
+                                } else {
+#pragma unroll
+                                    for (int j = 0; j < 16; ++j) {
+                                        const int n = c0 + j;
+                                        if (n >= lo && n < hi) {
+                                            float x = v[j];
+                                            if (p.o[s].accum) x += to_acc<float>(dst[n - lo]);
+                                            dst[n - lo] = from_acc<TSrc>(x);
+                                        }
+                                    }
+                                }
+                            }
+                            seg_lo = seg_hi;
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(tempty_bar(a));
+        }
+    }
+    // ---- teardown ----
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 4) tmem_dealloc(tmem_base, 512);
+}
+
+// W[K][N] (row-major TSrc) -> canonical K-major no-swizzle bf16 images (hi, lo), Npad rows:
+//   byte offset of (n, k) = ((n/8)*(K/8) + k/8)*128 + (n%8)*16 + (k%8)*2
+template <typename TSrc>
+__global__ void pack_w_kernel(int K, int N, int Npad, const TSrc* __restrict__ W, bf16* __restrict__ out) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= Npad * K) return;
+    const int n = e / K, k = e % K;
+    const float w = (n < N) ? to_acc<float>(W[(int64_t)k * N + n]) : 0.f;
+    const bf16 h = __float2bfloat16_rn(w);
+    const bf16 l = __float2bfloat16_rn(w - __bfloat162float(h));
+    const int64_t off = ((int64_t)(n / 8) * (K / 8) + k / 8) * 64 + (n % 8) * 8 + (k % 8);
+    out[off] = h;
+    out[(int64_t)Npad * K + off] = l;
+}
+
+}  // namespace
+
+static int tc_npad(int N) { return (N + 15) / 16 * 16; }
+
+extern "C" int64_t ab2_linear_packed_bytes(int dtype, int K, int N) {
+    if (dtype == AB2_F64 || K % 16 != 0 || K <= 0 || N <= 0) return 0;
+    const int Npad = tc_npad(N);
+    if (Npad > 256) return 0;
+    const int64_t bytes = (int64_t)Npad * K * 2 * 2;  // hi + lo images
+    const int64_t used = (dtype == AB2_F32) ? bytes : bytes / 2;
+    if (used > MAX_W_BYTES) return 0;
+    return bytes;
+}
+
+extern "C" int ab2_linear_pack(int dtype, int K, int N, const void* W, void* packed, void* stream) {
+    AB2_CHECK_ARG(ab2_linear_packed_bytes(dtype, K, N) > 0, "shape not supported by the tensor-core path");
+    AB2_CHECK_ARG(W && packed, "null pointer");
+    const int Npad = tc_npad(N);
+    cudaStream_t st = (cudaStream_t)stream;
+    const int total = Npad * K;
+    if (dtype == AB2_F32)
+        pack_w_kernel<float><<<(total + 255) / 256, 256, 0, st>>>(K, N, Npad, (const float*)W, (bf16*)packed);
+    else
+        pack_w_kernel<bf16><<<(total + 255) / 256, 256, 0, st>>>(K, N, Npad, (const bf16*)W, (bf16*)packed);
+    AB2_CUDA_LAUNCH_CHECK();
+    return 0;
+}
+
+// returns 0 if launched, -1 if this call is not eligible (caller falls back to linear.cu)
+int ab2_linear_tc_try(int dtype, int64_t M, int K, int N, int n_a, const void* const* a_ptr, const int64_t* a_ld,
+                      const int32_t* a_width, int act, const void* Wpacked, int n_o, void* const* o_ptr, const int64_t* o_ld,
+                      const int32_t* o_width, const int32_t* o_accum, int epi, const void* aux, int64_t aux_ld, cudaStream_t st) {
+    if (!g_ab2_opt_linear_tc || !Wpacked || dtype == AB2_F64) return -1;
+    if (ab2_linear_packed_bytes(dtype, K, N) == 0) return -1;
+    const int esz = (dtype == AB2_F32) ? 4 : 2;
+    for (int s = 0; s < n_a; ++s) {
+        if (a_width[s] % 8 != 0) return -1;
+        if ((reinterpret_cast<uintptr_t>(a_ptr[s]) % 16) != 0 || (a_ld[s] * esz) % 16 != 0) return -1;
+    }
+    static int num_sms = 0;
+    static int max_smem = 0;
+    if (num_sms == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+        cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    }
+    TcParams p;
+    memset(&p, 0, sizeof(p));
+    p.M = M; p.K = K; p.N = N; p.Npad = tc_npad(N); p.n_a = n_a; p.act = act; p.Wpacked = Wpacked; p.n_o = n_o;
+    p.epi = epi; p.aux = aux; p.aux_ld = aux_ld; p.num_tiles = (M + BM - 1) / BM;
+    for (int s = 0; s < n_a; ++s) { p.a[s].ptr = a_ptr[s]; p.a[s].ld = a_ld[s]; p.a[s].width = a_width[s]; }
+    for (int s = 0; s < n_o; ++s) { p.o[s].ptr = o_ptr[s]; p.o[s].ld = o_ld[s]; p.o[s].width = o_width[s]; p.o[s].accum = o_accum ? o_accum[s] : 0; }
+    const bool split = dtype == AB2_F32;
+    const int w_bytes = p.Npad * K * 2 * (split ? 2 : 1);
+    const int stage_bytes = STAGE_HALF * (split ? 2 : 1);
+    const size_t smem = ((w_bytes + 127) & ~127) + (size_t)NSTAGE * stage_bytes + (2 * NSTAGE + 4) * 8 + 16;
+    if ((int)smem > max_smem) return -1;
+    const unsigned grid = (unsigned)((p.num_tiles < num_sms) ? p.num_tiles : num_sms);
+    cudaError_t e;
+    if (split) {
+        e = cudaFuncSetAttribute(linear_tc_kernel<float, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) { cudaGetLastError(); return -1; }
+        linear_tc_kernel<float, true><<<grid, NTHREADS, smem, st>>>(p);
+    } else {
+        e = cudaFuncSetAttribute(linear_tc_kernel<bf16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) { cudaGetLastError(); return -1; }
+        linear_tc_kernel<bf16, false><<<grid, NTHREADS, smem, st>>>(p);
+    }
+    return 0;
+}

@@ -11,6 +11,7 @@
 // channel fastest so all global accesses are coalesced).  The l_max=2 register-tiled
 // fast path lives in tp_fast.cu.
 #include "common.cuh"
+#include "tp_fast.cuh"
 
 #define AB2_TP_MAXD 64
 
@@ -95,7 +96,6 @@ __global__ void __launch_bounds__(128) tp_bwd_generic_kernel(int64_t E, int U, i
 extern "C" int ab2_tp_fwd(int dtype, int lmax, int64_t N, int64_t E, int U, int d_in, int d_out, int nnz, const int32_t* tab_ijk,
                           const void* cgw, const int32_t* row_ptr, const int32_t* ctr, const void* gamma, const void* Vin,
                           int implicit_v0, const void* Y, const void* w0, int64_t w0_ld, void* Vout, void* stream) {
-    (void)N; (void)row_ptr;
     if (E == 0) return 0;
     const int D = (lmax + 1) * (lmax + 1);
     AB2_CHECK_ARG(lmax >= 0 && lmax <= AB2_MAX_LMAX, "lmax");
@@ -103,6 +103,12 @@ extern "C" int ab2_tp_fwd(int dtype, int lmax, int64_t N, int64_t E, int U, int 
     AB2_CHECK_ARG(tab_ijk && cgw && ctr && gamma && Vout, "null pointer");
     AB2_CHECK_ARG(implicit_v0 ? (Y && w0 && d_in == D) : (Vin != nullptr), "input features");
     cudaStream_t st = (cudaStream_t)stream;
+    if (g_ab2_opt_tp_fast && row_ptr && ab2_tp_fast_supported(dtype, D, d_in, d_out) && (!implicit_v0 || d_in == D)) {
+        if (ab2_tp_fwd_fast(dtype, N, U, D, d_in, d_out, nnz, tab_ijk, cgw, row_ptr, gamma, Vin, implicit_v0, Y, w0, w0_ld, Vout, st) == 0) {
+            AB2_CUDA_LAUNCH_CHECK();
+            return 0;
+        }
+    }
     AB2_DISPATCH_DTYPE(dtype, tp_fwd_generic_kernel<TAct, TAcc><<<ab2_blocks(E * U, 128), 128, 0, st>>>(
                                   E, U, D, d_in, d_out, nnz, tab_ijk, (const TAcc*)cgw, ctr, (const TAcc*)gamma, (const TAct*)Vin,
                                   implicit_v0, (const TAcc*)Y, (const TAct*)w0, w0_ld, (TAct*)Vout));
@@ -114,7 +120,6 @@ extern "C" int ab2_tp_bwd(int dtype, int lmax, int64_t N, int64_t E, int U, int 
                           const void* cgw, const int32_t* row_ptr, const int32_t* ctr, const void* gamma, const void* Vin,
                           int implicit_v0, const void* Y, const void* w0, int64_t w0_ld, const void* gVout, void* gVin, void* gw0,
                           int64_t gw0_ld, void* gY, void* ggamma, void* stream) {
-    (void)row_ptr;
     if (E == 0) return 0;
     const int D = (lmax + 1) * (lmax + 1);
     AB2_CHECK_ARG(lmax >= 0 && lmax <= AB2_MAX_LMAX, "lmax");
@@ -122,7 +127,14 @@ extern "C" int ab2_tp_bwd(int dtype, int lmax, int64_t N, int64_t E, int U, int 
     AB2_CHECK_ARG(tab_ijk && cgw && ctr && gamma && gVout && ggamma, "null pointer");
     AB2_CHECK_ARG(implicit_v0 ? (Y && w0 && gw0 && gY && d_in == D) : (Vin && gVin), "input features / grads");
     cudaStream_t st = (cudaStream_t)stream;
-    // ggamma is accumulated with atomics: zero it first
+    if (g_ab2_opt_tp_fast && row_ptr && ab2_tp_fast_supported(dtype, D, d_in, d_out) && (!implicit_v0 || d_in == D)) {
+        if (ab2_tp_bwd_fast(dtype, N, U, D, d_in, d_out, nnz, tab_ijk, cgw, row_ptr, gamma, Vin, implicit_v0, Y, w0, w0_ld, gVout, gVin,
+                            gw0, gw0_ld, gY, ggamma, st) == 0) {
+            AB2_CUDA_LAUNCH_CHECK();
+            return 0;
+        }
+    }
+    // generic path: ggamma is accumulated with atomics: zero it first
     const size_t acc_size = (dtype == AB2_F64) ? 8 : 4;
     AB2_CUDA_CALL(cudaMemsetAsync(ggamma, 0, (size_t)N * D * U * acc_size, st));
     AB2_DISPATCH_DTYPE(dtype, tp_bwd_generic_kernel<TAct, TAcc><<<ab2_blocks(E * U, 128), 128, 0, st>>>(

@@ -1,0 +1,17 @@
+// Internal (non-ABI) entry points of the register-tiled tensor-product kernels (tp_fast.cu).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#define AB2_FAST_MAXD 25
+
+bool ab2_tp_fast_supported(int dtype, int D, int d_in, int d_out);
+// return 0 on launch, -1 if the shape/dtype has no fast instantiation
+int ab2_tp_fwd_fast(int dtype, int64_t N, int U, int D, int d_in, int d_out, int nnz, const int32_t* tab, const void* cgw,
+                    const int32_t* row_ptr, const void* gamma, const void* Vin, int implicit_v0, const void* Y, const void* w0,
+                    int64_t w0_ld, void* Vout, cudaStream_t st);
+int ab2_tp_bwd_fast(int dtype, int64_t N, int U, int D, int d_in, int d_out, int nnz, const int32_t* tab, const void* cgw,
+                    const int32_t* row_ptr, const void* gamma, const void* Vin, int implicit_v0, const void* Y, const void* w0,
+                    int64_t w0_ld, const void* gVout, void* gVin, void* gw0, int64_t gw0_ld, void* gY, void* ggamma, cudaStream_t st);
+
+extern int g_ab2_opt_tp_fast;

@@ -102,6 +102,9 @@ class PackedMLP:
         self.silu = mlp.nonlinearity == "silu"
         self.W = [w.to(device=device, dtype=dtype).contiguous() for w in ws]
         self.WT = [w.T.to(device=device, dtype=dtype).contiguous() for w in ws]
+        # tcgen05 path: packed bf16 hi/lo images (None where the shape is not eligible)
+        self.Wp = [_lib.linear_pack(w) for w in self.W]
+        self.WTp = [_lib.linear_pack(w) for w in self.WT]
         self.dims = [ws[0].shape[0]] + [w.shape[1] for w in ws]
         self.dtype = dtype
         self.device = device
@@ -119,10 +122,10 @@ class PackedMLP:
             last = k == self.n_layers - 1
             act = _lib.ACT_SILU if (k > 0 and self.silu) else _lib.ACT_NONE
             if last:
-                _lib.linear(cur, self.W[k], out_segs, act=act)
+                _lib.linear(cur, self.W[k], out_segs, act=act, W_packed=self.Wp[k])
             else:
                 h = torch.empty(M, self.dims[k + 1], dtype=self.dtype, device=self.device)
-                _lib.linear(cur, self.W[k], [h], act=act)
+                _lib.linear(cur, self.W[k], [h], act=act, W_packed=self.Wp[k])
                 pre.append(h)
                 cur = [h]
         return pre
@@ -132,11 +135,11 @@ class PackedMLP:
         cur = list(gout_segs)
         for k in range(self.n_layers - 1, -1, -1):
             if k == 0:
-                _lib.linear(cur, self.WT[0], gin_segs, o_accum=gin_accum)
+                _lib.linear(cur, self.WT[0], gin_segs, o_accum=gin_accum, W_packed=self.WTp[0])
             else:
                 g = torch.empty(M, self.dims[k], dtype=self.dtype, device=self.device)
                 if self.silu:
-                    _lib.linear(cur, self.WT[k], [g], epi=_lib.EPI_MUL_DSILU, aux=pre[k - 1])
+                    _lib.linear(cur, self.WT[k], [g], epi=_lib.EPI_MUL_DSILU, aux=pre[k - 1], W_packed=self.WTp[k])
                 else:
-                    _lib.linear(cur, self.WT[k], [g])
+                    _lib.linear(cur, self.WT[k], [g], W_packed=self.WTp[k])
                 cur = [g]

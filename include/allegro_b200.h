@@ -38,6 +38,9 @@ const char* ab2_last_error(void);
 int ab2_version(void);
 /* 1 if a CUDA device with compute capability 10.x is current, else 0 (no error). */
 int ab2_device_ok(void);
+/* Kernel-selection switches (for A/B tests): "tp_fast" (register-tiled tensor product, default 1),
+ * "linear_tc" (tcgen05 tensor-core linear, default 1).  0 forces the shape-generic kernels. */
+int ab2_set_option(const char* key, int value);
 
 /* ---- operator level: the reference's own kernel plug-in point ----------------------- */
 
@@ -80,9 +83,18 @@ int ab2_sh_bwd(int acc_dtype, int lmax, int64_t E, const void* vec, const void* 
  * A segments: (ptr, leading dim in elements, width); widths sum to K; outputs likewise to N. */
 int ab2_linear(int dtype, int64_t M, int K, int N, int n_a, const void* const* a_ptr_host,
                const int64_t* a_ld_host, const int32_t* a_width_host, int act, const void* W,
+               const void* W_packed /* nullable: image from ab2_linear_pack -> tcgen05 path */,
                int n_o, void* const* o_ptr_host, const int64_t* o_ld_host,
                const int32_t* o_width_host, const int32_t* o_accum_host, int epi, const void* aux,
                int64_t aux_ld, void* stream);
+
+/* Tensor-core (tcgen05) path of ab2_linear.  ab2_linear_packed_bytes returns the size of the
+ * packed weight image (bf16 hi + lo parts in the UMMA canonical K-major core-matrix layout) or 0
+ * if (dtype, K, N) is not eligible (fp64, K % 16 != 0, N > 256, image > 128 KB);
+ * ab2_linear_pack builds it on the device from W[K][N].  With fp32 storage the kernel computes
+ * A_hi W_hi + A_lo W_hi + A_hi W_lo in bf16 MMAs with fp32 accumulation (~2^-16 relative). */
+int64_t ab2_linear_packed_bytes(int dtype, int K, int N);
+int ab2_linear_pack(int dtype, int K, int N, const void* W, void* packed, void* stream);
 
 /* _channels.py:44-57 + _contract.py:195-204 fused: gamma[c][j][u] =
  *   sf * sum_{z in row c} Y[z][j] * w[z][irrep(j)][u]      (a4, a7; deterministic, no atomics) */

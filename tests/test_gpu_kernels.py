@@ -88,6 +88,55 @@ def test_linear_concat_split_act_epi(dtype, shape):
             assert (b[:, :2] == 0.5).all()
 
 
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("shape", [(1000, [64, 32], [64, 96]), (77, [64], [96, 64, 96]), (40000, [64, 64, 64], [64]),
+                                   (300, [64], [1]), (129, [64, 96], [64, 64, 32]), (5000, [32, 16], [32]), (128, [96, 64, 96], [64])])
+@pytest.mark.parametrize("mode", ["plain", "silu_in", "dsilu_epi_accum"])
+def test_linear_tensor_core_path(dtype, shape, mode):
+    """tcgen05 path (16-byte aligned segments, K % 16 == 0) against an fp64 reference and against
+    the CUDA-core kernel.  fp32 storage uses the 3-term bf16 split: held to 1e-4 (measured ~1e-5)."""
+    M, awid, owid = shape
+    K, N = sum(awid), sum(owid)
+    g = torch.Generator().manual_seed(M + K + N)
+    abufs = [torch.randn(M, w + 8, generator=g, dtype=torch.float64) for w in awid]
+    W = torch.randn(K, N, generator=g, dtype=torch.float64) / math.sqrt(K)
+    aux = torch.randn(M, N, generator=g, dtype=torch.float64)
+    act = 1 if mode == "silu_in" else 0
+    epi = 1 if mode == "dsilu_epi_accum" else 0
+    accum = [mode == "dsilu_epi_accum" and (i % 2 == 1) for i in range(len(owid))]
+    A = torch.cat([b[:, 4 : 4 + w] for b, w in zip(abufs, awid)], -1).to(dtype).double()
+    if act:
+        A = torch.nn.functional.silu(A)
+    ref = A @ W.to(dtype).double()
+    if epi:
+        x = aux.to(dtype).double()
+        sg = torch.sigmoid(x)
+        ref = ref * (sg * (1 + x * (1 - sg)))
+    Wd = W.to(DEV, dtype)
+    packed = _lib.linear_pack(Wd)
+    assert packed is not None
+    res = {}
+    for name, pk in (("tc", packed), ("simt", None)):
+        dsegs = [b.to(DEV, dtype)[:, 4 : 4 + w] for b, w in zip(abufs, awid)]
+        obufs = [torch.full((M, w + 4), 0.25, device=DEV, dtype=dtype) for w in owid]
+        osegs = [b[:, 4:] for b in obufs]
+        _lib.linear(dsegs, Wd, osegs, o_accum=accum, act=act, epi=epi, aux=aux.to(DEV, dtype) if epi else None, W_packed=pk)
+        got = torch.cat([o.double().cpu() for o in osegs], -1)
+        for b in obufs:
+            assert (b[:, :4] == 0.25).all()
+        res[name] = got
+    exp = ref.clone()
+    o = 0
+    for w, a in zip(owid, accum):
+        if a:
+            exp[:, o : o + w] += 0.25
+        o += w
+    scale = exp.abs().max().item()
+    tol = 1e-4 if dtype == torch.float32 else 2e-2
+    assert (res["tc"] - exp).abs().max().item() / scale < tol
+    assert (res["simt"] - exp).abs().max().item() / scale < (1e-5 if dtype == torch.float32 else 2e-2)
+
+
 @pytest.mark.parametrize("lmax", [1, 2, 3])
 @pytest.mark.parametrize("U", [4, 32, 48])
 @pytest.mark.parametrize("dtype", [torch.float64, torch.float32, torch.bfloat16])
@@ -142,12 +191,22 @@ def _tp_case(lmax, layer, L, U, coupling, dtype, seed=0):
     return c, b
 
 
-@pytest.mark.parametrize("case", [(1, 0, 1), (2, 0, 2), (2, 1, 2), (3, 0, 3), (3, 1, 3), (3, 2, 3), (1, 0, 2)])
+@pytest.fixture(params=[1, 0], ids=["fast", "generic"])
+def tp_fast(request):
+    _lib.set_option("tp_fast", request.param)
+    yield request.param
+    _lib.set_option("tp_fast", 1)
+
+
+@pytest.mark.parametrize("case", [(1, 0, 1), (2, 0, 2), (2, 1, 2), (3, 0, 3), (3, 1, 3), (3, 2, 3), (1, 0, 2), (1, 1, 3)])
 @pytest.mark.parametrize("coupling", [True, False])
 @pytest.mark.parametrize("dtype", [torch.float64, torch.float32, torch.bfloat16])
-def test_tp_fwd_bwd_explicit(case, coupling, dtype):
+@pytest.mark.parametrize("U", [8, 32, 40])
+def test_tp_fwd_bwd_explicit(case, coupling, dtype, U, tp_fast):
     lmax, layer, L = case
-    U, N, E = 8, 23, 300
+    if U != 8 and (dtype == torch.float64 or not coupling):
+        pytest.skip("channel-chunk coverage only needed once")
+    N, E = 23, 300
     c, b = _tp_case(lmax, layer, L, U, coupling, dtype)
     csr, ctr = _csr_random(N, E, seed=layer)
     acc = _lib.ACC_DTYPE[dtype]
@@ -177,9 +236,10 @@ def test_tp_fwd_bwd_explicit(case, coupling, dtype):
 
 @pytest.mark.parametrize("lmax", [1, 2, 3])
 @pytest.mark.parametrize("dtype", [torch.float64, torch.float32, torch.bfloat16])
-def test_tp_fwd_bwd_implicit_v0(lmax, dtype):
+@pytest.mark.parametrize("U", [8, 32, 40])
+def test_tp_fwd_bwd_implicit_v0(lmax, dtype, U, tp_fast):
     """Layer 0 with Vin = Y (x) w0 formed on the fly (tensorembed.py:95)."""
-    U, N, E, L = 8, 19, 250, 2
+    N, E, L = 19, 250, 2
     c, b = _tp_case(lmax, 0, L, U, True, dtype)
     csr, ctr = _csr_random(N, E, seed=3)
     acc = _lib.ACC_DTYPE[dtype]

@@ -68,6 +68,20 @@ def test_c2_shape_small(dtype, tol):
     _check(oracle, model, d, tol, tol)
 
 
+def test_c2_shape_generic_kernels_fp32():
+    """Same as above with the shape-generic kernels forced (A/B against the fast paths)."""
+    from allegro_b200 import _lib
+
+    _lib.set_option("tp_fast", 0)
+    _lib.set_option("linear_tc", 0)
+    try:
+        oracle, model, d = _pair("c2", 3, "float32")
+        _check(oracle, model, d, 1e-4, 1e-4)
+    finally:
+        _lib.set_option("tp_fast", 1)
+        _lib.set_option("linear_tc", 1)
+
+
 def test_c2_bf16():
     oracle, model, d = _pair("c2", 3, "bfloat16")
     ee, ef = _check(oracle, model, d, 2e-2, 5e-2)
