@@ -46,6 +46,9 @@ _SIGNATURES = {
     "ab2_edge_sum_bwd": ([_i32, _i64, _vp, _vp, _dbl, _vp, _vp], C.c_int),
     "ab2_force_scatter": ([_i32, _i64, _i64, _vp, _vp, _vp, _vp, _vp], C.c_int),
     "ab2_transpose_ui": ([_i32, _i64, _i32, _i32, _vp, _vp, _i32, _vp], C.c_int),
+    "ab2_edge_vec": ([_i32, _i32, _i64, _vp, _vp, _vp, _vp, _vp, _vp], C.c_int),
+    "ab2_radial_fwd": ([_i32, _i64, _i32, _i32, _dbl, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp], C.c_int),
+    "ab2_radial_bwd": ([_i32, _i64, _i32, _i32, _dbl, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp], C.c_int),
 }
 
 
@@ -358,3 +361,31 @@ def op_contract(mode: int, U, d1, d2, dout, tab, cgw, a, b, idxs, out):
             )
         )
     return out
+
+
+def edge_vec(pos: torch.Tensor, ctr, nbr, shift: Optional[torch.Tensor], acc_dtype) -> torch.Tensor:
+    E = ctr.shape[0]
+    vec = torch.empty(E, 3, dtype=acc_dtype, device=pos.device)
+    if shift is not None:
+        assert shift.dtype == pos.dtype
+    with _timed("edge_vec"):
+        _check(load().ab2_edge_vec(DTYPE_ENUM[pos.dtype], DTYPE_ENUM[acc_dtype], E, _ptr(_contig(pos, "pos")), _ptr(ctr), _ptr(nbr),
+                                   _ptr(_contig(shift, "shift")) if shift is not None else None, _ptr(vec), _stream()))
+    return vec
+
+
+def radial_fwd(dtype, S_rc: int, p_cut: float, vec, ctr, nbr, types, rmax_table, bessel_w, Wb, cemb, nemb) -> torch.Tensor:
+    E = ctr.shape[0]
+    e0 = torch.empty(E, S_rc, dtype=dtype, device=vec.device)
+    with _timed("radial_fwd"):
+        _check(load().ab2_radial_fwd(DTYPE_ENUM[dtype], E, S_rc, bessel_w.numel(), float(p_cut), _ptr(vec), _ptr(ctr), _ptr(nbr), _ptr(types),
+                                     _ptr(rmax_table), rmax_table.shape[0], _ptr(bessel_w), _ptr(Wb), _ptr(cemb), _ptr(nemb), _ptr(e0), _stream()))
+    return e0
+
+
+def radial_bwd(dtype, S_rc: int, p_cut: float, vec, ctr, nbr, types, rmax_table, bessel_w, Wb, cemb, nemb, g_e0, gvec):
+    E = ctr.shape[0]
+    with _timed("radial_bwd"):
+        _check(load().ab2_radial_bwd(DTYPE_ENUM[dtype], E, S_rc, bessel_w.numel(), float(p_cut), _ptr(vec), _ptr(ctr), _ptr(nbr), _ptr(types),
+                                     _ptr(rmax_table), rmax_table.shape[0], _ptr(bessel_w), _ptr(Wb), _ptr(cemb), _ptr(nemb),
+                                     _ptr(_contig(g_e0, "g_e0")), _ptr(gvec), _stream()))

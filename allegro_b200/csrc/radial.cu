@@ -1,0 +1,180 @@
+// Upstream two-body scalar track and edge geometry, so that the whole
+// energy+force evaluation runs without torch autograd:
+//
+//   edge vectors      r_z = pos[nbr] - pos[ctr] (+ shift)          nequip with_edge_vectors_ (tensorembed.py:86)
+//   x = |r| / r_max(t_c, t_n)                                      EdgeLengthNormalizer (allegro_models.py:153-157)
+//   B_n(x) = sin(pi w_n x)/(pi x) * f_p(x),  n = 1..num_bessels    BesselEdgeLengthEncoding + PolynomialCutoff
+//                                                                  (allegro/nn/scalarembed.py:60-66)
+//   e0[z][c] = typeemb[t_c, t_n][c] * sum_n B_n W_b[n][c]          ProductTypeEmbedding (_edgeembed.py:68-85)
+//
+// and the adjoint (g_e0 -> d/d r_z).  One warp per edge, lane = embedding column(s): the [E][S_rc]
+// rows are read/written coalesced; the 8-term radial basis is recomputed by every lane (cheap) so
+// nothing but e0 touches HBM.
+#include "common.cuh"
+
+#define AB2_MAX_BESSEL 16
+
+template <typename T>
+__device__ __forceinline__ T ab2_sin(T x);
+template <>
+__device__ __forceinline__ float ab2_sin<float>(float x) { return sinf(x); }
+template <>
+__device__ __forceinline__ double ab2_sin<double>(double x) { return sin(x); }
+template <typename T>
+__device__ __forceinline__ T ab2_cos(T x);
+template <>
+__device__ __forceinline__ float ab2_cos<float>(float x) { return cosf(x); }
+template <>
+__device__ __forceinline__ double ab2_cos<double>(double x) { return cos(x); }
+__device__ __forceinline__ float ab2_pow(float x, float p) { return powf(x, p); }
+__device__ __forceinline__ double ab2_pow(double x, double p) { return pow(x, p); }
+
+template <typename TPos, typename TAcc>
+__global__ void __launch_bounds__(256) edge_vec_kernel(int64_t E, const TPos* __restrict__ pos, const int32_t* __restrict__ ctr,
+                                                       const int32_t* __restrict__ nbr, const TPos* __restrict__ shift,
+                                                       TAcc* __restrict__ vec) {
+    const int64_t z = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (z >= E) return;
+    const int64_t i = ctr[z], j = nbr[z];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        TPos d = pos[j * 3 + a] - pos[i * 3 + a];
+        if (shift) d += shift[z * 3 + a];
+        vec[z * 3 + a] = (TAcc)d;
+    }
+}
+
+// radial basis and (optionally) its derivative w.r.t. x
+template <typename TAcc, bool GRAD>
+__device__ __forceinline__ void bessel_basis(TAcc x, TAcc p, int nb, const TAcc* __restrict__ bw, TAcc* B, TAcc* dB) {
+    const TAcc PI = TAcc(3.14159265358979323846);
+    if (x >= TAcc(1)) {
+        for (int n = 0; n < nb; ++n) {
+            B[n] = TAcc(0);
+            if (GRAD) dB[n] = TAcc(0);
+        }
+        return;
+    }
+    const TAcc xp = ab2_pow(x, p);  // x^p
+    const TAcc a = (p + 1) * (p + 2) / 2, b = p * (p + 2), c = p * (p + 1) / 2;
+    const TAcc f = TAcc(1) - a * xp + b * xp * x - c * xp * x * x;
+    const TAcc df = GRAD ? (-a * p * xp / x + b * (p + 1) * xp - c * (p + 2) * xp * x) : TAcc(0);
+    const TAcc inv = TAcc(1) / (PI * x);
+    for (int n = 0; n < nb; ++n) {
+        const TAcc arg = PI * bw[n] * x;
+        const TAcc s = ab2_sin(arg) * inv;  // sin(pi w x)/(pi x)
+        B[n] = s * f;
+        if (GRAD) {
+            const TAcc ds = (bw[n] * ab2_cos(arg) - s) / x;  // d/dx [sin(pi w x)/(pi x)]
+            dB[n] = ds * f + s * df;
+        }
+    }
+}
+
+template <typename TAct, typename TAcc>
+__global__ void __launch_bounds__(256) radial_fwd_kernel(int64_t E, int S_rc, int nb, TAcc p, const TAcc* __restrict__ vec,
+                                                         const int32_t* __restrict__ ctr, const int32_t* __restrict__ nbr,
+                                                         const int32_t* __restrict__ types, const TAcc* __restrict__ rmax_table,
+                                                         int num_types, const TAcc* __restrict__ bw, const TAcc* __restrict__ Wb,
+                                                         const TAcc* __restrict__ cemb, const TAcc* __restrict__ nemb,
+                                                         TAct* __restrict__ e0) {
+    const int64_t z = ((int64_t)blockIdx.x * 256 + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (z >= E) return;
+    const TAcc vx = vec[z * 3], vy = vec[z * 3 + 1], vz = vec[z * 3 + 2];
+    const TAcc r = sqrt(vx * vx + vy * vy + vz * vz);
+    const int tc = types[ctr[z]], tn = types[nbr[z]];
+    const TAcc x = r / rmax_table[tc * num_types + tn];
+    TAcc B[AB2_MAX_BESSEL];
+    bessel_basis<TAcc, false>(x, p, nb, bw, B, nullptr);
+    const int half = S_rc >> 1;
+    for (int c = lane; c < S_rc; c += 32) {
+        TAcc s = TAcc(0);
+        for (int n = 0; n < nb; ++n) s += B[n] * Wb[n * S_rc + c];
+        const TAcc te = (c < half) ? cemb[tc * half + c] : nemb[tn * half + (c - half)];
+        e0[z * S_rc + c] = from_acc<TAct>(te * s);
+    }
+}
+
+template <typename TAct, typename TAcc>
+__global__ void __launch_bounds__(256) radial_bwd_kernel(int64_t E, int S_rc, int nb, TAcc p, const TAcc* __restrict__ vec,
+                                                         const int32_t* __restrict__ ctr, const int32_t* __restrict__ nbr,
+                                                         const int32_t* __restrict__ types, const TAcc* __restrict__ rmax_table,
+                                                         int num_types, const TAcc* __restrict__ bw, const TAcc* __restrict__ Wb,
+                                                         const TAcc* __restrict__ cemb, const TAcc* __restrict__ nemb,
+                                                         const TAct* __restrict__ ge0, TAcc* __restrict__ gvec) {
+    const int64_t z = ((int64_t)blockIdx.x * 256 + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (z >= E) return;
+    const TAcc vx = vec[z * 3], vy = vec[z * 3 + 1], vz = vec[z * 3 + 2];
+    const TAcc r = sqrt(vx * vx + vy * vy + vz * vz);
+    const int tc = types[ctr[z]], tn = types[nbr[z]];
+    const TAcc rmax = rmax_table[tc * num_types + tn];
+    const TAcc x = r / rmax;
+    TAcc B[AB2_MAX_BESSEL], dB[AB2_MAX_BESSEL];
+    bessel_basis<TAcc, true>(x, p, nb, bw, B, dB);
+    // gB[n] = sum_c ge0[c] * te[c] * Wb[n][c];  gx = sum_n gB[n] dB[n]  -> fold: gx = sum_c ge0[c] te[c] (sum_n dB[n] Wb[n][c])
+    const int half = S_rc >> 1;
+    TAcc gx = TAcc(0);
+    for (int c = lane; c < S_rc; c += 32) {
+        TAcc s = TAcc(0);
+        for (int n = 0; n < nb; ++n) s += dB[n] * Wb[n * S_rc + c];
+        const TAcc te = (c < half) ? cemb[tc * half + c] : nemb[tn * half + (c - half)];
+        gx += to_acc<TAcc>(ge0[z * S_rc + c]) * te * s;
+    }
+    gx = warp_sum(gx);
+    if (lane < 3) {
+        const TAcc comp = lane == 0 ? vx : (lane == 1 ? vy : vz);
+        gvec[z * 3 + lane] += gx / rmax * comp / r;  // dx/dr_vec = r_vec / (|r| r_max)
+    }
+}
+
+extern "C" int ab2_edge_vec(int pos_dtype, int acc_dtype, int64_t E, const void* pos, const int32_t* ctr, const int32_t* nbr,
+                            const void* shift, void* vec, void* stream) {
+    if (E == 0) return 0;
+    AB2_CHECK_ARG(pos && ctr && nbr && vec, "null pointer");
+    AB2_CHECK_ARG(pos_dtype == AB2_F64 || pos_dtype == AB2_F32, "positions must be fp64 or fp32");
+    cudaStream_t st = (cudaStream_t)stream;
+    const unsigned g = ab2_blocks(E, 256);
+    const bool acc64 = acc_dtype == AB2_F64;
+    if (pos_dtype == AB2_F64 && acc64)
+        edge_vec_kernel<double, double><<<g, 256, 0, st>>>(E, (const double*)pos, ctr, nbr, (const double*)shift, (double*)vec);
+    else if (pos_dtype == AB2_F64)
+        edge_vec_kernel<double, float><<<g, 256, 0, st>>>(E, (const double*)pos, ctr, nbr, (const double*)shift, (float*)vec);
+    else if (acc64)
+        edge_vec_kernel<float, double><<<g, 256, 0, st>>>(E, (const float*)pos, ctr, nbr, (const float*)shift, (double*)vec);
+    else
+        edge_vec_kernel<float, float><<<g, 256, 0, st>>>(E, (const float*)pos, ctr, nbr, (const float*)shift, (float*)vec);
+    AB2_CUDA_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int ab2_radial_fwd(int dtype, int64_t E, int S_rc, int num_bessels, double p_cut, const void* vec, const int32_t* ctr,
+                              const int32_t* nbr, const int32_t* types, const void* rmax_table, int num_types, const void* bessel_w,
+                              const void* Wb, const void* center_embed, const void* neighbor_embed, void* e0, void* stream) {
+    if (E == 0) return 0;
+    AB2_CHECK_ARG(vec && ctr && nbr && types && rmax_table && bessel_w && Wb && center_embed && neighbor_embed && e0, "null pointer");
+    AB2_CHECK_ARG(num_bessels > 0 && num_bessels <= AB2_MAX_BESSEL && S_rc > 0 && S_rc % 2 == 0, "num_bessels / embedding dim");
+    cudaStream_t st = (cudaStream_t)stream;
+    AB2_DISPATCH_DTYPE(dtype, radial_fwd_kernel<TAct, TAcc><<<ab2_blocks(E * 32, 256), 256, 0, st>>>(
+                                  E, S_rc, num_bessels, (TAcc)p_cut, (const TAcc*)vec, ctr, nbr, types, (const TAcc*)rmax_table, num_types,
+                                  (const TAcc*)bessel_w, (const TAcc*)Wb, (const TAcc*)center_embed, (const TAcc*)neighbor_embed, (TAct*)e0));
+    AB2_CUDA_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int ab2_radial_bwd(int dtype, int64_t E, int S_rc, int num_bessels, double p_cut, const void* vec, const int32_t* ctr,
+                              const int32_t* nbr, const int32_t* types, const void* rmax_table, int num_types, const void* bessel_w,
+                              const void* Wb, const void* center_embed, const void* neighbor_embed, const void* g_e0, void* gvec,
+                              void* stream) {
+    if (E == 0) return 0;
+    AB2_CHECK_ARG(vec && ctr && nbr && types && rmax_table && bessel_w && Wb && center_embed && neighbor_embed && g_e0 && gvec, "null pointer");
+    AB2_CHECK_ARG(num_bessels > 0 && num_bessels <= AB2_MAX_BESSEL && S_rc > 0 && S_rc % 2 == 0, "num_bessels / embedding dim");
+    cudaStream_t st = (cudaStream_t)stream;
+    AB2_DISPATCH_DTYPE(dtype, radial_bwd_kernel<TAct, TAcc><<<ab2_blocks(E * 32, 256), 256, 0, st>>>(
+                                  E, S_rc, num_bessels, (TAcc)p_cut, (const TAcc*)vec, ctr, nbr, types, (const TAcc*)rmax_table, num_types,
+                                  (const TAcc*)bessel_w, (const TAcc*)Wb, (const TAcc*)center_embed, (const TAcc*)neighbor_embed,
+                                  (const TAct*)g_e0, (TAcc*)gvec));
+    AB2_CUDA_LAUNCH_CHECK();
+    return 0;
+}

@@ -175,11 +175,19 @@ class DistributedAllegro:
             D.EDGE_CELL_SHIFT_KEY: dec.edge_cell_shift,
             D.CELL_KEY: dec.cell,
         }
-        with torch.enable_grad():
-            out = self.model(data)
+        if hasattr(self.model, "energy_and_forces"):
+            # autograd-free CUDA path: forces on owned AND ghost atoms come out of one pass
+            data[D.POSITIONS_KEY] = pos_local.detach()
+            out = self.model.energy_and_forces(data)
             e_atoms = out[D.PER_ATOM_ENERGY_KEY][: dec.n_owned]
             e_local = e_atoms.sum()
-            (g,) = torch.autograd.grad(e_local, pos_local)
+            g = -out[D.FORCE_KEY]
+        else:
+            with torch.enable_grad():
+                out = self.model(data)
+                e_atoms = out[D.PER_ATOM_ENERGY_KEY][: dec.n_owned]
+                e_local = e_atoms.sum()
+                (g,) = torch.autograd.grad(e_local, pos_local)
         g_owned = g[: dec.n_owned].clone()
         dec.exchange_reverse(g[dec.n_owned :].contiguous(), g_owned)
         e_tot = e_local.detach().double().clone().reshape(1)

@@ -29,7 +29,7 @@ from ..nn._modules import (
     TwoBodySphericalHarmonicTensorEmbed,
 )
 from ..nn._mlp import ScalarMLPFunction
-from ..nn._pipeline import AllegroCore, core_apply
+from ..nn._pipeline import AllegroCore, UpstreamPack, core_apply, energy_forces
 from ..o3 import Irreps
 
 _DTYPES = {"float32": torch.float32, "float64": torch.float64, "bfloat16": torch.bfloat16}
@@ -141,8 +141,45 @@ class FusedAllegroEnergy(torch.nn.Module):
                 raise RuntimeError("allegro_b200: the model must live on a CUDA device (no CPU path for the hot path)")
             self._core = AllegroCore(self.tensor_embed, self.allegro, self.edge_readout, self.avg_num_neighbors,
                                      self.model_dtype, dev)
+            self._upstream = UpstreamPack(self.edge_norm, self.radial_chemical_embed, self.scalar_embed_mlp, self.model_dtype, dev)
             self._core_key = key
         return self._core
+
+    def energy_and_forces(self, data: D.Type) -> D.Type:
+        """Energies AND forces in one pass of hand-written kernels (no torch autograd anywhere):
+        what ForceStressOutput(AllegroEnergyModel) computes (allegro_models.py:101-103)."""
+        pos = data[D.POSITIONS_KEY]
+        if not pos.is_cuda:
+            raise RuntimeError("allegro_b200: inputs must be CUDA tensors (no CPU fallback on the hot path)")
+        core = self.core()
+        n = pos.shape[0]
+        csr = self._csr(data[D.EDGE_INDEX_KEY], n)
+        shift_vec = None
+        if D.EDGE_CELL_SHIFT_KEY in data and D.CELL_KEY in data:
+            sh = data[D.EDGE_CELL_SHIFT_KEY]
+            key = (sh.data_ptr(), sh._version, data[D.CELL_KEY].data_ptr(), data[D.CELL_KEY]._version, id(csr))
+            if getattr(self, "_shift_cache", None) is None or self._shift_cache[0] != key:
+                s = sh if csr.perm is None else sh[csr.perm]
+                self._shift_cache = (key, (s.to(pos.dtype) @ data[D.CELL_KEY].view(3, 3).to(pos.dtype)).contiguous())
+            shift_vec = self._shift_cache[1]
+        types = data[D.ATOM_TYPE_KEY].reshape(-1)
+        tkey = (types.data_ptr(), types._version)
+        if getattr(self, "_types_cache", None) is None or self._types_cache[0] != tkey:
+            self._types_cache = (tkey, types.to(torch.int32).contiguous())
+        ss = self.per_type_energy_scale_shift
+        gscale = ss.scales[types].to(core.acc)
+        Ei, F, X, Ez = energy_forces(core, self._upstream, csr, pos.detach().contiguous(), self._types_cache[1], shift_vec, gscale)
+        e_atom = ss(Ei.unsqueeze(-1), types)
+        out = dict(data)
+        if csr.perm is not None:
+            inv = torch.empty_like(csr.perm)
+            inv[csr.perm] = torch.arange(csr.perm.shape[0], device=csr.perm.device)
+            X, Ez = X[inv], Ez[inv]
+        out[D.EDGE_FEATURES_KEY], out[D.EDGE_ENERGY_KEY] = X, Ez
+        out[D.PER_ATOM_ENERGY_KEY] = e_atom
+        out[D.TOTAL_ENERGY_KEY] = e_atom.sum(dim=0, keepdim=True)
+        out[D.FORCE_KEY] = F.to(pos.dtype)
+        return out
 
     def _csr(self, edge_index: torch.Tensor, n: int):
         key = (edge_index.data_ptr(), edge_index._version, tuple(edge_index.shape), n)
@@ -197,6 +234,8 @@ class ForceStressOutput(torch.nn.Module):
         self.model = model
 
     def forward(self, data: D.Type) -> D.Type:
+        if hasattr(self.model, "energy_and_forces") and not getattr(self, "use_autograd", False):
+            return self.model.energy_and_forces(data)
         data = dict(data)
         pos = data[D.POSITIONS_KEY].detach().clone().requires_grad_(True)
         data[D.POSITIONS_KEY] = pos

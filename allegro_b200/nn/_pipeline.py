@@ -171,6 +171,46 @@ class AllegroCore:
         return gvec, gx_emb
 
 
+class UpstreamPack:
+    """Device constants of the two-body scalar embedding (edge_norm, radial_chemical_embed,
+    scalar_embed_mlp) for ab2_radial_fwd/bwd + the packed scalar-embed MLP."""
+
+    def __init__(self, edge_norm, radial, scalar_embed_mlp, dtype, device):
+        acc = _lib.ACC_DTYPE[dtype]
+        te = radial.type_embed
+        self.p = float(radial.bessel_encode.p)
+        self.S_rc = radial.out_dim
+        self.rmax_table = edge_norm.rmax_table.detach().to(device=device, dtype=acc).contiguous()
+        self.bessel_w = radial.bessel_encode.bessel_weights.detach().reshape(-1).to(device=device, dtype=acc).contiguous()
+        self.Wb = te.basis_linear.folded_weights()[0].to(device=device, dtype=acc).contiguous()
+        self.cemb = te.center_embed.weight.detach().to(device=device, dtype=acc).contiguous()
+        self.nemb = te.neighbor_embed.weight.detach().to(device=device, dtype=acc).contiguous()
+        self.mlp = PackedMLP(scalar_embed_mlp, dtype, device)
+        self.dtype = dtype
+
+
+def energy_forces(core: "AllegroCore", up: UpstreamPack, csr: EdgeCSR, pos: torch.Tensor, types_i32: torch.Tensor,
+                  shift_vec: Optional[torch.Tensor], gEi_scale: Optional[torch.Tensor]):
+    """Whole path with no torch autograd: positions -> (Ei [N], forces [n_atoms,3], X, Ez).
+    ``gEi_scale`` = d E_total / d Ei (per-type scales), None = ones."""
+    dt, acc = core.dtype, core.acc
+    E = csr.num_edges
+    _lib.set_tag("fwd.radial")
+    vec = _lib.edge_vec(pos, csr.ctr, csr.nbr, shift_vec, acc)
+    e0 = _lib.radial_fwd(dt, up.S_rc, up.p, vec, csr.ctr, csr.nbr, types_i32, up.rmax_table, up.bessel_w, up.Wb, up.cemb, up.nemb)
+    x_emb = torch.empty(E, core.S_in, dtype=dt, device=pos.device)
+    pre_se = up.mlp.forward([e0], [x_emb])
+    Ei, X, Ez, sv = core.forward(csr, vec, x_emb)
+    gEi = gEi_scale if gEi_scale is not None else torch.ones_like(Ei)
+    gvec, gx_emb = core.backward(sv, gEi)
+    _lib.set_tag("bwd.radial")
+    g_e0 = torch.empty(E, up.S_rc, dtype=dt, device=pos.device)
+    up.mlp.backward([gx_emb], pre_se, [g_e0], [False])
+    _lib.radial_bwd(dt, up.S_rc, up.p, vec, csr.ctr, csr.nbr, types_i32, up.rmax_table, up.bessel_w, up.Wb, up.cemb, up.nemb, g_e0, gvec)
+    F = _lib.force_scatter(gvec, csr.row_ptr, csr.nbr, pos.shape[0])
+    return Ei, F, X, Ez
+
+
 class _CoreFn(torch.autograd.Function):
     """(vec, x_emb) -> per-atom energies; backward gives (d/dvec, d/dx_emb).  Weights are not
     differentiated (inference / MD path, like the reference's Triton back-end)."""

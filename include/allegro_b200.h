@@ -141,6 +141,30 @@ int ab2_edge_sum_bwd(int acc_dtype, int64_t E, const int32_t* ctr, const void* g
 int ab2_force_scatter(int acc_dtype, int64_t N, int64_t E, const int32_t* row_ptr,
                       const int32_t* nbr, const void* gvec, void* F, void* stream);
 
+/* ---- upstream two-body scalar track + geometry ------------------ */
+
+/* nequip with_edge_vectors_ (tensorembed.py:86): vec[z] = pos[nbr[z]] - pos[ctr[z]] (+ shift[z]),
+ * computed in the positions' dtype (AB2_F64 / AB2_F32), stored in the accumulate dtype.
+ * shift = edge_cell_shift @ cell, nullable. */
+int ab2_edge_vec(int pos_dtype, int acc_dtype, int64_t E, const void* pos, const int32_t* ctr,
+                 const int32_t* nbr, const void* shift, void* vec, void* stream);
+
+/* EdgeLengthNormalizer + BesselEdgeLengthEncoding*PolynomialCutoff + ProductTypeEmbedding
+ * (allegro_models.py:153-157, scalarembed.py:60-81, _edgeembed.py:68-85):
+ *   x = |vec| / rmax_table[t_c][t_n];  B_n = sin(pi w_n x)/(pi x) * f_p(x);
+ *   e0[z][c] = (c < S_rc/2 ? center_embed[t_c][c] : neighbor_embed[t_n][c - S_rc/2]) * sum_n B_n Wb[n][c]
+ * Tables are in the accumulate dtype; e0 in the activation dtype. */
+int ab2_radial_fwd(int dtype, int64_t E, int S_rc, int num_bessels, double p_cut, const void* vec,
+                   const int32_t* ctr, const int32_t* nbr, const int32_t* types,
+                   const void* rmax_table, int num_types, const void* bessel_w, const void* Wb,
+                   const void* center_embed, const void* neighbor_embed, void* e0, void* stream);
+/* adjoint: gvec[z] += (d e0 / d vec)^T g_e0[z] */
+int ab2_radial_bwd(int dtype, int64_t E, int S_rc, int num_bessels, double p_cut, const void* vec,
+                   const int32_t* ctr, const int32_t* nbr, const int32_t* types,
+                   const void* rmax_table, int num_types, const void* bessel_w, const void* Wb,
+                   const void* center_embed, const void* neighbor_embed, const void* g_e0,
+                   void* gvec, void* stream);
+
 /* layout helpers between the reference strided layout [z][u][i] and the internal [z][i][u] */
 int ab2_transpose_ui(int dtype, int64_t E, int U, int d, const void* src, void* dst, int to_internal,
                      void* stream);

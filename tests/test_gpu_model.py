@@ -82,6 +82,22 @@ def test_c2_shape_generic_kernels_fp32():
         _lib.set_option("linear_tc", 1)
 
 
+def test_autograd_path_matches_direct_path():
+    """ForceStressOutput via torch.autograd through the custom Function == the autograd-free
+    energy_and_forces pass (both are product paths; the second is the default)."""
+    oracle, model, d = _pair("c2", 3, "float64")
+    dd = _to_dev(d)
+    direct = model(dd)
+    model.use_autograd = True
+    try:
+        _check(oracle, model, d, 1e-9, 1e-9)
+        auto = model(dd)
+    finally:
+        model.use_autograd = False
+    assert (direct[D.FORCE_KEY] - auto[D.FORCE_KEY]).abs().max() < 1e-10
+    assert (direct[D.PER_ATOM_ENERGY_KEY] - auto[D.PER_ATOM_ENERGY_KEY]).abs().max() < 1e-10
+
+
 def test_c2_bf16():
     oracle, model, d = _pair("c2", 3, "bfloat16")
     ee, ef = _check(oracle, model, d, 2e-2, 5e-2)
