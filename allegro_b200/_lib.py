@@ -39,7 +39,7 @@ _SIGNATURES = {
     "ab2_linear_packed_bytes": ([_i32, _i32, _i32], C.c_int64),
     "ab2_linear_pack": ([_i32, _i32, _i32, _vp, _vp, _vp], C.c_int),
     "ab2_env_sum": ([_i32, _i32, _i64, _i32, _vp, _vp, _vp, _i64, _dbl, _vp, _vp], C.c_int),
-    "ab2_env_bwd": ([_i32, _i32, _i64, _i32, _vp, _vp, _vp, _i64, _vp, _dbl, _vp, _i64, _vp, _vp], C.c_int),
+    "ab2_env_bwd": ([_i32, _i32, _i64, _i64, _i32, _vp, _vp, _vp, _vp, _i64, _vp, _dbl, _vp, _i64, _vp, _vp], C.c_int),
     "ab2_tp_fwd": ([_i32, _i32, _i64, _i64, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _i64, _vp, _vp], C.c_int),
     "ab2_tp_bwd": ([_i32, _i32, _i64, _i64, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _i64, _vp, _vp, _vp, _i64, _vp, _vp, _vp], C.c_int),
     "ab2_edge_sum": ([_i32, _i64, _vp, _vp, _dbl, _vp, _vp], C.c_int),
@@ -255,14 +255,15 @@ def env_sum(dtype, lmax: int, N: int, U: int, row_ptr, Y, w: torch.Tensor, sf: f
     return out
 
 
-def env_bwd(dtype, lmax: int, U: int, ctr, Y, w: torch.Tensor, ggamma, sf: float, gw: torch.Tensor, gY: torch.Tensor):
+def env_bwd(dtype, lmax: int, U: int, ctr, Y, w: torch.Tensor, ggamma, sf: float, gw: torch.Tensor, gY: torch.Tensor, row_ptr=None):
     w, w_ld = _row_strided(w, "w")
     gw, gw_ld = _row_strided(gw, "gw")
     E = Y.shape[0]
     with _timed("env_bwd", 1):
         _check(
             load().ab2_env_bwd(
-                DTYPE_ENUM[dtype], lmax, E, U, _ptr(ctr), _ptr(_contig(Y, "Y")), _ptr(w), w_ld, _ptr(_contig(ggamma, "ggamma")), float(sf),
+                DTYPE_ENUM[dtype], lmax, ggamma.shape[0], E, U, _ptr(row_ptr), _ptr(ctr), _ptr(_contig(Y, "Y")), _ptr(w), w_ld,
+                _ptr(_contig(ggamma, "ggamma")), float(sf),
                 _ptr(gw), gw_ld, _ptr(_contig(gY, "gY")), _stream(),
             )
         )

@@ -79,6 +79,92 @@ __global__ void __launch_bounds__(128) env_bwd_kernel(int64_t E, int U, const in
     }
 }
 
+// Reduce D (<=16) per-lane values across the warp with a multi-value butterfly: 16 shuffles instead
+// of 5*D.  On return lane 2*j (and 2*j+1) holds the warp total of value j.
+template <typename TAcc, int D>
+__device__ __forceinline__ TAcc warp_multi_sum(const TAcc (&v)[D], int lane) {
+    static_assert(D <= 16, "at most 16 values");
+    TAcc a[16];
+#pragma unroll
+    for (int t = 0; t < 16; ++t) a[t] = t < D ? v[t] : TAcc(0);
+    TAcc b[8];
+#pragma unroll
+    for (int t = 0; t < 8; ++t) {
+        const bool up = lane & 16;
+        const TAcc send = up ? a[t] : a[t + 8];
+        const TAcc got = __shfl_xor_sync(0xffffffffu, send, 16);
+        b[t] = (up ? a[t + 8] : a[t]) + got;
+    }
+    TAcc c[4];
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+        const bool up = lane & 8;
+        const TAcc send = up ? b[t] : b[t + 4];
+        const TAcc got = __shfl_xor_sync(0xffffffffu, send, 8);
+        c[t] = (up ? b[t + 4] : b[t]) + got;
+    }
+    TAcc d[2];
+#pragma unroll
+    for (int t = 0; t < 2; ++t) {
+        const bool up = lane & 4;
+        const TAcc send = up ? c[t] : c[t + 2];
+        const TAcc got = __shfl_xor_sync(0xffffffffu, send, 4);
+        d[t] = (up ? c[t + 2] : c[t]) + got;
+    }
+    const bool up = lane & 2;
+    const TAcc send = up ? d[0] : d[1];
+    const TAcc got = __shfl_xor_sync(0xffffffffu, send, 2);
+    TAcc e = (up ? d[1] : d[0]) + got;
+    e += __shfl_xor_sync(0xffffffffu, e, 1);
+    return e;  // value index = lane >> 1
+}
+
+// Warp per (centre, 32-channel chunk): ggamma[c][.][u] is loaded once into registers and the
+// centre's edges are streamed (two in flight).  Same arithmetic as env_bwd_kernel.
+template <typename TAct, typename TAcc, int LMAX>
+__global__ void __launch_bounds__(128) env_bwd_fast_kernel(int64_t N, int U, const int32_t* __restrict__ row_ptr,
+                                                           const TAcc* __restrict__ Y, const TAct* __restrict__ w, int64_t w_ld,
+                                                           const TAcc* __restrict__ ggamma, TAcc sf, TAct* __restrict__ gw,
+                                                           int64_t gw_ld, TAcc* __restrict__ gY) {
+    constexpr int D = (LMAX + 1) * (LMAX + 1);
+    const int nchunk = (U + 31) >> 5;
+    const int64_t wid = ((int64_t)blockIdx.x * 128 + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    const int64_t c = wid / nchunk;
+    if (c >= N) return;
+    const int u = (int)(wid % nchunk) * 32 + lane;
+    const bool live = u < U;
+    const int beg = row_ptr[c], end = row_ptr[c + 1];
+    TAcc gg[D];
+#pragma unroll
+    for (int j = 0; j < D; ++j) gg[j] = live ? sf * ggamma[(c * D + j) * U + u] : TAcc(0);
+#pragma unroll 2
+    for (int64_t z = beg; z < end; ++z) {
+        TAcc Yz[D], wl[LMAX + 1];
+#pragma unroll
+        for (int j = 0; j < D; ++j) Yz[j] = Y[z * D + j];
+#pragma unroll
+        for (int l = 0; l <= LMAX; ++l) wl[l] = live ? to_acc<TAcc>(w[z * w_ld + l * U + u]) : TAcc(0);
+        TAcc part[D];
+#pragma unroll
+        for (int l = 0; l <= LMAX; ++l) {
+            TAcc gwl = TAcc(0);
+#pragma unroll
+            for (int j = l * l; j < (l + 1) * (l + 1); ++j) {
+                gwl += Yz[j] * gg[j];
+                part[j] = wl[l] * gg[j];
+            }
+            if (live) gw[z * gw_ld + l * U + u] = from_acc<TAct>(gwl);
+        }
+        const TAcc tot = warp_multi_sum<TAcc, D>(part, lane);
+        const int j = lane >> 1;
+        if (!(lane & 1) && j < D) {
+            if (nchunk == 1) gY[z * D + j] += tot;
+            else atomicAdd(&gY[z * D + j], tot);
+        }
+    }
+}
+
 extern "C" int ab2_env_sum(int dtype, int lmax, int64_t N, int U, const int32_t* row_ptr, const void* Y, const void* w,
                            int64_t w_ld, double sf, void* gamma, void* stream) {
     if (N == 0) return 0;
@@ -92,11 +178,32 @@ extern "C" int ab2_env_sum(int dtype, int lmax, int64_t N, int U, const int32_t*
     return 0;
 }
 
-extern "C" int ab2_env_bwd(int dtype, int lmax, int64_t E, int U, const int32_t* ctr, const void* Y, const void* w, int64_t w_ld,
-                           const void* ggamma, double sf, void* gw, int64_t gw_ld, void* gY, void* stream) {
+extern int g_ab2_opt_tp_fast;
+
+extern "C" int ab2_env_bwd(int dtype, int lmax, int64_t N, int64_t E, int U, const int32_t* row_ptr, const int32_t* ctr, const void* Y,
+                           const void* w, int64_t w_ld, const void* ggamma, double sf, void* gw, int64_t gw_ld, void* gY,
+                           void* stream) {
     if (E == 0) return 0;
     AB2_CHECK_ARG(ctr && Y && w && ggamma && gw && gY && U > 0, "null pointer / U");
     cudaStream_t st = (cudaStream_t)stream;
+    if (g_ab2_opt_tp_fast && row_ptr && lmax <= 3) {
+        const int64_t warps = N * ((U + 31) / 32);
+        if (lmax == 3) {
+            AB2_DISPATCH_DTYPE(dtype, env_bwd_fast_kernel<TAct, TAcc, 3><<<ab2_blocks(warps * 32, 128), 128, 0, st>>>(
+                                          N, U, row_ptr, (const TAcc*)Y, (const TAct*)w, w_ld, (const TAcc*)ggamma, (TAcc)sf, (TAct*)gw, gw_ld, (TAcc*)gY));
+        } else if (lmax == 2) {
+            AB2_DISPATCH_DTYPE(dtype, env_bwd_fast_kernel<TAct, TAcc, 2><<<ab2_blocks(warps * 32, 128), 128, 0, st>>>(
+                                          N, U, row_ptr, (const TAcc*)Y, (const TAct*)w, w_ld, (const TAcc*)ggamma, (TAcc)sf, (TAct*)gw, gw_ld, (TAcc*)gY));
+        } else if (lmax == 1) {
+            AB2_DISPATCH_DTYPE(dtype, env_bwd_fast_kernel<TAct, TAcc, 1><<<ab2_blocks(warps * 32, 128), 128, 0, st>>>(
+                                          N, U, row_ptr, (const TAcc*)Y, (const TAct*)w, w_ld, (const TAcc*)ggamma, (TAcc)sf, (TAct*)gw, gw_ld, (TAcc*)gY));
+        } else {
+            AB2_DISPATCH_DTYPE(dtype, env_bwd_fast_kernel<TAct, TAcc, 0><<<ab2_blocks(warps * 32, 128), 128, 0, st>>>(
+                                          N, U, row_ptr, (const TAcc*)Y, (const TAct*)w, w_ld, (const TAcc*)ggamma, (TAcc)sf, (TAct*)gw, gw_ld, (TAcc*)gY));
+        }
+        AB2_CUDA_LAUNCH_CHECK();
+        return 0;
+    }
     AB2_DISPATCH_DTYPE(dtype, AB2_DISPATCH_LMAX(lmax, env_bwd_kernel<TAct, TAcc, LMAX><<<ab2_blocks(E * 32, 128), 128, 0, st>>>(
                                                           E, U, ctr, (const TAcc*)Y, (const TAct*)w, w_ld, (const TAcc*)ggamma, (TAcc)sf,
                                                           (TAct*)gw, gw_ld, (TAcc*)gY)));

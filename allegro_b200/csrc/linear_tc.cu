@@ -4,19 +4,19 @@
 //
 // M = number of edges (10^5..10^8), K,N <= 256: a tall-skinny GEMM that is HBM-bound once the
 // MACs run on tensor cores (12-25 KFLOP per ~0.5-1 KB row).  Structure (one persistent CTA per
-// SM, 9 warps, warp-specialised, all hand-written PTX):
+// SM, 13 warps, warp-specialised, all hand-written PTX):
 //
-//   warps 0-3  producers : coalesced global loads of the concatenated A row segments
+//   warps 0-7  producers : coalesced global loads of the concatenated A row segments
 //                          (8 rows x 128 B per warp instruction), optional SiLU, split of the fp32
 //                          value into bf16 hi + bf16 lo, 16-byte st.shared into a ring of
 //                          128-row x 32-k stages in the UMMA canonical K-major (no-swizzle,
 //                          8x16B core matrix) layout; fence.proxy.async + mbarrier arrive.
-//   warp  4    MMA       : one elected lane issues tcgen05.mma.cta_group::1.kind::f16
+//   warp  8    MMA       : one elected lane issues tcgen05.mma.cta_group::1.kind::f16
 //                          (M=128, N<=256, K=16) from shared-memory descriptors into one of two
 //                          TMEM accumulators; fp32 storage uses the 3-term split
 //                          A_hi W_hi + A_lo W_hi + A_hi W_lo (~2^-16 relative, fp32 accumulate);
 //                          tcgen05.commit releases ring slots / publishes the accumulator.
-//   warps 5-8  epilogue  : tcgen05.ld 32x32b (lane = row), silu' / accumulate epilogue, split
+//   warps 9-12 epilogue  : tcgen05.ld 32x32b (lane = row), silu' / accumulate epilogue, split
 //                          into the output column segments, vectorised global stores.
 //
 // W (all of it: <= 128 KB as bf16 hi+lo) is staged once per CTA from a pre-packed image
@@ -31,7 +31,8 @@ constexpr int BM = 128;       // rows per tile = UMMA M
 constexpr int KC = 32;        // k per ring stage
 constexpr int NSTAGE = 6;
 constexpr int STAGE_HALF = BM * KC * 2;  // bytes of one bf16 [128][32] operand image (8 KB)
-constexpr int NTHREADS = 288;
+constexpr int NPROD = 8;                       // producer warps
+constexpr int NTHREADS = (NPROD + 1 + 4) * 32;  // producers + MMA issuer + epilogue
 constexpr int MAX_W_BYTES = 128 * 1024;
 
 struct TcSeg {
@@ -104,6 +105,15 @@ __device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint6
         "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+__device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
@@ -181,7 +191,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) linear_tc_kernel(const TcParams p
     // ---- one-time setup ----
     if (threadIdx.x == 0) {
         for (int s = 0; s < NSTAGE; ++s) {
-            mbar_init(full_bar(s), 128);
+            mbar_init(full_bar(s), NPROD * 32);
             mbar_init(empty_bar(s), 1);
         }
         for (int a = 0; a < 2; ++a) {
@@ -190,7 +200,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) linear_tc_kernel(const TcParams p
         }
         fence_barrier_init();
     }
-    if (warp == 4) tmem_alloc(smem_u32(tmem_slot), 512);
+    if (warp == NPROD) tmem_alloc(smem_u32(tmem_slot), 512);
     // stage W (pre-packed canonical image) with plain 16-byte copies
     {
         const uint4* src = reinterpret_cast<const uint4*>(p.Wpacked);
@@ -206,59 +216,75 @@ __global__ void __launch_bounds__(NTHREADS, 1) linear_tc_kernel(const TcParams p
     const int nkb = (p.K + KC - 1) / KC;
     const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.Npad >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 
-    if (warp < 4) {
+    if (warp < NPROD) {
         // =============================== producers ===============================
+        // 16 row-groups of 8 rows per stage, 2 per warp; lane -> (row in group, 8-wide k chunk).
+        // Register double buffering: the loads of work item s+1 are in flight while item s is
+        // converted and stored, and while this warp waits for its ring slot.
+        constexpr int GPW = 16 / NPROD;  // row groups per warp per stage
         const int r8 = lane & 7, kc = lane >> 3;
+        const int64_t my_tiles = (p.num_tiles > blockIdx.x) ? (p.num_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+        const int64_t total = my_tiles * nkb;
         int stage = 0;
         uint32_t phase = 0;
-        for (int64_t tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-            const int64_t m0 = tile * BM;
-            for (int kb = 0; kb < nkb; ++kb) {
-                mbar_wait(empty_bar(stage), phase ^ 1);
-                uint8_t* st_hi = sA + stage * stage_bytes;
-                const int k = kb * KC + kc * 8;
-                float v[4][8];
+        auto fetch = [&](int64_t seq, float (&v)[GPW][8]) {
+            const int64_t tile = blockIdx.x + (seq / nkb) * gridDim.x;
+            const int kb = (int)(seq % nkb);
+            const int k = kb * KC + kc * 8;
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const int64_t m = m0 + (warp * 4 + i) * 8 + r8;
-                    if (m < p.M && k < p.K) {
-                        load8<TSrc>(p, m, k, v[i]);
-                    } else {
+            for (int i = 0; i < GPW; ++i) {
+                const int64_t m = tile * BM + (warp * GPW + i) * 8 + r8;
+                if (m < p.M && k < p.K) {
+                    load8<TSrc>(p, m, k, v[i]);
+                } else {
 #pragma unroll
-                        for (int t = 0; t < 8; ++t) v[i][t] = 0.f;
-                    }
+                    for (int t = 0; t < 8; ++t) v[i][t] = 0.f;
                 }
+            }
+        };
+        auto emit = [&](float (&v)[GPW][8]) {
+            mbar_wait(empty_bar(stage), phase ^ 1);
+            uint8_t* st_hi = sA + stage * stage_bytes;
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    if (p.act == AB2_ACT_SILU) {
+            for (int i = 0; i < GPW; ++i) {
+                if (p.act == AB2_ACT_SILU) {
 #pragma unroll
-                        for (int t = 0; t < 8; ++t) v[i][t] = silu_f(v[i][t]);
-                    }
-                    const int g = warp * 4 + i;
-                    const uint32_t off = g * (KC / 8) * 128 + kc * 128 + r8 * 16;
-                    uint32_t hi[4];
-                    float lo[8];
-#pragma unroll
-                    for (int t = 0; t < 4; ++t) {
-                        const __nv_bfloat16 h0 = __float2bfloat16_rn(v[i][2 * t]), h1 = __float2bfloat16_rn(v[i][2 * t + 1]);
-                        lo[2 * t] = v[i][2 * t] - __bfloat162float(h0);
-                        lo[2 * t + 1] = v[i][2 * t + 1] - __bfloat162float(h1);
-                        __nv_bfloat162 hh;
-                        hh.x = h0; hh.y = h1;
-                        hi[t] = *reinterpret_cast<uint32_t*>(&hh);
-                    }
-                    *reinterpret_cast<uint4*>(st_hi + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-                    if constexpr (SPLIT) {
-                        *reinterpret_cast<uint4*>(st_hi + STAGE_HALF + off) =
-                            make_uint4(pack_bf16x2(lo[0], lo[1]), pack_bf16x2(lo[2], lo[3]), pack_bf16x2(lo[4], lo[5]), pack_bf16x2(lo[6], lo[7]));
-                    }
+                    for (int t = 0; t < 8; ++t) v[i][t] = silu_f(v[i][t]);
                 }
-                fence_proxy_async();
-                mbar_arrive(full_bar(stage));
-                if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
+                const int g = warp * GPW + i;
+                const uint32_t off = g * (KC / 8) * 128 + kc * 128 + r8 * 16;
+                uint32_t hi[4];
+                float lo[8];
+#pragma unroll
+                for (int t = 0; t < 4; ++t) {
+                    const __nv_bfloat16 h0 = __float2bfloat16_rn(v[i][2 * t]), h1 = __float2bfloat16_rn(v[i][2 * t + 1]);
+                    lo[2 * t] = v[i][2 * t] - __bfloat162float(h0);
+                    lo[2 * t + 1] = v[i][2 * t + 1] - __bfloat162float(h1);
+                    __nv_bfloat162 hh;
+                    hh.x = h0; hh.y = h1;
+                    hi[t] = *reinterpret_cast<uint32_t*>(&hh);
+                }
+                *reinterpret_cast<uint4*>(st_hi + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                if constexpr (SPLIT) {
+                    *reinterpret_cast<uint4*>(st_hi + STAGE_HALF + off) =
+                        make_uint4(pack_bf16x2(lo[0], lo[1]), pack_bf16x2(lo[2], lo[3]), pack_bf16x2(lo[4], lo[5]), pack_bf16x2(lo[6], lo[7]));
+                }
+            }
+            fence_proxy_async();
+            mbar_arrive(full_bar(stage));
+            if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
+        };
+        float va[GPW][8], vb[GPW][8];
+        if (total > 0) fetch(0, va);
+        for (int64_t seq = 0; seq < total; seq += 2) {
+            if (seq + 1 < total) fetch(seq + 1, vb);
+            emit(va);
+            if (seq + 1 < total) {
+                if (seq + 2 < total) fetch(seq + 2, va);
+                emit(vb);
             }
         }
-    } else if (warp == 4) {
+    } else if (warp == NPROD) {
         // =============================== MMA issuer ===============================
         int stage = 0;
         uint32_t phase = 0;
@@ -307,56 +333,72 @@ __global__ void __launch_bounds__(NTHREADS, 1) linear_tc_kernel(const TcParams p
             tc_fence_after();
             const int64_t m = tile * BM + q * 32 + lane;
             const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * 256);
-            for (int c0 = 0; c0 < p.Npad; c0 += 16) {
-                uint32_t r[16];
-                tmem_ld16(t_row + c0, r);
-                if (m < p.M) {
-                    float v[16];
+            // two 16-column TMEM loads in flight, then the epilogue of both
+            auto process = [&](int c0, const uint32_t (&r)[16]) {
+                if (m >= p.M) return;
+                float v[16];
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
-                    if (p.epi == AB2_EPI_MUL_DSILU) {
-                        const TSrc* ax = (const TSrc*)p.aux + m * p.aux_ld + c0;
+                for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
+                if (p.epi == AB2_EPI_MUL_DSILU) {
+                    const TSrc* ax = (const TSrc*)p.aux + m * p.aux_ld + c0;
+                    if (sizeof(TSrc) == 4 && c0 + 16 <= p.N && ((reinterpret_cast<uintptr_t>(ax) & 15) == 0)) {
+                        const float4* a4 = reinterpret_cast<const float4*>(ax);
+#pragma unroll
+                        for (int t = 0; t < 4; ++t) {
+                            const float4 x = __ldg(a4 + t);
+                            v[4 * t] *= dsilu_f(x.x); v[4 * t + 1] *= dsilu_f(x.y); v[4 * t + 2] *= dsilu_f(x.z); v[4 * t + 3] *= dsilu_f(x.w);
+                        }
+                    } else {
 #pragma unroll
                         for (int j = 0; j < 16; ++j)
                             if (c0 + j < p.N) v[j] *= dsilu_f(to_acc<float>(ax[j]));
                     }
-                    // scatter the 16 columns into the output segments
-                    int seg_lo = 0;
+                }
+                // scatter the 16 columns into the output segments
+                int seg_lo = 0;
 #pragma unroll
-                    for (int s = 0; s < AB2_MAX_SEG; ++s) {
-                        if (s < p.n_o) {
-                            const int seg_hi = seg_lo + p.o[s].width;
-                            const int lo = max(seg_lo, c0), hi = min(seg_hi, min(c0 + 16, p.N));
-                            if (lo < hi) {
-                                TSrc* dst = (TSrc*)p.o[s].ptr + m * p.o[s].ld + (lo - seg_lo);
-                                const bool vec = (sizeof(TSrc) == 4) && (hi - lo == 16) && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0);
-                                if (vec) {
-                                    float4* d4 = reinterpret_cast<float4*>(dst);
+                for (int s = 0; s < AB2_MAX_SEG; ++s) {
+                    if (s < p.n_o) {
+                        const int seg_hi = seg_lo + p.o[s].width;
+                        const int lo = max(seg_lo, c0), hi = min(seg_hi, min(c0 + 16, p.N));
+                        if (lo < hi) {
+                            TSrc* dst = (TSrc*)p.o[s].ptr + m * p.o[s].ld + (lo - seg_lo);
+                            const bool vec = (sizeof(TSrc) == 4) && (hi - lo == 16) && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0);
+                            if (vec) {
+                                float4* d4 = reinterpret_cast<float4*>(dst);
 #pragma unroll
-                                    for (int t = 0; t < 4; ++t) {
-                                        float4 o4 = make_float4(v[4 * t], v[4 * t + 1], v[4 * t + 2], v[4 * t + 3]);
-                                        if (p.o[s].accum) {
-                                            const float4 old = d4[t];
-                                            o4.x += old.x; o4.y += old.y; o4.z += old.z; o4.w += old.w;
-                                        }
-                                        d4[t] = o4;
+                                for (int t = 0; t < 4; ++t) {
+                                    float4 o4 = make_float4(v[4 * t], v[4 * t + 1], v[4 * t + 2], v[4 * t + 3]);
+                                    if (p.o[s].accum) {
+                                        const float4 old = d4[t];
+                                        o4.x += old.x; o4.y += old.y; o4.z += old.z; o4.w += old.w;
                                     }
-                                } else {
+                                    d4[t] = o4;
+                                }
+                            } else {
 #pragma unroll
-                                    for (int j = 0; j < 16; ++j) {
-                                        const int n = c0 + j;
-                                        if (n >= lo && n < hi) {
-                                            float x = v[j];
-                                            if (p.o[s].accum) x += to_acc<float>(dst[n - lo]);
-                                            dst[n - lo] = from_acc<TSrc>(x);
-                                        }
+                                for (int j = 0; j < 16; ++j) {
+                                    const int n = c0 + j;
+                                    if (n >= lo && n < hi) {
+                                        float x = v[j];
+                                        if (p.o[s].accum) x += to_acc<float>(dst[n - lo]);
+                                        dst[n - lo] = from_acc<TSrc>(x);
                                     }
                                 }
                             }
-                            seg_lo = seg_hi;
                         }
+                        seg_lo = seg_hi;
                     }
                 }
+            };
+            for (int c0 = 0; c0 < p.Npad; c0 += 32) {
+                uint32_t r0[16], r1[16];
+                const bool two = c0 + 16 < p.Npad;
+                tmem_ld16_nowait(t_row + c0, r0);
+                if (two) tmem_ld16_nowait(t_row + c0 + 16, r1);
+                tmem_ld_wait();
+                process(c0, r0);
+                if (two) process(c0 + 16, r1);
             }
             tc_fence_before();
             mbar_arrive(tempty_bar(a));
@@ -365,7 +407,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) linear_tc_kernel(const TcParams p
     // ---- teardown ----
     tc_fence_before();
     __syncthreads();
-    if (warp == 4) tmem_dealloc(tmem_base, 512);
+    if (warp == NPROD) tmem_dealloc(tmem_base, 512);
 }
 
 // W[K][N] (row-major TSrc) -> canonical K-major no-swizzle bf16 images (hi, lo), Npad rows:

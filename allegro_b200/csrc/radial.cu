@@ -7,9 +7,7 @@
 //                                                                  (allegro/nn/scalarembed.py:60-66)
 //   e0[z][c] = typeemb[t_c, t_n][c] * sum_n B_n W_b[n][c]          ProductTypeEmbedding (_edgeembed.py:68-85)
 //
-// and the adjoint (g_e0 -> d/d r_z).  One warp per edge, lane = embedding column(s): the [E][S_rc]
-// rows are read/written coalesced; the 8-term radial basis is recomputed by every lane (cheap) so
-// nothing but e0 touches HBM.
+// and the adjoint (g_e0 -> d/d r_z); nothing but e0 / g_e0 touches HBM.
 #include "common.cuh"
 
 #define AB2_MAX_BESSEL 16
@@ -71,6 +69,9 @@ __device__ __forceinline__ void bessel_basis(TAcc x, TAcc p, int nb, const TAcc*
     }
 }
 
+// Block = 256 edges.  Phase 1: one thread per edge evaluates the radial basis ONCE (sin/pow are the
+// expensive part) into shared memory.  Phase 2: one warp per edge, lane = embedding column(s), so the
+// [E][S_rc] rows are written (read) with coalesced 128-byte accesses.
 template <typename TAct, typename TAcc>
 __global__ void __launch_bounds__(256) radial_fwd_kernel(int64_t E, int S_rc, int nb, TAcc p, const TAcc* __restrict__ vec,
                                                          const int32_t* __restrict__ ctr, const int32_t* __restrict__ nbr,
@@ -78,21 +79,39 @@ __global__ void __launch_bounds__(256) radial_fwd_kernel(int64_t E, int S_rc, in
                                                          int num_types, const TAcc* __restrict__ bw, const TAcc* __restrict__ Wb,
                                                          const TAcc* __restrict__ cemb, const TAcc* __restrict__ nemb,
                                                          TAct* __restrict__ e0) {
-    const int64_t z = ((int64_t)blockIdx.x * 256 + threadIdx.x) >> 5;
-    const int lane = threadIdx.x & 31;
-    if (z >= E) return;
-    const TAcc vx = vec[z * 3], vy = vec[z * 3 + 1], vz = vec[z * 3 + 2];
-    const TAcc r = sqrt(vx * vx + vy * vy + vz * vz);
-    const int tc = types[ctr[z]], tn = types[nbr[z]];
-    const TAcc x = r / rmax_table[tc * num_types + tn];
-    TAcc B[AB2_MAX_BESSEL];
-    bessel_basis<TAcc, false>(x, p, nb, bw, B, nullptr);
-    const int half = S_rc >> 1;
-    for (int c = lane; c < S_rc; c += 32) {
-        TAcc s = TAcc(0);
-        for (int n = 0; n < nb; ++n) s += B[n] * Wb[n * S_rc + c];
-        const TAcc te = (c < half) ? cemb[tc * half + c] : nemb[tn * half + (c - half)];
-        e0[z * S_rc + c] = from_acc<TAct>(te * s);
+    __shared__ TAcc sB[AB2_MAX_BESSEL][256];
+    __shared__ int s_tc[256], s_tn[256];
+    const int t = threadIdx.x;
+    const int64_t z0 = (int64_t)blockIdx.x * 256;
+    {
+        const int64_t z = z0 + t;
+        TAcc B[AB2_MAX_BESSEL];
+        int tc = 0, tn = 0;
+        if (z < E) {
+            const TAcc vx = vec[z * 3], vy = vec[z * 3 + 1], vz = vec[z * 3 + 2];
+            const TAcc r = sqrt(vx * vx + vy * vy + vz * vz);
+            tc = types[ctr[z]];
+            tn = types[nbr[z]];
+            bessel_basis<TAcc, false>(r / rmax_table[tc * num_types + tn], p, nb, bw, B, nullptr);
+        } else {
+            for (int n = 0; n < nb; ++n) B[n] = TAcc(0);
+        }
+        for (int n = 0; n < nb; ++n) sB[n][t] = B[n];
+        s_tc[t] = tc;
+        s_tn[t] = tn;
+    }
+    __syncthreads();
+    const int warp = t >> 5, lane = t & 31, half = S_rc >> 1;
+    for (int e = warp; e < 256; e += 8) {
+        const int64_t z = z0 + e;
+        if (z >= E) break;
+        const int tc = s_tc[e], tn = s_tn[e];
+        for (int c = lane; c < S_rc; c += 32) {
+            TAcc s = TAcc(0);
+            for (int n = 0; n < nb; ++n) s += sB[n][e] * Wb[n * S_rc + c];
+            const TAcc te = (c < half) ? cemb[tc * half + c] : nemb[tn * half + (c - half)];
+            e0[z * S_rc + c] = from_acc<TAct>(te * s);
+        }
     }
 }
 
@@ -103,29 +122,53 @@ __global__ void __launch_bounds__(256) radial_bwd_kernel(int64_t E, int S_rc, in
                                                          int num_types, const TAcc* __restrict__ bw, const TAcc* __restrict__ Wb,
                                                          const TAcc* __restrict__ cemb, const TAcc* __restrict__ nemb,
                                                          const TAct* __restrict__ ge0, TAcc* __restrict__ gvec) {
-    const int64_t z = ((int64_t)blockIdx.x * 256 + threadIdx.x) >> 5;
-    const int lane = threadIdx.x & 31;
-    if (z >= E) return;
-    const TAcc vx = vec[z * 3], vy = vec[z * 3 + 1], vz = vec[z * 3 + 2];
-    const TAcc r = sqrt(vx * vx + vy * vy + vz * vz);
-    const int tc = types[ctr[z]], tn = types[nbr[z]];
-    const TAcc rmax = rmax_table[tc * num_types + tn];
-    const TAcc x = r / rmax;
-    TAcc B[AB2_MAX_BESSEL], dB[AB2_MAX_BESSEL];
-    bessel_basis<TAcc, true>(x, p, nb, bw, B, dB);
-    // gB[n] = sum_c ge0[c] * te[c] * Wb[n][c];  gx = sum_n gB[n] dB[n]  -> fold: gx = sum_c ge0[c] te[c] (sum_n dB[n] Wb[n][c])
-    const int half = S_rc >> 1;
-    TAcc gx = TAcc(0);
-    for (int c = lane; c < S_rc; c += 32) {
-        TAcc s = TAcc(0);
-        for (int n = 0; n < nb; ++n) s += dB[n] * Wb[n * S_rc + c];
-        const TAcc te = (c < half) ? cemb[tc * half + c] : nemb[tn * half + (c - half)];
-        gx += to_acc<TAcc>(ge0[z * S_rc + c]) * te * s;
+    __shared__ TAcc sdB[AB2_MAX_BESSEL][256];
+    __shared__ TAcc s_gx[256];
+    __shared__ int s_tc[256], s_tn[256];
+    const int t = threadIdx.x;
+    const int64_t z0 = (int64_t)blockIdx.x * 256;
+    const int64_t zt = z0 + t;
+    TAcc vx = 0, vy = 0, vz = 0, r = 1, rmax = 1;
+    {
+        TAcc B[AB2_MAX_BESSEL], dB[AB2_MAX_BESSEL];
+        int tc = 0, tn = 0;
+        if (zt < E) {
+            vx = vec[zt * 3]; vy = vec[zt * 3 + 1]; vz = vec[zt * 3 + 2];
+            r = sqrt(vx * vx + vy * vy + vz * vz);
+            tc = types[ctr[zt]];
+            tn = types[nbr[zt]];
+            rmax = rmax_table[tc * num_types + tn];
+            bessel_basis<TAcc, true>(r / rmax, p, nb, bw, B, dB);
+        } else {
+            for (int n = 0; n < nb; ++n) dB[n] = TAcc(0);
+        }
+        for (int n = 0; n < nb; ++n) sdB[n][t] = dB[n];
+        s_tc[t] = tc;
+        s_tn[t] = tn;
     }
-    gx = warp_sum(gx);
-    if (lane < 3) {
-        const TAcc comp = lane == 0 ? vx : (lane == 1 ? vy : vz);
-        gvec[z * 3 + lane] += gx / rmax * comp / r;  // dx/dr_vec = r_vec / (|r| r_max)
+    __syncthreads();
+    // gx = sum_c ge0[c] te[c] (sum_n dB[n] Wb[n][c])
+    const int warp = t >> 5, lane = t & 31, half = S_rc >> 1;
+    for (int e = warp; e < 256; e += 8) {
+        const int64_t z = z0 + e;
+        if (z >= E) break;
+        const int tc = s_tc[e], tn = s_tn[e];
+        TAcc gx = TAcc(0);
+        for (int c = lane; c < S_rc; c += 32) {
+            TAcc s = TAcc(0);
+            for (int n = 0; n < nb; ++n) s += sdB[n][e] * Wb[n * S_rc + c];
+            const TAcc te = (c < half) ? cemb[tc * half + c] : nemb[tn * half + (c - half)];
+            gx += to_acc<TAcc>(ge0[z * S_rc + c]) * te * s;
+        }
+        gx = warp_sum(gx);
+        if (lane == 0) s_gx[e] = gx;
+    }
+    __syncthreads();
+    if (zt < E) {
+        const TAcc f = s_gx[t] / (rmax * r);  // dx/dr_vec = r_vec / (|r| r_max)
+        gvec[zt * 3] += f * vx;
+        gvec[zt * 3 + 1] += f * vy;
+        gvec[zt * 3 + 2] += f * vz;
     }
 }
 
@@ -156,7 +199,7 @@ extern "C" int ab2_radial_fwd(int dtype, int64_t E, int S_rc, int num_bessels, d
     AB2_CHECK_ARG(vec && ctr && nbr && types && rmax_table && bessel_w && Wb && center_embed && neighbor_embed && e0, "null pointer");
     AB2_CHECK_ARG(num_bessels > 0 && num_bessels <= AB2_MAX_BESSEL && S_rc > 0 && S_rc % 2 == 0, "num_bessels / embedding dim");
     cudaStream_t st = (cudaStream_t)stream;
-    AB2_DISPATCH_DTYPE(dtype, radial_fwd_kernel<TAct, TAcc><<<ab2_blocks(E * 32, 256), 256, 0, st>>>(
+    AB2_DISPATCH_DTYPE(dtype, radial_fwd_kernel<TAct, TAcc><<<ab2_blocks(E, 256), 256, 0, st>>>(
                                   E, S_rc, num_bessels, (TAcc)p_cut, (const TAcc*)vec, ctr, nbr, types, (const TAcc*)rmax_table, num_types,
                                   (const TAcc*)bessel_w, (const TAcc*)Wb, (const TAcc*)center_embed, (const TAcc*)neighbor_embed, (TAct*)e0));
     AB2_CUDA_LAUNCH_CHECK();
@@ -171,7 +214,7 @@ extern "C" int ab2_radial_bwd(int dtype, int64_t E, int S_rc, int num_bessels, d
     AB2_CHECK_ARG(vec && ctr && nbr && types && rmax_table && bessel_w && Wb && center_embed && neighbor_embed && g_e0 && gvec, "null pointer");
     AB2_CHECK_ARG(num_bessels > 0 && num_bessels <= AB2_MAX_BESSEL && S_rc > 0 && S_rc % 2 == 0, "num_bessels / embedding dim");
     cudaStream_t st = (cudaStream_t)stream;
-    AB2_DISPATCH_DTYPE(dtype, radial_bwd_kernel<TAct, TAcc><<<ab2_blocks(E * 32, 256), 256, 0, st>>>(
+    AB2_DISPATCH_DTYPE(dtype, radial_bwd_kernel<TAct, TAcc><<<ab2_blocks(E, 256), 256, 0, st>>>(
                                   E, S_rc, num_bessels, (TAcc)p_cut, (const TAcc*)vec, ctr, nbr, types, (const TAcc*)rmax_table, num_types,
                                   (const TAcc*)bessel_w, (const TAcc*)Wb, (const TAcc*)center_embed, (const TAcc*)neighbor_embed,
                                   (const TAct*)g_e0, (TAcc*)gvec));

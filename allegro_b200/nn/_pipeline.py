@@ -162,7 +162,7 @@ class AllegroCore:
                 _lib.tp_bwd(dt, self.lmax, N, E, U, ly["d_in"], ly["d_out"], ly["tab"], ly["cgw"], csr.row_ptr, csr.ctr,
                             sv.gamma[l], sv.V[l], None, None, gV_next, gV_in, None, None, ggamma)
             gomega = torch.empty(E, self.nw, dtype=dt, device=dev)
-            _lib.env_bwd(dt, self.lmax, U, csr.ctr, sv.Y, sv.omega[l], ggamma, self.sf, gomega, gY)
+            _lib.env_bwd(dt, self.lmax, U, csr.ctr, sv.Y, sv.omega[l], ggamma, self.sf, gomega, gY, row_ptr=csr.row_ptr)
             gV_next, gomega_next = gV_in, gomega
         _lib.set_tag("bwd.embed")
         gx_emb = torch.empty(E, self.S_in, dtype=dt, device=dev)

@@ -130,8 +130,16 @@ def run_ours(args, rank: int, world: int):
     dtype = args.dtype or systems.CONFIGS[cfg]["dtype"]
     model, data, d_cpu, kw, n_atoms, n_edges = build_workload(cfg, dtype, dev)
     K, W = args.steps, args.warmup
+    graphed = None
+    if not args.no_graph:
+        from allegro_b200.graph import GraphedEnergyForces
+
+        graphed = GraphedEnergyForces(model, data)
 
     def step():
+        return graphed() if graphed is not None else model(data)
+
+    def step_eager():
         return model(data)
 
     for _ in range(W):
@@ -155,7 +163,7 @@ def run_ours(args, rank: int, world: int):
     _lib.PROF.reset()
     _lib.PROF.enabled = True
     for _ in range(K):
-        out = step()
+        out = step_eager()
     times = _lib.PROF.times_ms()
     _lib.PROF.enabled = False
     # ---- leg 3: end to end through the public API with HOST buffers ----
@@ -165,8 +173,11 @@ def run_ours(args, rank: int, world: int):
     data_e2e = dict(data)
 
     def step_e2e():
-        data_e2e[D.POSITIONS_KEY] = pos_host.to(dev, non_blocking=True)
-        o = model(data_e2e)
+        if graphed is not None:
+            o = graphed(pos_host)  # H2D of the positions into the graph's static buffer, then replay
+        else:
+            data_e2e[D.POSITIONS_KEY] = pos_host.to(dev, non_blocking=True)
+            o = model(data_e2e)
         f_host.copy_(o[D.FORCE_KEY], non_blocking=True)
         e_host.copy_(o[D.TOTAL_ENERGY_KEY], non_blocking=True)
 
@@ -209,7 +220,7 @@ def run_ours(args, rank: int, world: int):
         "dtype": {"float64": "f64", "float32": "f32", "bfloat16": "bf16"}[dtype], "data": "synthetic",
         "config": {"workload": f"{cfg}: {systems.CONFIGS[cfg]['system']}, {n_atoms} atoms, {n_edges} edges, l_max={kw['l_max']}, "
                                f"n_layers={kw['num_layers']}, S={kw['num_scalar_features']}, U={kw['num_tensor_features']}, r_max={kw['r_max']}",
-                   "global_atoms": n_atoms, "parallelism": "1 GPU", "timing": "CUDA events, inputs larger than L2 (per-step working set "
+                   "global_atoms": n_atoms, "parallelism": "1 GPU", "cuda_graph": graphed is not None, "timing": "CUDA events, inputs larger than L2 (per-step working set "
                    f"~{n_edges * 5e3 / 1e9:.1f} GB >> 126 MB L2), neighbour list resident"},
         "ns_per_day_at_1fs": 1e3 / ms * 0.0864,
         "clocks": clocks,
@@ -389,6 +400,7 @@ def main():
     ap.add_argument("--config", default="c2")
     ap.add_argument("--dtype", default=None, choices=[None, "float64", "float32", "bfloat16"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="launch every kernel from Python instead of replaying a CUDA graph")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))

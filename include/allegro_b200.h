@@ -104,9 +104,9 @@ int ab2_env_sum(int dtype, int lmax, int64_t N, int U, const int32_t* row_ptr, c
 /* Adjoint of ab2_env_sum given ggamma[N][d][U]:
  *   gw[z][r][u] = sf * sum_{j in r} Y[z][j] ggamma[c][j][u]
  *   gY[z][j]   += sf * sum_u w[z][irrep(j)][u] ggamma[c][j][u]     (appendix B steps 3-4) */
-int ab2_env_bwd(int dtype, int lmax, int64_t E, int U, const int32_t* ctr, const void* Y,
-                const void* w, int64_t w_ld, const void* ggamma, double sf, void* gw,
-                int64_t gw_ld, void* gY, void* stream);
+int ab2_env_bwd(int dtype, int lmax, int64_t N, int64_t E, int U, const int32_t* row_ptr,
+                const int32_t* ctr, const void* Y, const void* w, int64_t w_ld, const void* ggamma,
+                double sf, void* gw, int64_t gw_ld, void* gY, void* stream);
 
 /* _contract.py:205-251 for one layer on the fused layout (a8, a10):
  *   Vout[z][k][u] = sum_i Vin[z][i][u] * M_c[u][i][k],

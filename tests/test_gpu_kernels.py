@@ -140,7 +140,8 @@ def test_linear_tensor_core_path(dtype, shape, mode):
 @pytest.mark.parametrize("lmax", [1, 2, 3])
 @pytest.mark.parametrize("U", [4, 32, 48])
 @pytest.mark.parametrize("dtype", [torch.float64, torch.float32, torch.bfloat16])
-def test_env_sum_and_bwd(lmax, U, dtype):
+@pytest.mark.parametrize("fastpath", [True, False])
+def test_env_sum_and_bwd(lmax, U, dtype, fastpath):
     N, E = 37, 600
     csr, ctr = _csr_random(N, E, seed=U)
     g = torch.Generator().manual_seed(lmax * 10 + U)
@@ -168,7 +169,8 @@ def test_env_sum_and_bwd(lmax, U, dtype):
     gY_ref, gw_ref = torch.autograd.grad(loss, (Yt, wt))
     gw = torch.zeros(E, n_ir * U + 1, device=DEV, dtype=dtype)
     gY = torch.ones(E, Dd, device=DEV, dtype=acc)
-    _lib.env_bwd(dtype, lmax, U, csr.ctr, Y.to(DEV, acc), wbuf.to(DEV, dtype)[:, 2 : 2 + n_ir * U], gg.to(DEV, acc), sf, gw[:, 1:], gY)
+    _lib.env_bwd(dtype, lmax, U, csr.ctr, Y.to(DEV, acc), wbuf.to(DEV, dtype)[:, 2 : 2 + n_ir * U], gg.to(DEV, acc), sf, gw[:, 1:], gY,
+                 row_ptr=csr.row_ptr if fastpath else None)
     tol = {torch.float64: 1e-12, torch.float32: 1e-5, torch.bfloat16: 1e-2}[dtype]
     assert _rel(gw[:, 1:], gw_ref) < tol
     assert _rel(gY - 1.0, gY_ref) < (1e-5 if dtype != torch.float64 else 1e-12)
