@@ -79,46 +79,6 @@ __global__ void __launch_bounds__(128) env_bwd_kernel(int64_t E, int U, const in
     }
 }
 
-// Reduce D (<=16) per-lane values across the warp with a multi-value butterfly: 16 shuffles instead
-// of 5*D.  On return lane 2*j (and 2*j+1) holds the warp total of value j.
-template <typename TAcc, int D>
-__device__ __forceinline__ TAcc warp_multi_sum(const TAcc (&v)[D], int lane) {
-    static_assert(D <= 16, "at most 16 values");
-    TAcc a[16];
-#pragma unroll
-    for (int t = 0; t < 16; ++t) a[t] = t < D ? v[t] : TAcc(0);
-    TAcc b[8];
-#pragma unroll
-    for (int t = 0; t < 8; ++t) {
-        const bool up = lane & 16;
-        const TAcc send = up ? a[t] : a[t + 8];
-        const TAcc got = __shfl_xor_sync(0xffffffffu, send, 16);
-        b[t] = (up ? a[t + 8] : a[t]) + got;
-    }
-    TAcc c[4];
-#pragma unroll
-    for (int t = 0; t < 4; ++t) {
-        const bool up = lane & 8;
-        const TAcc send = up ? b[t] : b[t + 4];
-        const TAcc got = __shfl_xor_sync(0xffffffffu, send, 8);
-        c[t] = (up ? b[t + 4] : b[t]) + got;
-    }
-    TAcc d[2];
-#pragma unroll
-    for (int t = 0; t < 2; ++t) {
-        const bool up = lane & 4;
-        const TAcc send = up ? c[t] : c[t + 2];
-        const TAcc got = __shfl_xor_sync(0xffffffffu, send, 4);
-        d[t] = (up ? c[t + 2] : c[t]) + got;
-    }
-    const bool up = lane & 2;
-    const TAcc send = up ? d[0] : d[1];
-    const TAcc got = __shfl_xor_sync(0xffffffffu, send, 2);
-    TAcc e = (up ? d[1] : d[0]) + got;
-    e += __shfl_xor_sync(0xffffffffu, e, 1);
-    return e;  // value index = lane >> 1
-}
-
 // Warp per (centre, 32-channel chunk): ggamma[c][.][u] is loaded once into registers and the
 // centre's edges are streamed (two in flight).  Same arithmetic as env_bwd_kernel.
 template <typename TAct, typename TAcc, int LMAX>

@@ -29,7 +29,9 @@ namespace {
 
 constexpr int BM = 128;       // rows per tile = UMMA M
 constexpr int KC = 32;        // k per ring stage
-constexpr int NSTAGE = 6;
+constexpr int NSTAGE = 6;        // max ring stages (run-time count p.nstage <= NSTAGE)
+constexpr int EPI_LD = 36;       // floats per staged row (32 + 4 pad): conflict-free 16-byte accesses
+constexpr int EPI_BYTES = 4 * 32 * EPI_LD * 4;  // 4 epilogue warps x 32 rows
 constexpr int STAGE_HALF = BM * KC * 2;  // bytes of one bf16 [128][32] operand image (8 KB)
 constexpr int NPROD = 8;                       // producer warps
 constexpr int NTHREADS = (NPROD + 1 + 4) * 32;  // producers + MMA issuer + epilogue
@@ -55,6 +57,7 @@ struct TcParams {
     const void* aux;
     int64_t aux_ld;
     int64_t num_tiles;
+    int nstage;
 };
 
 // ---- PTX wrappers ---------------------------------------------------------------------
@@ -179,7 +182,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) linear_tc_kernel(const TcParams p
     uint8_t* sW = smem;
     uint8_t* sA = smem + ((w_bytes + 127) & ~127);
     const int stage_bytes = SPLIT ? 2 * STAGE_HALF : STAGE_HALF;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sA + NSTAGE * stage_bytes);
+    float* sEpi = reinterpret_cast<float*>(sA + p.nstage * stage_bytes);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(sEpi) + EPI_BYTES);
     // bars: full[NSTAGE], empty[NSTAGE], tmem_full[2], tmem_empty[2]; then the TMEM base word
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NSTAGE + 4);
     const uint32_t bar0 = smem_u32(bars);
@@ -272,7 +276,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) linear_tc_kernel(const TcParams p
             }
             fence_proxy_async();
             mbar_arrive(full_bar(stage));
-            if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
+            if (++stage == p.nstage) { stage = 0; phase ^= 1; }
         };
         float va[GPW][8], vb[GPW][8];
         if (total > 0) fetch(0, va);
@@ -319,7 +323,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) linear_tc_kernel(const TcParams p
                     if (kb == nkb - 1) umma_commit(tfull_bar(a));   // accumulator complete
                 }
                 __syncwarp();
-                if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
+                if (++stage == p.nstage) { stage = 0; phase ^= 1; }
             }
         }
     } else {
@@ -391,14 +395,68 @@ __global__ void __launch_bounds__(NTHREADS, 1) linear_tc_kernel(const TcParams p
                     }
                 }
             };
+            float* stg = sEpi + (warp & 3) * 32 * EPI_LD;
+            const int64_t m_base = tile * BM + q * 32;
             for (int c0 = 0; c0 < p.Npad; c0 += 32) {
                 uint32_t r0[16], r1[16];
                 const bool two = c0 + 16 < p.Npad;
                 tmem_ld16_nowait(t_row + c0, r0);
                 if (two) tmem_ld16_nowait(t_row + c0 + 16, r1);
                 tmem_ld_wait();
-                process(c0, r0);
-                if (two) process(c0 + 16, r1);
+                // coalesced path: the 32-column chunk lies inside one fp32 output segment, 16-byte aligned
+                int seg = -1, seg_lo = 0;
+                if (sizeof(TSrc) == 4 && two && c0 + 32 <= p.N) {
+                    int lo = 0;
+#pragma unroll
+                    for (int s2 = 0; s2 < AB2_MAX_SEG; ++s2) {
+                        if (s2 < p.n_o) {
+                            if (c0 >= lo && c0 + 32 <= lo + p.o[s2].width) { seg = s2; seg_lo = lo; }
+                            lo += p.o[s2].width;
+                        }
+                    }
+                    if (seg >= 0) {
+                        const uintptr_t base = reinterpret_cast<uintptr_t>((const float*)p.o[seg].ptr + (c0 - seg_lo));
+                        if ((base & 15) || ((p.o[seg].ld * 4) & 15)) seg = -1;
+                        if (p.epi == AB2_EPI_MUL_DSILU &&
+                            ((reinterpret_cast<uintptr_t>((const float*)p.aux + c0) & 15) || ((p.aux_ld * 4) & 15))) seg = -1;
+                    }
+                }
+                if (seg >= 0) {
+                    // stage my row (lane) : 32 floats -> shared, then every global access covers 4 rows x 128 B
+                    float4* srow = reinterpret_cast<float4*>(stg + lane * EPI_LD);
+#pragma unroll
+                    for (int t = 0; t < 4; ++t) {
+                        srow[t] = make_float4(__uint_as_float(r0[4 * t]), __uint_as_float(r0[4 * t + 1]), __uint_as_float(r0[4 * t + 2]), __uint_as_float(r0[4 * t + 3]));
+                        srow[4 + t] = make_float4(__uint_as_float(r1[4 * t]), __uint_as_float(r1[4 * t + 1]), __uint_as_float(r1[4 * t + 2]), __uint_as_float(r1[4 * t + 3]));
+                    }
+                    __syncwarp();
+                    const int rsub = lane >> 3, c4 = lane & 7;
+                    float* obase = (float*)p.o[seg].ptr + (c0 - seg_lo) + c4 * 4;
+                    const float* abase = (const float*)p.aux + c0 + c4 * 4;
+                    const int acc = p.o[seg].accum;
+#pragma unroll
+                    for (int itr = 0; itr < 8; ++itr) {
+                        const int row = itr * 4 + rsub;
+                        const int64_t mr = m_base + row;
+                        if (mr < p.M) {
+                            float4 x = *reinterpret_cast<const float4*>(stg + row * EPI_LD + c4 * 4);
+                            if (p.epi == AB2_EPI_MUL_DSILU) {
+                                const float4 ax = __ldg(reinterpret_cast<const float4*>(abase + mr * p.aux_ld));
+                                x.x *= dsilu_f(ax.x); x.y *= dsilu_f(ax.y); x.z *= dsilu_f(ax.z); x.w *= dsilu_f(ax.w);
+                            }
+                            float4* dst = reinterpret_cast<float4*>(obase + mr * p.o[seg].ld);
+                            if (acc) {
+                                const float4 old = *dst;
+                                x.x += old.x; x.y += old.y; x.z += old.z; x.w += old.w;
+                            }
+                            *dst = x;
+                        }
+                    }
+                    __syncwarp();
+                } else {
+                    process(c0, r0);
+                    if (two) process(c0 + 16, r1);
+                }
             }
             tc_fence_before();
             mbar_arrive(tempty_bar(a));
@@ -481,8 +539,14 @@ int ab2_linear_tc_try(int dtype, int64_t M, int K, int N, int n_a, const void* c
     const bool split = dtype == AB2_F32;
     const int w_bytes = p.Npad * K * 2 * (split ? 2 : 1);
     const int stage_bytes = STAGE_HALF * (split ? 2 : 1);
-    const size_t smem = ((w_bytes + 127) & ~127) + (size_t)NSTAGE * stage_bytes + (2 * NSTAGE + 4) * 8 + 16;
-    if ((int)smem > max_smem) return -1;
+    int nstage = NSTAGE;
+    size_t smem = 0;
+    for (; nstage >= 3; --nstage) {
+        smem = ((w_bytes + 127) & ~127) + (size_t)nstage * stage_bytes + EPI_BYTES + (2 * NSTAGE + 4) * 8 + 16;
+        if ((int)smem <= max_smem) break;
+    }
+    if (nstage < 3) return -1;
+    p.nstage = nstage;
     const unsigned grid = (unsigned)((p.num_tiles < num_sms) ? p.num_tiles : num_sms);
     cudaError_t e;
     if (split) {

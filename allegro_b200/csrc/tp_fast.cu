@@ -96,8 +96,8 @@ __global__ void __launch_bounds__(128) tp_fwd_fast_kernel(int64_t N, int U, int 
     }
 }
 
-template <typename TAct, typename TAcc, int D_IN, int D_OUT, int DG, bool IMPLICIT>
-__global__ void __launch_bounds__(128) tp_bwd_fast_kernel(int64_t N, int U, int D, int nnz, const int32_t* __restrict__ tabp,
+template <typename TAct, typename TAcc, int D_IN, int D_OUT, int DG, bool IMPLICIT, bool GM_ONLY>
+__global__ void __launch_bounds__(128, GM_ONLY ? 3 : 1) tp_bwd_fast_kernel(int64_t N, int U, int D, int nnz, const int32_t* __restrict__ tabp,
                                                           const TAcc* __restrict__ cgw, const int32_t* __restrict__ row_ptr,
                                                           const TAcc* __restrict__ gamma, const TAct* __restrict__ Vin,
                                                           const TAcc* __restrict__ Y, const TAct* __restrict__ w0, int64_t w0_ld,
@@ -114,24 +114,32 @@ __global__ void __launch_bounds__(128) tp_bwd_fast_kernel(int64_t N, int U, int 
     const bool live = u < U;
     const int beg = row_ptr[c], end = row_ptr[c + 1];
     WarpSmem<TAcc, D_IN, D_OUT, DG>& sm = smem[warp];
-    TAcc M[D_IN][D_OUT], gM[D_IN][D_OUT];
-    build_M<TAcc, D_IN, D_OUT, DG>(M, sm, lane, nnz, tabp, cgw, U, u, live, gamma + c * D * U);
+    TAcc M[GM_ONLY ? 1 : D_IN][GM_ONLY ? 1 : D_OUT], gM[D_IN][D_OUT];
+    if constexpr (!GM_ONLY) build_M<TAcc, D_IN, D_OUT, DG>(M, sm, lane, nnz, tabp, cgw, U, u, live, gamma + c * D * U);
 #pragma unroll
     for (int i = 0; i < D_IN; ++i)
 #pragma unroll
         for (int k = 0; k < D_OUT; ++k) gM[i][k] = TAcc(0);
+#pragma unroll(GM_ONLY ? 2 : 1)
     for (int64_t z = beg; z < end; ++z) {
         TAcc v[D_IN], w0l[5], Yz[D_IN], go[D_OUT];
         load_vin<TAct, TAcc, D_IN, IMPLICIT>(v, w0l, Yz, z, U, u, live, Vin, Y, w0, w0_ld);
 #pragma unroll
         for (int k = 0; k < D_OUT; ++k) go[k] = live ? to_acc<TAcc>(gVout[(z * D_OUT + k) * U + u]) : TAcc(0);
+        if constexpr (GM_ONLY) {
+#pragma unroll
+            for (int i = 0; i < D_IN; ++i)
+#pragma unroll
+                for (int k = 0; k < D_OUT; ++k) gM[i][k] += v[i] * go[k];
+            continue;
+        }
         TAcc gin[D_IN];
 #pragma unroll
         for (int i = 0; i < D_IN; ++i) {
             TAcc s = TAcc(0);
 #pragma unroll
             for (int k = 0; k < D_OUT; ++k) {
-                s += M[i][k] * go[k];
+                if constexpr (!GM_ONLY) s += M[i][k] * go[k];
                 gM[i][k] += v[i] * go[k];
             }
             gin[i] = s;
@@ -178,6 +186,13 @@ __global__ void __launch_bounds__(128) tp_bwd_fast_kernel(int64_t N, int U, int 
 template <typename TAct, typename TAcc, int D_IN, int D_OUT, int DG>
 int launch_fwd(int64_t N, int U, int D, int nnz, const int32_t* tabp, const void* cgw, const int32_t* row_ptr, const void* gamma,
                const void* Vin, int implicit_v0, const void* Y, const void* w0, int64_t w0_ld, void* Vout, cudaStream_t st) {
+    {
+        const int dt = sizeof(TAct) == 4 ? AB2_F32 : AB2_BF16;
+        if (g_ab2_opt_tp_fast >= 1 && g_ab2_opt_tp_fast != 2 &&
+            ab2_tp_smem(0, dt, N, U, D, D_IN, D_OUT, nnz, tabp, cgw, row_ptr, gamma, Vin, implicit_v0, Y, w0, w0_ld, Vout, nullptr, nullptr,
+                        nullptr, 0, nullptr, st) == 0)
+            return 0;
+    }
     const int64_t warps = N * ((U + 31) / 32);
     const unsigned grid = ab2_blocks(warps, 4);
     if (implicit_v0) {
@@ -201,16 +216,38 @@ int launch_bwd(int64_t N, int U, int D, int nnz, const int32_t* tabp, const void
                void* gw0, int64_t gw0_ld, void* gY, void* ggamma, cudaStream_t st) {
     const int64_t warps = N * ((U + 31) / 32);
     const unsigned grid = ab2_blocks(warps, 4);
+    if constexpr (D_IN * D_OUT >= 49) {
+        // big M: split the backward.  A) gin / gw0 / gY with M in shared memory (tp_smem.cu, high occupancy);
+        //                             B) gM -> ggamma with only gM in registers (this file).
+        const int dt = sizeof(TAct) == 4 ? AB2_F32 : AB2_BF16;
+        if (g_ab2_opt_tp_fast != 2 &&
+            ab2_tp_smem(1, dt, N, U, D, D_IN, D_OUT, nnz, tabp, cgw, row_ptr, gamma, Vin, implicit_v0, Y, w0, w0_ld, nullptr, gVout, gVin,
+                        gw0, gw0_ld, gY, st) == 0) {
+            if (implicit_v0) {
+                if constexpr (D_IN == 1 || D_IN == 4 || D_IN == 9 || D_IN == 16) {
+                    tp_bwd_fast_kernel<TAct, TAcc, D_IN, D_OUT, DG, true, true><<<grid, 128, 0, st>>>(
+                        N, U, D, nnz, tabp, (const TAcc*)cgw, row_ptr, (const TAcc*)gamma, nullptr, (const TAcc*)Y, (const TAct*)w0, w0_ld,
+                        (const TAct*)gVout, nullptr, nullptr, 0, nullptr, (TAcc*)ggamma);
+                    return 0;
+                }
+            } else {
+                tp_bwd_fast_kernel<TAct, TAcc, D_IN, D_OUT, DG, false, true><<<grid, 128, 0, st>>>(
+                    N, U, D, nnz, tabp, (const TAcc*)cgw, row_ptr, (const TAcc*)gamma, (const TAct*)Vin, nullptr, nullptr, 0,
+                    (const TAct*)gVout, nullptr, nullptr, 0, nullptr, (TAcc*)ggamma);
+                return 0;
+            }
+        }
+    }
     if (implicit_v0) {
         if constexpr (D_IN == 1 || D_IN == 4 || D_IN == 9 || D_IN == 16) {
-            tp_bwd_fast_kernel<TAct, TAcc, D_IN, D_OUT, DG, true><<<grid, 128, 0, st>>>(
+            tp_bwd_fast_kernel<TAct, TAcc, D_IN, D_OUT, DG, true, false><<<grid, 128, 0, st>>>(
                 N, U, D, nnz, tabp, (const TAcc*)cgw, row_ptr, (const TAcc*)gamma, nullptr, (const TAcc*)Y, (const TAct*)w0, w0_ld,
                 (const TAct*)gVout, nullptr, (TAct*)gw0, gw0_ld, (TAcc*)gY, (TAcc*)ggamma);
         } else {
             return -1;
         }
     } else {
-        tp_bwd_fast_kernel<TAct, TAcc, D_IN, D_OUT, DG, false><<<grid, 128, 0, st>>>(
+        tp_bwd_fast_kernel<TAct, TAcc, D_IN, D_OUT, DG, false, false><<<grid, 128, 0, st>>>(
             N, U, D, nnz, tabp, (const TAcc*)cgw, row_ptr, (const TAcc*)gamma, (const TAct*)Vin, nullptr, nullptr, 0,
             (const TAct*)gVout, (TAct*)gVin, nullptr, 0, nullptr, (TAcc*)ggamma);
     }

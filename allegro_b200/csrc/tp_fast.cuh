@@ -14,4 +14,9 @@ int ab2_tp_bwd_fast(int dtype, int64_t N, int U, int D, int d_in, int d_out, int
                     const int32_t* row_ptr, const void* gamma, const void* Vin, int implicit_v0, const void* Y, const void* w0,
                     int64_t w0_ld, const void* gVout, void* gVin, void* gw0, int64_t gw0_ld, void* gY, void* ggamma, cudaStream_t st);
 
-extern int g_ab2_opt_tp_fast;
+// shared-memory-M kernels (tp_smem.cu): mode 0 forward, mode 1 backward part A (gin / gw0 / gY)
+int ab2_tp_smem(int mode, int dtype, int64_t N, int U, int D, int d_in, int d_out, int nnz, const int32_t* tab, const void* cgw,
+                const int32_t* row_ptr, const void* gamma, const void* Vin, int implicit_v0, const void* Y, const void* w0,
+                int64_t w0_ld, void* Vout, const void* gVout, void* gVin, void* gw0, int64_t gw0_ld, void* gY, cudaStream_t st);
+
+extern int g_ab2_opt_tp_fast;  // 0 generic, 1 fast (smem-M fwd, split bwd), 2 register-M kernels only

@@ -193,7 +193,7 @@ def _tp_case(lmax, layer, L, U, coupling, dtype, seed=0):
     return c, b
 
 
-@pytest.fixture(params=[1, 0], ids=["fast", "generic"])
+@pytest.fixture(params=[1, 2, 0], ids=["fast", "regM", "generic"])
 def tp_fast(request):
     _lib.set_option("tp_fast", request.param)
     yield request.param
