@@ -29,7 +29,9 @@ namespace {
 
 constexpr int BM = 128;       // rows per tile = UMMA M
 constexpr int KC = 32;        // k per ring stage
-constexpr int NSTAGE = 6;        // max ring stages (run-time count p.nstage <= NSTAGE)
+constexpr int NSTAGE = 4;        // max ring stages (run-time count p.nstage <= NSTAGE)
+constexpr int RAW_DEPTH = 4;     // cp.async stages in flight per producer thread
+constexpr int RAW_STAGE = 256 * 4 * 16;  // bytes: 256 producer threads x 4 x 16-byte chunks
 constexpr int EPI_LD = 36;       // floats per staged row (32 + 4 pad): conflict-free 16-byte accesses
 constexpr int EPI_BYTES = 4 * 32 * EPI_LD * 4;  // 4 epilogue warps x 32 rows
 constexpr int STAGE_HALF = BM * KC * 2;  // bytes of one bf16 [128][32] operand image (8 KB)
@@ -127,6 +129,26 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+__device__ __forceinline__ void cp_async16(uint32_t dst_smem, const void* src, uint32_t src_bytes) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst_smem), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// global address of concat columns [k, k+8) of row m (nullptr if outside K)
+template <typename TSrc>
+__device__ __forceinline__ const TSrc* seg_ptr(const TcParams& p, int64_t m, int k) {
+#pragma unroll
+    for (int s = 0; s < AB2_MAX_SEG; ++s) {
+        if (s < p.n_a) {
+            if (k < p.a[s].width) return (const TSrc*)p.a[s].ptr + m * p.a[s].ld + k;
+            k -= p.a[s].width;
+        }
+    }
+    return nullptr;
+}
+
 // shared-memory matrix descriptor: K-major, SWIZZLE_NONE, 8x16B core matrices.
 // canonical layout (16-byte units) ((8,n),2):((1,SBO),LBO): LBO = byte distance between core
 // matrices adjacent in K, SBO = between 8-row groups.
@@ -182,7 +204,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) linear_tc_kernel(const TcParams p
     uint8_t* sW = smem;
     uint8_t* sA = smem + ((w_bytes + 127) & ~127);
     const int stage_bytes = SPLIT ? 2 * STAGE_HALF : STAGE_HALF;
-    float* sEpi = reinterpret_cast<float*>(sA + p.nstage * stage_bytes);
+    uint8_t* sRaw = sA + p.nstage * stage_bytes;
+    float* sEpi = reinterpret_cast<float*>(sRaw + RAW_DEPTH * RAW_STAGE);
     uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(sEpi) + EPI_BYTES);
     // bars: full[NSTAGE], empty[NSTAGE], tmem_full[2], tmem_empty[2]; then the TMEM base word
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NSTAGE + 4);
@@ -231,18 +254,45 @@ __global__ void __launch_bounds__(NTHREADS, 1) linear_tc_kernel(const TcParams p
         const int64_t total = my_tiles * nkb;
         int stage = 0;
         uint32_t phase = 0;
+        constexpr int CH = (sizeof(TSrc) == 4) ? 2 : 1;  // 16-byte chunks per 8 elements
+        const uint32_t raw_u = smem_u32(sRaw);
+        // issue the asynchronous copies of work item `seq` into this thread's private raw slot
+        auto issue = [&](int64_t seq) {
+            if (seq < total) {
+                const int64_t tile = blockIdx.x + (seq / nkb) * gridDim.x;
+                const int kb = (int)(seq % nkb);
+                const int k = kb * KC + kc * 8;
+                const int slot = (int)(seq % RAW_DEPTH);
+#pragma unroll
+                for (int i = 0; i < GPW; ++i) {
+                    const int64_t m = tile * BM + (warp * GPW + i) * 8 + r8;
+                    const TSrc* src = (m < p.M && k < p.K) ? seg_ptr<TSrc>(p, m, k) : nullptr;
+#pragma unroll
+                    for (int h = 0; h < CH; ++h) {
+                        const uint32_t dst = raw_u + (uint32_t)(((slot * 4 + i * CH + h) * 256 + threadIdx.x) * 16);
+                        const void* g = src ? (const void*)(reinterpret_cast<const uint8_t*>(src) + 16 * h) : p.Wpacked;
+                        cp_async16(dst, g, src ? 16u : 0u);  // src-size 0 -> zero fill
+                    }
+                }
+            }
+            cp_async_commit();  // always commit so that group counting stays uniform
+        };
         auto fetch = [&](int64_t seq, float (&v)[GPW][8]) {
-            const int64_t tile = blockIdx.x + (seq / nkb) * gridDim.x;
-            const int kb = (int)(seq % nkb);
-            const int k = kb * KC + kc * 8;
+            const int slot = (int)(seq % RAW_DEPTH);
 #pragma unroll
             for (int i = 0; i < GPW; ++i) {
-                const int64_t m = tile * BM + (warp * GPW + i) * 8 + r8;
-                if (m < p.M && k < p.K) {
-                    load8<TSrc>(p, m, k, v[i]);
+                if constexpr (sizeof(TSrc) == 4) {
+                    const float4 x = *reinterpret_cast<const float4*>(sRaw + ((slot * 4 + i * 2 + 0) * 256 + threadIdx.x) * 16);
+                    const float4 y = *reinterpret_cast<const float4*>(sRaw + ((slot * 4 + i * 2 + 1) * 256 + threadIdx.x) * 16);
+                    v[i][0] = x.x; v[i][1] = x.y; v[i][2] = x.z; v[i][3] = x.w; v[i][4] = y.x; v[i][5] = y.y; v[i][6] = y.z; v[i][7] = y.w;
                 } else {
+                    const uint4 x = *reinterpret_cast<const uint4*>(sRaw + ((slot * 4 + i) * 256 + threadIdx.x) * 16);
+                    const __nv_bfloat162* hh = reinterpret_cast<const __nv_bfloat162*>(&x);
 #pragma unroll
-                    for (int t = 0; t < 8; ++t) v[i][t] = 0.f;
+                    for (int t = 0; t < 4; ++t) {
+                        const float2 f = __bfloat1622float2(hh[t]);
+                        v[i][2 * t] = f.x; v[i][2 * t + 1] = f.y;
+                    }
                 }
             }
         };
@@ -278,16 +328,17 @@ __global__ void __launch_bounds__(NTHREADS, 1) linear_tc_kernel(const TcParams p
             mbar_arrive(full_bar(stage));
             if (++stage == p.nstage) { stage = 0; phase ^= 1; }
         };
-        float va[GPW][8], vb[GPW][8];
-        if (total > 0) fetch(0, va);
-        for (int64_t seq = 0; seq < total; seq += 2) {
-            if (seq + 1 < total) fetch(seq + 1, vb);
-            emit(va);
-            if (seq + 1 < total) {
-                if (seq + 2 < total) fetch(seq + 2, va);
-                emit(vb);
-            }
+        static_assert(GPW == 2, "raw slot layout assumes 2 row groups per producer warp");
+#pragma unroll
+        for (int d = 0; d < RAW_DEPTH; ++d) issue(d);
+        for (int64_t seq = 0; seq < total; ++seq) {
+            cp_async_wait<RAW_DEPTH - 1>();  // the oldest group (= item seq) has landed
+            float v[GPW][8];
+            fetch(seq, v);
+            issue(seq + RAW_DEPTH);           // refill the slot just drained
+            emit(v);
         }
+        cp_async_wait<0>();
     } else if (warp == NPROD) {
         // =============================== MMA issuer ===============================
         int stage = 0;
@@ -434,22 +485,31 @@ __global__ void __launch_bounds__(NTHREADS, 1) linear_tc_kernel(const TcParams p
                     float* obase = (float*)p.o[seg].ptr + (c0 - seg_lo) + c4 * 4;
                     const float* abase = (const float*)p.aux + c0 + c4 * 4;
                     const int acc = p.o[seg].accum;
+                    // all dependent global loads first (8 rows in flight), then compute + store
+                    float4 ax[8], old[8];
+                    const bool epi = p.epi == AB2_EPI_MUL_DSILU;
+                    const int64_t old_ld = p.o[seg].ld;
+#pragma unroll
+                    for (int itr = 0; itr < 8; ++itr) {
+                        const int64_t mr = m_base + itr * 4 + rsub;
+                        if (mr < p.M) {
+                            if (epi) ax[itr] = __ldg(reinterpret_cast<const float4*>(abase + mr * p.aux_ld));
+                            if (acc) old[itr] = *reinterpret_cast<const float4*>(obase + mr * old_ld);
+                        }
+                    }
 #pragma unroll
                     for (int itr = 0; itr < 8; ++itr) {
                         const int row = itr * 4 + rsub;
                         const int64_t mr = m_base + row;
                         if (mr < p.M) {
                             float4 x = *reinterpret_cast<const float4*>(stg + row * EPI_LD + c4 * 4);
-                            if (p.epi == AB2_EPI_MUL_DSILU) {
-                                const float4 ax = __ldg(reinterpret_cast<const float4*>(abase + mr * p.aux_ld));
-                                x.x *= dsilu_f(ax.x); x.y *= dsilu_f(ax.y); x.z *= dsilu_f(ax.z); x.w *= dsilu_f(ax.w);
+                            if (epi) {
+                                x.x *= dsilu_f(ax[itr].x); x.y *= dsilu_f(ax[itr].y); x.z *= dsilu_f(ax[itr].z); x.w *= dsilu_f(ax[itr].w);
                             }
-                            float4* dst = reinterpret_cast<float4*>(obase + mr * p.o[seg].ld);
                             if (acc) {
-                                const float4 old = *dst;
-                                x.x += old.x; x.y += old.y; x.z += old.z; x.w += old.w;
+                                x.x += old[itr].x; x.y += old[itr].y; x.z += old[itr].z; x.w += old[itr].w;
                             }
-                            *dst = x;
+                            *reinterpret_cast<float4*>(obase + mr * old_ld) = x;
                         }
                     }
                     __syncwarp();
@@ -541,11 +601,11 @@ int ab2_linear_tc_try(int dtype, int64_t M, int K, int N, int n_a, const void* c
     const int stage_bytes = STAGE_HALF * (split ? 2 : 1);
     int nstage = NSTAGE;
     size_t smem = 0;
-    for (; nstage >= 3; --nstage) {
-        smem = ((w_bytes + 127) & ~127) + (size_t)nstage * stage_bytes + EPI_BYTES + (2 * NSTAGE + 4) * 8 + 16;
+    for (; nstage >= 2; --nstage) {
+        smem = ((w_bytes + 127) & ~127) + (size_t)nstage * stage_bytes + RAW_DEPTH * RAW_STAGE + EPI_BYTES + (2 * NSTAGE + 4) * 8 + 16;
         if ((int)smem <= max_smem) break;
     }
-    if (nstage < 3) return -1;
+    if (nstage < 2) return -1;
     p.nstage = nstage;
     const unsigned grid = (unsigned)((p.num_tiles < num_sms) ? p.num_tiles : num_sms);
     cudaError_t e;
