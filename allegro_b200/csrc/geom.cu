@@ -16,12 +16,14 @@ void ab2_set_error(const char* fmt, ...) {
 
 int g_ab2_opt_tp_fast = 1;
 int g_ab2_opt_linear_tc = 1;
+int g_ab2_opt_tc_debug = 0;
 
 extern "C" const char* ab2_last_error(void) { return g_err; }
 extern "C" int ab2_set_option(const char* key, int value) {
     if (!key) return 1;
     if (!strcmp(key, "tp_fast")) { g_ab2_opt_tp_fast = value; return 0; }
     if (!strcmp(key, "linear_tc")) { g_ab2_opt_linear_tc = value; return 0; }
+    if (!strcmp(key, "tc_debug")) { g_ab2_opt_tc_debug = value; return 0; }
     ab2_set_error("unknown option %s", key);
     return 1;
 }

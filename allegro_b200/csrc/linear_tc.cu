@@ -24,6 +24,7 @@
 #include "common.cuh"
 
 extern int g_ab2_opt_linear_tc;
+extern int g_ab2_opt_tc_debug;  // bit0: no epilogue global stores, bit1: no producer global loads, bit2: no MMA issue
 
 namespace {
 
@@ -60,6 +61,7 @@ struct TcParams {
     int64_t aux_ld;
     int64_t num_tiles;
     int nstage;
+    int debug;
 };
 
 // ---- PTX wrappers ---------------------------------------------------------------------
@@ -70,6 +72,11 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
 }
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+// arrive without release ordering of this thread's earlier global stores (the consumer only needs
+// the tcgen05 / shared-memory effects, which are ordered by the explicit fences)
+__device__ __forceinline__ void mbar_arrive_relaxed(uint32_t bar) {
+    asm volatile("mbarrier.arrive.relaxed.cta.shared::cta.b64 _, [%0];" ::"r"(bar));
 }
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     asm volatile(
@@ -159,6 +166,15 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes
     d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
     d |= (uint64_t)1 << 46;  // descriptor version (Blackwell)
     return d;                // base_offset = 0, lbo_mode = 0, layout_type = 0 (SWIZZLE_NONE)
+}
+
+// branch-free SiLU and SiLU' (MUFU ex2 / rcp, ~2 ulp): IEEE division has a slow-path branch that
+// serialises the unrolled epilogue / producer loops.
+__device__ __forceinline__ float sigmoid_fast(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
+__device__ __forceinline__ float silu_fast(float x) { return x * sigmoid_fast(x); }
+__device__ __forceinline__ float dsilu_fast(float x) {
+    const float sg = sigmoid_fast(x);
+    return sg * (1.f + x * (1.f - sg));
 }
 
 __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
@@ -266,7 +282,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) linear_tc_kernel(const TcParams p
 #pragma unroll
                 for (int i = 0; i < GPW; ++i) {
                     const int64_t m = tile * BM + (warp * GPW + i) * 8 + r8;
-                    const TSrc* src = (m < p.M && k < p.K) ? seg_ptr<TSrc>(p, m, k) : nullptr;
+                    const TSrc* src = (m < p.M && k < p.K && !(p.debug & 2)) ? seg_ptr<TSrc>(p, m, k) : nullptr;
 #pragma unroll
                     for (int h = 0; h < CH; ++h) {
                         const uint32_t dst = raw_u + (uint32_t)(((slot * 4 + i * CH + h) * 256 + threadIdx.x) * 16);
@@ -303,7 +319,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) linear_tc_kernel(const TcParams p
             for (int i = 0; i < GPW; ++i) {
                 if (p.act == AB2_ACT_SILU) {
 #pragma unroll
-                    for (int t = 0; t < 8; ++t) v[i][t] = silu_f(v[i][t]);
+                    for (int t = 0; t < 8; ++t) v[i][t] = silu_fast(v[i][t]);
                 }
                 const int g = warp * GPW + i;
                 const uint32_t off = g * (KC / 8) * 128 + kc * 128 + r8 * 16;
@@ -358,7 +374,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) linear_tc_kernel(const TcParams p
                 if (lane == 0) {
                     const uint32_t a_hi = smem_u32(sA + stage * stage_bytes);
                     const int ksteps = min(2, (p.K - kb * KC) / 16);
-                    for (int ks = 0; ks < ksteps; ++ks) {
+                    for (int ks = 0; ks < ((p.debug & 4) ? 0 : ksteps); ++ks) {
                         const uint64_t da_hi = make_desc(a_hi + ks * 256, 128, (KC / 8) * 128);
                         const uint32_t wk = sW_u + (uint32_t)(kb * (KC / 8) + ks * 2) * 128;
                         const uint64_t db_hi = make_desc(wk, 128, w_sbo);
@@ -456,7 +472,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) linear_tc_kernel(const TcParams p
                 tmem_ld_wait();
                 // coalesced path: the 32-column chunk lies inside one fp32 output segment, 16-byte aligned
                 int seg = -1, seg_lo = 0;
-                if (sizeof(TSrc) == 4 && two && c0 + 32 <= p.N) {
+                if (sizeof(TSrc) == 4 && two && c0 + 32 <= p.N && !(p.debug & 64)) {
                     int lo = 0;
 #pragma unroll
                     for (int s2 = 0; s2 < AB2_MAX_SEG; ++s2) {
@@ -472,7 +488,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) linear_tc_kernel(const TcParams p
                             ((reinterpret_cast<uintptr_t>((const float*)p.aux + c0) & 15) || ((p.aux_ld * 4) & 15))) seg = -1;
                     }
                 }
-                if (seg >= 0) {
+                if (p.debug & 1) {
+                } else if (seg >= 0) {
                     // stage my row (lane) : 32 floats -> shared, then every global access covers 4 rows x 128 B
                     float4* srow = reinterpret_cast<float4*>(stg + lane * EPI_LD);
 #pragma unroll
@@ -485,33 +502,44 @@ __global__ void __launch_bounds__(NTHREADS, 1) linear_tc_kernel(const TcParams p
                     float* obase = (float*)p.o[seg].ptr + (c0 - seg_lo) + c4 * 4;
                     const float* abase = (const float*)p.aux + c0 + c4 * 4;
                     const int acc = p.o[seg].accum;
-                    // all dependent global loads first (8 rows in flight), then compute + store
-                    float4 ax[8], old[8];
+                    // 1) all shared-memory reads, 2) (uniform) epilogue variants with all global loads
+                    //    issued before use, 3) predicated 4-rows-x-128-B stores.
                     const bool epi = p.epi == AB2_EPI_MUL_DSILU;
                     const int64_t old_ld = p.o[seg].ld;
+                    float4 x[8];
+                    bool ok[8];
+                    int64_t mrc[8];  // row index clamped into range: loads are unconditional (no divergence)
 #pragma unroll
                     for (int itr = 0; itr < 8; ++itr) {
+                        x[itr] = *reinterpret_cast<const float4*>(stg + (itr * 4 + rsub) * EPI_LD + c4 * 4);
                         const int64_t mr = m_base + itr * 4 + rsub;
-                        if (mr < p.M) {
-                            if (epi) ax[itr] = __ldg(reinterpret_cast<const float4*>(abase + mr * p.aux_ld));
-                            if (acc) old[itr] = *reinterpret_cast<const float4*>(obase + mr * old_ld);
+                        ok[itr] = mr < p.M;
+                        mrc[itr] = ok[itr] ? mr : p.M - 1;
+                    }
+                    if (epi) {
+                        float4 ax[8];
+#pragma unroll
+                        for (int itr = 0; itr < 8; ++itr)
+                            ax[itr] = __ldg(reinterpret_cast<const float4*>(abase + mrc[itr] * p.aux_ld));
+#pragma unroll
+                        for (int itr = 0; itr < 8; ++itr) {
+                            x[itr].x *= dsilu_fast(ax[itr].x); x[itr].y *= dsilu_fast(ax[itr].y);
+                            x[itr].z *= dsilu_fast(ax[itr].z); x[itr].w *= dsilu_fast(ax[itr].w);
+                        }
+                    }
+                    if (acc) {
+                        float4 old[8];
+#pragma unroll
+                        for (int itr = 0; itr < 8; ++itr)
+                            old[itr] = *reinterpret_cast<const float4*>(obase + mrc[itr] * old_ld);
+#pragma unroll
+                        for (int itr = 0; itr < 8; ++itr) {
+                            x[itr].x += old[itr].x; x[itr].y += old[itr].y; x[itr].z += old[itr].z; x[itr].w += old[itr].w;
                         }
                     }
 #pragma unroll
-                    for (int itr = 0; itr < 8; ++itr) {
-                        const int row = itr * 4 + rsub;
-                        const int64_t mr = m_base + row;
-                        if (mr < p.M) {
-                            float4 x = *reinterpret_cast<const float4*>(stg + row * EPI_LD + c4 * 4);
-                            if (epi) {
-                                x.x *= dsilu_f(ax[itr].x); x.y *= dsilu_f(ax[itr].y); x.z *= dsilu_f(ax[itr].z); x.w *= dsilu_f(ax[itr].w);
-                            }
-                            if (acc) {
-                                x.x += old[itr].x; x.y += old[itr].y; x.z += old[itr].z; x.w += old[itr].w;
-                            }
-                            *reinterpret_cast<float4*>(obase + mr * old_ld) = x;
-                        }
-                    }
+                    for (int itr = 0; itr < 8; ++itr)
+                        if (ok[itr]) *reinterpret_cast<float4*>(obase + mrc[itr] * old_ld) = x[itr];
                     __syncwarp();
                 } else {
                     process(c0, r0);
@@ -519,7 +547,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) linear_tc_kernel(const TcParams p
                 }
             }
             tc_fence_before();
-            mbar_arrive(tempty_bar(a));
+            if (p.debug & 8) mbar_arrive(tempty_bar(a));
+            else mbar_arrive_relaxed(tempty_bar(a));
         }
     }
     // ---- teardown ----
@@ -607,6 +636,7 @@ int ab2_linear_tc_try(int dtype, int64_t M, int K, int N, int n_a, const void* c
     }
     if (nstage < 2) return -1;
     p.nstage = nstage;
+    p.debug = g_ab2_opt_tc_debug;
     const unsigned grid = (unsigned)((p.num_tiles < num_sms) ? p.num_tiles : num_sms);
     cudaError_t e;
     if (split) {
