@@ -183,6 +183,67 @@ __global__ void __launch_bounds__(128, GM_ONLY ? 3 : 1) tp_bwd_fast_kernel(int64
     }
 }
 
+// Backward part B with the gM accumulators split over NS warps of one CTA (warp s owns input
+// components i in [s*IW, (s+1)*IW)): IW*D_OUT accumulators per thread instead of D_IN*D_OUT, so
+// ~60 registers and 3-4x the resident warps of the monolithic kernel.  One CTA = one (centre,
+// 32-channel chunk); the CG contraction gM -> ggamma is done once by warp 0 after a block barrier.
+template <typename TAct, typename TAcc, int D_IN, int D_OUT, int DG, bool IMPLICIT, int NS>
+__global__ void __launch_bounds__(NS * 32, 8) tp_bwd_gm_split_kernel(int64_t N, int U, int D, int nnz, const int32_t* __restrict__ tabp,
+                                                                     const TAcc* __restrict__ cgw, const int32_t* __restrict__ row_ptr,
+                                                                     const TAct* __restrict__ Vin, const TAcc* __restrict__ Y,
+                                                                     const TAct* __restrict__ w0, int64_t w0_ld,
+                                                                     const TAct* __restrict__ gVout, TAcc* __restrict__ ggamma) {
+    constexpr int IW = D_IN / NS;
+    static_assert(IW * NS == D_IN, "D_IN must be divisible by the split");
+    __shared__ TAcc sGM[D_IN * D_OUT][32];
+    __shared__ TAcc sG[DG][32];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nchunk = (U + 31) >> 5;
+    const int64_t c = blockIdx.x / nchunk;
+    const int u = (int)(blockIdx.x % nchunk) * 32 + lane;
+    const bool live = u < U;
+    const int beg = row_ptr[c], end = row_ptr[c + 1];
+    const int i0 = warp * IW;
+    TAcc gM[IW][D_OUT];
+#pragma unroll
+    for (int i = 0; i < IW; ++i)
+#pragma unroll
+        for (int k = 0; k < D_OUT; ++k) gM[i][k] = TAcc(0);
+#pragma unroll 2
+    for (int64_t z = beg; z < end; ++z) {
+        TAcc go[D_OUT], v[IW];
+#pragma unroll
+        for (int k = 0; k < D_OUT; ++k) go[k] = live ? to_acc<TAcc>(gVout[(z * D_OUT + k) * U + u]) : TAcc(0);
+#pragma unroll
+        for (int i = 0; i < IW; ++i) {
+            if constexpr (IMPLICIT) {
+                v[i] = live ? Y[z * D_IN + i0 + i] * to_acc<TAcc>(w0[z * w0_ld + sh_l_of(i0 + i) * U + u]) : TAcc(0);
+            } else {
+                v[i] = live ? to_acc<TAcc>(Vin[(z * D_IN + i0 + i) * U + u]) : TAcc(0);
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < IW; ++i)
+#pragma unroll
+            for (int k = 0; k < D_OUT; ++k) gM[i][k] += v[i] * go[k];
+    }
+#pragma unroll
+    for (int i = 0; i < IW; ++i)
+#pragma unroll
+        for (int k = 0; k < D_OUT; ++k) sGM[(i0 + i) * D_OUT + k][lane] = gM[i][k];
+    __syncthreads();
+    if (warp == 0) {
+        for (int j = 0; j < D; ++j) sG[j][lane] = TAcc(0);
+        if (live) {
+            for (int n = 0; n < nnz; ++n) {
+                const int i = tabp[3 * n], j = tabp[3 * n + 1], k = tabp[3 * n + 2];
+                sG[j][lane] += cgw[(int64_t)n * U + u] * sGM[i * D_OUT + k][lane];
+            }
+            for (int j = 0; j < D; ++j) ggamma[(c * D + j) * U + u] = sG[j][lane];
+        }
+    }
+}
+
 template <typename TAct, typename TAcc, int D_IN, int D_OUT, int DG>
 int launch_fwd(int64_t N, int U, int D, int nnz, const int32_t* tabp, const void* cgw, const int32_t* row_ptr, const void* gamma,
                const void* Vin, int implicit_v0, const void* Y, const void* w0, int64_t w0_ld, void* Vout, cudaStream_t st) {
@@ -223,17 +284,18 @@ int launch_bwd(int64_t N, int U, int D, int nnz, const int32_t* tabp, const void
         if (g_ab2_opt_tp_fast != 2 &&
             ab2_tp_smem(1, dt, N, U, D, D_IN, D_OUT, nnz, tabp, cgw, row_ptr, gamma, Vin, implicit_v0, Y, w0, w0_ld, nullptr, gVout, gVin,
                         gw0, gw0_ld, gY, st) == 0) {
+            constexpr int NS = (D_IN % 3 == 0) ? 3 : ((D_IN % 2 == 0) ? 2 : 1);
+            const unsigned gridB = (unsigned)(N * ((U + 31) / 32));
             if (implicit_v0) {
                 if constexpr (D_IN == 1 || D_IN == 4 || D_IN == 9 || D_IN == 16) {
-                    tp_bwd_fast_kernel<TAct, TAcc, D_IN, D_OUT, DG, true, true><<<grid, 128, 0, st>>>(
-                        N, U, D, nnz, tabp, (const TAcc*)cgw, row_ptr, (const TAcc*)gamma, nullptr, (const TAcc*)Y, (const TAct*)w0, w0_ld,
-                        (const TAct*)gVout, nullptr, nullptr, 0, nullptr, (TAcc*)ggamma);
+                    tp_bwd_gm_split_kernel<TAct, TAcc, D_IN, D_OUT, DG, true, NS><<<gridB, NS * 32, 0, st>>>(
+                        N, U, D, nnz, tabp, (const TAcc*)cgw, row_ptr, nullptr, (const TAcc*)Y, (const TAct*)w0, w0_ld, (const TAct*)gVout,
+                        (TAcc*)ggamma);
                     return 0;
                 }
             } else {
-                tp_bwd_fast_kernel<TAct, TAcc, D_IN, D_OUT, DG, false, true><<<grid, 128, 0, st>>>(
-                    N, U, D, nnz, tabp, (const TAcc*)cgw, row_ptr, (const TAcc*)gamma, (const TAct*)Vin, nullptr, nullptr, 0,
-                    (const TAct*)gVout, nullptr, nullptr, 0, nullptr, (TAcc*)ggamma);
+                tp_bwd_gm_split_kernel<TAct, TAcc, D_IN, D_OUT, DG, false, NS><<<gridB, NS * 32, 0, st>>>(
+                    N, U, D, nnz, tabp, (const TAcc*)cgw, row_ptr, (const TAct*)Vin, nullptr, nullptr, 0, (const TAct*)gVout, (TAcc*)ggamma);
                 return 0;
             }
         }

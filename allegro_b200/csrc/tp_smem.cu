@@ -17,17 +17,23 @@
 
 namespace {
 
-constexpr int CPB = 4;  // centres per CTA
+constexpr int CPB = 3;  // centres per CTA
+
+template <typename T>
+struct alignas(4 * sizeof(T)) Vec4 {
+    T v[4];
+};
 
 template <typename TAct, typename TAcc, int D_IN, int D_OUT, bool IMPLICIT, int MODE>
-__global__ void __launch_bounds__(256, 3) tp_smem_kernel(int64_t N, int U, int D, int nnz, const int32_t* __restrict__ tab,
+__global__ void __launch_bounds__(256, 2) tp_smem_kernel(int64_t N, int U, int D, int nnz, const int32_t* __restrict__ tab,
                                                       const TAcc* __restrict__ cgw, const int32_t* __restrict__ row_ptr,
                                                       const TAcc* __restrict__ gamma, const TAct* __restrict__ Vin,
                                                       const TAcc* __restrict__ Y, const TAct* __restrict__ w0, int64_t w0_ld,
                                                       TAct* __restrict__ Vout, const TAct* __restrict__ gVout,
                                                       TAct* __restrict__ gVin, TAct* __restrict__ gw0, int64_t gw0_ld,
                                                       TAcc* __restrict__ gY) {
-    __shared__ TAcc sM[CPB][D_IN * D_OUT][32];
+    constexpr int KQ = (D_OUT + 3) / 4;  // output components in groups of 4 -> one 16-byte LDS per (i, group)
+    __shared__ Vec4<TAcc> sM[CPB][D_IN * KQ][32];
     __shared__ int s_rp[CPB + 1];
     const int tid = threadIdx.x;
     const int64_t c0 = (int64_t)blockIdx.x * CPB;
@@ -40,12 +46,15 @@ __global__ void __launch_bounds__(256, 3) tp_smem_kernel(int64_t N, int U, int D
         const int64_t c = c0 + cc;
         const int u = u0 + lu;
 #pragma unroll
-        for (int e = 0; e < D_IN * D_OUT; ++e) sM[cc][e][lu] = TAcc(0);
+        for (int e = 0; e < D_IN * KQ; ++e) {
+#pragma unroll
+            for (int t = 0; t < 4; ++t) sM[cc][e][lu].v[t] = TAcc(0);
+        }
         if (c < N && u < U) {
             const TAcc* __restrict__ g = gamma + c * D * U + u;
             for (int n = 0; n < nnz; ++n) {
                 const int i = tab[3 * n], j = tab[3 * n + 1], k = tab[3 * n + 2];
-                sM[cc][i * D_OUT + k][lu] += cgw[(int64_t)n * U + u] * g[(int64_t)j * U];
+                sM[cc][i * KQ + (k >> 2)][lu].v[k & 3] += cgw[(int64_t)n * U + u] * g[(int64_t)j * U];
             }
         }
     }
@@ -54,7 +63,6 @@ __global__ void __launch_bounds__(256, 3) tp_smem_kernel(int64_t N, int U, int D
     const int u = u0 + lane;
     const bool live = u < U;
     const int e_beg = s_rp[0], e_end = s_rp[CPB];
-#pragma unroll 2
     for (int64_t z = e_beg + warp; z < e_end; z += 8) {
         int cc = 0;
 #pragma unroll
@@ -77,7 +85,12 @@ __global__ void __launch_bounds__(256, 3) tp_smem_kernel(int64_t N, int U, int D
 #pragma unroll
             for (int i = 0; i < D_IN; ++i)
 #pragma unroll
-                for (int k = 0; k < D_OUT; ++k) out[k] += v[i] * sM[cc][i * D_OUT + k][lane];
+                for (int kq = 0; kq < KQ; ++kq) {
+                    const Vec4<TAcc> m4 = sM[cc][i * KQ + kq][lane];
+#pragma unroll
+                    for (int t = 0; t < 4; ++t)
+                        if (kq * 4 + t < D_OUT) out[kq * 4 + t] += v[i] * m4.v[t];
+                }
             if (live) {
 #pragma unroll
                 for (int k = 0; k < D_OUT; ++k) Vout[(z * D_OUT + k) * U + u] = from_acc<TAct>(out[k]);
@@ -91,7 +104,12 @@ __global__ void __launch_bounds__(256, 3) tp_smem_kernel(int64_t N, int U, int D
             for (int i = 0; i < D_IN; ++i) {
                 TAcc s = TAcc(0);
 #pragma unroll
-                for (int k = 0; k < D_OUT; ++k) s += sM[cc][i * D_OUT + k][lane] * go[k];
+                for (int kq = 0; kq < KQ; ++kq) {
+                    const Vec4<TAcc> m4 = sM[cc][i * KQ + kq][lane];
+#pragma unroll
+                    for (int t = 0; t < 4; ++t)
+                        if (kq * 4 + t < D_OUT) s += m4.v[t] * go[kq * 4 + t];
+                }
                 gin[i] = s;
             }
             if constexpr (IMPLICIT) {
@@ -145,7 +163,7 @@ int launch(int64_t N, int U, int D, int nnz, const int32_t* tab, const void* cgw
     return 0;
 }
 
-// shapes whose M (CPB * D_IN*D_OUT * 32 floats) fits the 48 KB static shared-memory limit
+// shapes whose M (CPB * D_IN * ceil(D_OUT/4)*4 * 32 floats) fits the 48 KB static shared-memory limit
 #define AB2_SMEM_SHAPES(X) X(4, 4, 4) X(4, 1, 4) X(9, 9, 9) X(9, 1, 9) X(16, 1, 16) X(7, 4, 4) X(4, 7, 4) X(7, 7, 4) X(7, 1, 4)
 
 }  // namespace
