@@ -78,7 +78,7 @@ __global__ void __launch_bounds__(128) tp_fwd_fast_kernel(int64_t N, int U, int 
     if (beg == end) return;
     TAcc M[D_IN][D_OUT];
     build_M<TAcc, D_IN, D_OUT, DG>(M, smem[warp], lane, nnz, tabp, cgw, U, u, live, gamma + c * D * U);
-#pragma unroll 2
+#pragma unroll(IMPLICIT ? 4 : 2)
     for (int64_t z = beg; z < end; ++z) {
         TAcc v[D_IN], w0l[5], Yz[D_IN];
         load_vin<TAct, TAcc, D_IN, IMPLICIT>(v, w0l, Yz, z, U, u, live, Vin, Y, w0, w0_ld);

@@ -15,6 +15,8 @@
 #include "common.cuh"
 #include "tp_fast.cuh"
 
+extern int g_ab2_opt_tp_variant;
+
 namespace {
 
 constexpr int CPB = 3;  // centres per CTA
@@ -24,8 +26,8 @@ struct alignas(4 * sizeof(T)) Vec4 {
     T v[4];
 };
 
-template <typename TAct, typename TAcc, int D_IN, int D_OUT, bool IMPLICIT, int MODE>
-__global__ void __launch_bounds__(256, 2) tp_smem_kernel(int64_t N, int U, int D, int nnz, const int32_t* __restrict__ tab,
+template <typename TAct, typename TAcc, int D_IN, int D_OUT, bool IMPLICIT, int MODE, int MINB>
+__global__ void __launch_bounds__(256, MINB) tp_smem_kernel(int64_t N, int U, int D, int nnz, const int32_t* __restrict__ tab,
                                                       const TAcc* __restrict__ cgw, const int32_t* __restrict__ row_ptr,
                                                       const TAcc* __restrict__ gamma, const TAct* __restrict__ Vin,
                                                       const TAcc* __restrict__ Y, const TAct* __restrict__ w0, int64_t w0_ld,
@@ -62,111 +64,149 @@ __global__ void __launch_bounds__(256, 2) tp_smem_kernel(int64_t N, int U, int D
     const int warp = tid >> 5, lane = tid & 31;
     const int u = u0 + lane;
     const bool live = u < U;
-    const int e_beg = s_rp[0], e_end = s_rp[CPB];
-    for (int64_t z = e_beg + warp; z < e_end; z += 8) {
-        int cc = 0;
+    // EPT consecutive edges of ONE centre per warp-item: every 16-byte LDS of M feeds EPT edges, which
+    // divides the shared-memory traffic (the limiter with one edge per item) by EPT.
+    constexpr int EPT = 1;
+    for (int cc = 0; cc < CPB; ++cc) {
+        const int e_beg = s_rp[cc], e_end = s_rp[cc + 1];
+        for (int64_t z0 = e_beg + warp * EPT; z0 < e_end; z0 += 8 * EPT) {
+            bool ok[EPT];
+            int64_t zz[EPT];
 #pragma unroll
-        for (int t = 1; t < CPB; ++t) cc += (z >= s_rp[t]) ? 1 : 0;
-        if constexpr (MODE == 0) {
-            TAcc v[D_IN];
-            if constexpr (IMPLICIT) {
-                TAcc w0l[5];
-#pragma unroll
-                for (int l = 0; l * l < D_IN; ++l) w0l[l] = live ? to_acc<TAcc>(w0[z * w0_ld + l * U + u]) : TAcc(0);
-#pragma unroll
-                for (int i = 0; i < D_IN; ++i) v[i] = Y[z * D_IN + i] * w0l[sh_l_of(i)];
-            } else {
-#pragma unroll
-                for (int i = 0; i < D_IN; ++i) v[i] = live ? to_acc<TAcc>(Vin[(z * D_IN + i) * U + u]) : TAcc(0);
+            for (int e = 0; e < EPT; ++e) {
+                ok[e] = (z0 + e) < e_end;
+                zz[e] = ok[e] ? z0 + e : z0;  // clamp: loads stay in range, stores are predicated
             }
-            TAcc out[D_OUT];
+            if constexpr (MODE == 0) {
+                TAcc v[EPT][D_IN];
 #pragma unroll
-            for (int k = 0; k < D_OUT; ++k) out[k] = TAcc(0);
+                for (int e = 0; e < EPT; ++e) {
+                    const int64_t z = zz[e];
+                    if constexpr (IMPLICIT) {
+                        TAcc w0l[5];
 #pragma unroll
-            for (int i = 0; i < D_IN; ++i)
+                        for (int l = 0; l * l < D_IN; ++l) w0l[l] = live ? to_acc<TAcc>(w0[z * w0_ld + l * U + u]) : TAcc(0);
 #pragma unroll
-                for (int kq = 0; kq < KQ; ++kq) {
-                    const Vec4<TAcc> m4 = sM[cc][i * KQ + kq][lane];
+                        for (int i = 0; i < D_IN; ++i) v[e][i] = Y[z * D_IN + i] * w0l[sh_l_of(i)];
+                    } else {
 #pragma unroll
-                    for (int t = 0; t < 4; ++t)
-                        if (kq * 4 + t < D_OUT) out[kq * 4 + t] += v[i] * m4.v[t];
-                }
-            if (live) {
-#pragma unroll
-                for (int k = 0; k < D_OUT; ++k) Vout[(z * D_OUT + k) * U + u] = from_acc<TAct>(out[k]);
-            }
-        } else {
-            TAcc go[D_OUT];
-#pragma unroll
-            for (int k = 0; k < D_OUT; ++k) go[k] = live ? to_acc<TAcc>(gVout[(z * D_OUT + k) * U + u]) : TAcc(0);
-            TAcc gin[D_IN];
-#pragma unroll
-            for (int i = 0; i < D_IN; ++i) {
-                TAcc s = TAcc(0);
-#pragma unroll
-                for (int kq = 0; kq < KQ; ++kq) {
-                    const Vec4<TAcc> m4 = sM[cc][i * KQ + kq][lane];
-#pragma unroll
-                    for (int t = 0; t < 4; ++t)
-                        if (kq * 4 + t < D_OUT) s += m4.v[t] * go[kq * 4 + t];
-                }
-                gin[i] = s;
-            }
-            if constexpr (IMPLICIT) {
-                TAcc Yz[D_IN], w0l[5], part[D_IN];
-#pragma unroll
-                for (int i = 0; i < D_IN; ++i) Yz[i] = Y[z * D_IN + i];
-#pragma unroll
-                for (int l = 0; l * l < D_IN; ++l) {
-                    w0l[l] = live ? to_acc<TAcc>(w0[z * w0_ld + l * U + u]) : TAcc(0);
-                    TAcc s = TAcc(0);
-#pragma unroll
-                    for (int i = l * l; i < (l + 1) * (l + 1); ++i) {
-                        s += Yz[i] * gin[i];
-                        part[i] = w0l[l] * gin[i];
+                        for (int i = 0; i < D_IN; ++i) v[e][i] = live ? to_acc<TAcc>(Vin[(z * D_IN + i) * U + u]) : TAcc(0);
                     }
-                    if (live) gw0[z * gw0_ld + l * U + u] = from_acc<TAct>(s);
                 }
-                const TAcc tot = warp_multi_sum<TAcc, D_IN>(part, lane);
-                const int j = lane >> 1;
-                if (!(lane & 1) && j < D_IN) {
-                    if (nchunk == 1) gY[z * D_IN + j] += tot;  // single writer per (z, j)
-                    else atomicAdd(&gY[z * D_IN + j], tot);
-                }
-            } else {
-                if (live) {
+                TAcc out[EPT][D_OUT];
 #pragma unroll
-                    for (int i = 0; i < D_IN; ++i) gVin[(z * D_IN + i) * U + u] = from_acc<TAct>(gin[i]);
+                for (int e = 0; e < EPT; ++e)
+#pragma unroll
+                    for (int k = 0; k < D_OUT; ++k) out[e][k] = TAcc(0);
+#pragma unroll
+                for (int i = 0; i < D_IN; ++i)
+#pragma unroll
+                    for (int kq = 0; kq < KQ; ++kq) {
+                        const Vec4<TAcc> m4 = sM[cc][i * KQ + kq][lane];
+#pragma unroll
+                        for (int t = 0; t < 4; ++t)
+                            if (kq * 4 + t < D_OUT) {
+#pragma unroll
+                                for (int e = 0; e < EPT; ++e) out[e][kq * 4 + t] += v[e][i] * m4.v[t];
+                            }
+                    }
+#pragma unroll
+                for (int e = 0; e < EPT; ++e)
+                    if (live && ok[e]) {
+#pragma unroll
+                        for (int k = 0; k < D_OUT; ++k) Vout[(zz[e] * D_OUT + k) * U + u] = from_acc<TAct>(out[e][k]);
+                    }
+            } else {
+                TAcc go[EPT][D_OUT];
+#pragma unroll
+                for (int e = 0; e < EPT; ++e)
+#pragma unroll
+                    for (int k = 0; k < D_OUT; ++k) go[e][k] = live ? to_acc<TAcc>(gVout[(zz[e] * D_OUT + k) * U + u]) : TAcc(0);
+                TAcc gin[EPT][D_IN];
+#pragma unroll
+                for (int i = 0; i < D_IN; ++i) {
+                    TAcc s[EPT];
+#pragma unroll
+                    for (int e = 0; e < EPT; ++e) s[e] = TAcc(0);
+#pragma unroll
+                    for (int kq = 0; kq < KQ; ++kq) {
+                        const Vec4<TAcc> m4 = sM[cc][i * KQ + kq][lane];
+#pragma unroll
+                        for (int t = 0; t < 4; ++t)
+                            if (kq * 4 + t < D_OUT) {
+#pragma unroll
+                                for (int e = 0; e < EPT; ++e) s[e] += m4.v[t] * go[e][kq * 4 + t];
+                            }
+                    }
+#pragma unroll
+                    for (int e = 0; e < EPT; ++e) gin[e][i] = s[e];
+                }
+#pragma unroll
+                for (int e = 0; e < EPT; ++e) {
+                    const int64_t z = zz[e];
+                    if constexpr (IMPLICIT) {
+                        TAcc part[D_IN];
+#pragma unroll
+                        for (int l = 0; l * l < D_IN; ++l) {
+                            const TAcc w0l = live ? to_acc<TAcc>(w0[z * w0_ld + l * U + u]) : TAcc(0);
+                            TAcc s = TAcc(0);
+#pragma unroll
+                            for (int i = l * l; i < (l + 1) * (l + 1); ++i) {
+                                s += Y[z * D_IN + i] * gin[e][i];
+                                part[i] = w0l * gin[e][i];
+                            }
+                            if (live && ok[e]) gw0[z * gw0_ld + l * U + u] = from_acc<TAct>(s);
+                        }
+                        const TAcc tot = warp_multi_sum<TAcc, D_IN>(part, lane);
+                        const int j = lane >> 1;
+                        if (ok[e] && !(lane & 1) && j < D_IN) {
+                            if (nchunk == 1) gY[z * D_IN + j] += tot;  // single writer per (z, j)
+                            else atomicAdd(&gY[z * D_IN + j], tot);
+                        }
+                    } else {
+                        if (live && ok[e]) {
+#pragma unroll
+                            for (int i = 0; i < D_IN; ++i) gVin[(z * D_IN + i) * U + u] = from_acc<TAct>(gin[e][i]);
+                        }
+                    }
                 }
             }
         }
     }
 }
 
-template <typename TAct, typename TAcc, int D_IN, int D_OUT, int MODE>
-int launch(int64_t N, int U, int D, int nnz, const int32_t* tab, const void* cgw, const int32_t* row_ptr, const void* gamma,
+template <typename TAct, typename TAcc, int D_IN, int D_OUT, int MODE, int MINB>
+int launch_v(int64_t N, int U, int D, int nnz, const int32_t* tab, const void* cgw, const int32_t* row_ptr, const void* gamma,
            const void* Vin, int implicit_v0, const void* Y, const void* w0, int64_t w0_ld, void* Vout, const void* gVout, void* gVin,
            void* gw0, int64_t gw0_ld, void* gY, cudaStream_t st) {
     dim3 grid(ab2_blocks(N, CPB), (unsigned)((U + 31) / 32));
     if (implicit_v0) {
         if constexpr (D_IN == 1 || D_IN == 4 || D_IN == 9 || D_IN == 16) {
-            tp_smem_kernel<TAct, TAcc, D_IN, D_OUT, true, MODE><<<grid, 256, 0, st>>>(
+            tp_smem_kernel<TAct, TAcc, D_IN, D_OUT, true, MODE, MINB><<<grid, 256, 0, st>>>(
                 N, U, D, nnz, tab, (const TAcc*)cgw, row_ptr, (const TAcc*)gamma, nullptr, (const TAcc*)Y, (const TAct*)w0, w0_ld,
                 (TAct*)Vout, (const TAct*)gVout, nullptr, (TAct*)gw0, gw0_ld, (TAcc*)gY);
             return 0;
         }
         return -1;
     }
-    tp_smem_kernel<TAct, TAcc, D_IN, D_OUT, false, MODE><<<grid, 256, 0, st>>>(
+    tp_smem_kernel<TAct, TAcc, D_IN, D_OUT, false, MODE, MINB><<<grid, 256, 0, st>>>(
         N, U, D, nnz, tab, (const TAcc*)cgw, row_ptr, (const TAcc*)gamma, (const TAct*)Vin, nullptr, nullptr, 0, (TAct*)Vout,
         (const TAct*)gVout, (TAct*)gVin, nullptr, 0, nullptr);
     return 0;
+}
+
+template <typename TAct, typename TAcc, int D_IN, int D_OUT, int MODE, typename... A>
+int launch(A... a) {
+    if (g_ab2_opt_tp_variant == 1) return launch_v<TAct, TAcc, D_IN, D_OUT, MODE, 3>(a...);
+    return launch_v<TAct, TAcc, D_IN, D_OUT, MODE, 2>(a...);
 }
 
 // shapes whose M (CPB * D_IN * ceil(D_OUT/4)*4 * 32 floats) fits the 48 KB static shared-memory limit
 #define AB2_SMEM_SHAPES(X) X(4, 4, 4) X(4, 1, 4) X(9, 9, 9) X(9, 1, 9) X(16, 1, 16) X(7, 4, 4) X(4, 7, 4) X(7, 7, 4) X(7, 1, 4)
 
 }  // namespace
+
+int g_ab2_opt_tp_variant = 0;
 
 int ab2_tp_smem(int mode, int dtype, int64_t N, int U, int D, int d_in, int d_out, int nnz, const int32_t* tab, const void* cgw,
                 const int32_t* row_ptr, const void* gamma, const void* Vin, int implicit_v0, const void* Y, const void* w0,
