@@ -14,7 +14,7 @@ import torch
 from . import build as _build
 
 AB2_F64, AB2_F32, AB2_BF16 = 0, 1, 2
-ACT_NONE, ACT_SILU = 0, 1
+ACT_NONE, ACT_SILU, ACT_MUL_DSILU = 0, 1, 2
 EPI_NONE, EPI_MUL_DSILU = 0, 1
 MAX_SEG = 4
 
@@ -35,7 +35,7 @@ _SIGNATURES = {
     "ab2_op_gather_rows": ([_i32, _i64, _i64, _dbl, _vp, _vp, _vp, _vp], C.c_int),
     "ab2_sh_fwd": ([_i32, _i32, _i64, _vp, _vp, _vp], C.c_int),
     "ab2_sh_bwd": ([_i32, _i32, _i64, _vp, _vp, _vp, _i32, _vp], C.c_int),
-    "ab2_linear": ([_i32, _i64, _i32, _i32, _i32, _vp, _vp, _vp, _i32, _vp, _vp, _i32, _vp, _vp, _vp, _vp, _i32, _vp, _i64, _vp], C.c_int),
+    "ab2_linear": ([_i32, _i64, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _i32, _vp, _vp, _vp, _vp, _i32, _vp, _i64, _vp], C.c_int),
     "ab2_linear_packed_bytes": ([_i32, _i32, _i32], C.c_int64),
     "ab2_linear_pack": ([_i32, _i32, _i32, _vp, _vp, _vp], C.c_int),
     "ab2_env_sum": ([_i32, _i32, _i64, _i32, _vp, _vp, _vp, _i64, _dbl, _vp, _vp], C.c_int),
@@ -196,6 +196,7 @@ def linear(
     epi: int = EPI_NONE,
     aux: Optional[torch.Tensor] = None,
     W_packed: Optional[torch.Tensor] = None,
+    a_aux: Optional[Sequence[Optional[torch.Tensor]]] = None,
 ):
     """Out (+)= epi(act(cat(a_segs, -1)) @ W); a_segs / o_segs are 2-D row-strided views.
     ``W_packed`` (from ``linear_pack``) enables the tcgen05 tensor-core path."""
@@ -211,6 +212,19 @@ def linear(
         assert t.dtype == dt and t.shape[0] == M
         a_ptr[s], a_ld[s], a_w[s] = t.data_ptr(), ld, t.shape[1]
         _ptr(t)
+    x_ptr = x_ld = None
+    if a_aux is not None:
+        assert act == ACT_MUL_DSILU and len(a_aux) == na
+        x_ptr = (C.c_void_p * na)()
+        x_ld = (C.c_int64 * na)()
+        for s, t in enumerate(a_aux):
+            if t is None:
+                x_ptr[s], x_ld[s] = None, 0
+            else:
+                t, ld = _row_strided(t, f"A aux segment {s}")
+                assert t.dtype == dt and t.shape == a_segs[s].shape
+                x_ptr[s], x_ld[s] = t.data_ptr(), ld
+                _ptr(t)
     o_ptr = (C.c_void_p * no)()
     o_ld = (C.c_int64 * no)()
     o_w = (C.c_int32 * no)()
@@ -228,7 +242,7 @@ def linear(
     with _timed("linear", 1):
         _check(
             load().ab2_linear(
-                DTYPE_ENUM[dt], M, K, N, na, a_ptr, a_ld, a_w, act, _ptr(_contig(W, "W")), _ptr(W_packed), no, o_ptr, o_ld, o_w, o_acc, epi,
+                DTYPE_ENUM[dt], M, K, N, na, a_ptr, a_ld, a_w, x_ptr, x_ld, act, _ptr(_contig(W, "W")), _ptr(W_packed), no, o_ptr, o_ld, o_w, o_acc, epi,
                 _ptr(aux), aux_ld, _stream(),
             )
         )

@@ -19,6 +19,8 @@ struct LinSeg {
     int64_t ld;
     int width;
     int accum;
+    const void* aux;   // A segments only: silu' multiplier source (AB2_ACT_MUL_DSILU)
+    int64_t aux_ld;
 };
 
 struct LinParams {
@@ -41,7 +43,12 @@ __device__ __forceinline__ TAcc lin_load_a(const LinParams& p, int64_t m, int k)
 #pragma unroll
     for (int s = 0; s < AB2_MAX_SEG; ++s) {
         if (s < p.n_a) {
-            if (k < p.a[s].width) return to_acc<TAcc>(((const TAct*)p.a[s].ptr)[m * p.a[s].ld + k]);
+            if (k < p.a[s].width) {
+                TAcc v = to_acc<TAcc>(((const TAct*)p.a[s].ptr)[m * p.a[s].ld + k]);
+                if (p.act == AB2_ACT_MUL_DSILU && p.a[s].aux)
+                    v *= dsilu_f(to_acc<TAcc>(((const TAct*)p.a[s].aux)[m * p.a[s].aux_ld + k]));
+                return v;
+            }
             k -= p.a[s].width;
         }
     }
@@ -130,11 +137,12 @@ __global__ void __launch_bounds__(256) linear_kernel(const LinParams p) {
 }
 
 int ab2_linear_tc_try(int dtype, int64_t M, int K, int N, int n_a, const void* const* a_ptr, const int64_t* a_ld,
-                      const int32_t* a_width, int act, const void* Wpacked, int n_o, void* const* o_ptr, const int64_t* o_ld,
+                      const int32_t* a_width, const void* const* a_aux, const int64_t* a_aux_ld, int act, const void* Wpacked, int n_o, void* const* o_ptr, const int64_t* o_ld,
                       const int32_t* o_width, const int32_t* o_accum, int epi, const void* aux, int64_t aux_ld, cudaStream_t st);
 
 extern "C" int ab2_linear(int dtype, int64_t M, int K, int N, int n_a, const void* const* a_ptr, const int64_t* a_ld,
-                          const int32_t* a_width, int act, const void* W, const void* Wpacked, int n_o, void* const* o_ptr,
+                          const int32_t* a_width, const void* const* a_aux, const int64_t* a_aux_ld, int act, const void* W,
+                          const void* Wpacked, int n_o, void* const* o_ptr,
                           const int64_t* o_ld, const int32_t* o_width, const int32_t* o_accum, int epi, const void* aux,
                           int64_t aux_ld, void* stream) {
     if (M == 0) return 0;
@@ -148,6 +156,8 @@ extern "C" int ab2_linear(int dtype, int64_t M, int K, int N, int n_a, const voi
     for (int s = 0; s < n_a; ++s) {
         AB2_CHECK_ARG(a_ptr[s] && a_width[s] > 0 && a_ld[s] >= a_width[s], "A segment");
         p.a[s].ptr = a_ptr[s]; p.a[s].ld = a_ld[s]; p.a[s].width = a_width[s]; ks += a_width[s];
+        p.a[s].aux = a_aux ? a_aux[s] : nullptr;
+        p.a[s].aux_ld = (a_aux && a_aux_ld) ? a_aux_ld[s] : 0;
     }
     for (int s = 0; s < n_o; ++s) {
         AB2_CHECK_ARG(o_ptr[s] && o_width[s] > 0 && o_ld[s] >= o_width[s], "output segment");
@@ -157,7 +167,7 @@ extern "C" int ab2_linear(int dtype, int64_t M, int K, int N, int n_a, const voi
     AB2_CHECK_ARG(ks == K, "A segment widths must sum to K");
     AB2_CHECK_ARG(ns == N, "output segment widths must sum to N");
     cudaStream_t st = (cudaStream_t)stream;
-    if (Wpacked && ab2_linear_tc_try(dtype, M, K, N, n_a, a_ptr, a_ld, a_width, act, Wpacked, n_o, o_ptr, o_ld, o_width, o_accum, epi,
+    if (Wpacked && ab2_linear_tc_try(dtype, M, K, N, n_a, a_ptr, a_ld, a_width, a_aux, a_aux_ld, act, Wpacked, n_o, o_ptr, o_ld, o_width, o_accum, epi,
                                      aux, aux_ld, st) == 0) {
         AB2_CUDA_LAUNCH_CHECK();
         return 0;

@@ -31,8 +31,8 @@ namespace {
 constexpr int BM = 128;       // rows per tile = UMMA M
 constexpr int KC = 32;        // k per ring stage
 constexpr int NSTAGE = 4;        // max ring stages (run-time count p.nstage <= NSTAGE)
-constexpr int RAW_DEPTH = 4;     // cp.async stages in flight per producer thread
-constexpr int RAW_STAGE = 256 * 4 * 16;  // bytes: 256 producer threads x 4 x 16-byte chunks
+constexpr int RAW_DEPTH = 4;     // max cp.async stages in flight per producer thread
+constexpr int RAW_STAGE = 256 * 4 * 16;  // bytes: 256 producer threads x 4 x 16-byte chunks (x2 with aux)
 constexpr int EPI_LD = 36;       // floats per staged row (32 + 4 pad): conflict-free 16-byte accesses
 constexpr int EPI_BYTES = 4 * 32 * EPI_LD * 4;  // 4 epilogue warps x 32 rows
 constexpr int STAGE_HALF = BM * KC * 2;  // bytes of one bf16 [128][32] operand image (8 KB)
@@ -45,6 +45,8 @@ struct TcSeg {
     int64_t ld;
     int width;
     int accum;
+    const void* aux;   // A segments: silu' multiplier source (AB2_ACT_MUL_DSILU), may be null
+    int64_t aux_ld;
 };
 
 struct TcParams {
@@ -62,6 +64,8 @@ struct TcParams {
     int64_t num_tiles;
     int nstage;
     int debug;
+    int raw_depth;  // cp.async stages in flight per producer thread (2 or 4)
+    int has_aux;    // act == AB2_ACT_MUL_DSILU: the raw slots carry A and aux chunks
 };
 
 // ---- PTX wrappers ---------------------------------------------------------------------
@@ -156,6 +160,18 @@ __device__ __forceinline__ const TSrc* seg_ptr(const TcParams& p, int64_t m, int
     return nullptr;
 }
 
+template <typename TSrc>
+__device__ __forceinline__ const TSrc* seg_aux_ptr(const TcParams& p, int64_t m, int k) {
+#pragma unroll
+    for (int s = 0; s < AB2_MAX_SEG; ++s) {
+        if (s < p.n_a) {
+            if (k < p.a[s].width) return p.a[s].aux ? (const TSrc*)p.a[s].aux + m * p.a[s].aux_ld + k : nullptr;
+            k -= p.a[s].width;
+        }
+    }
+    return nullptr;
+}
+
 // shared-memory matrix descriptor: K-major, SWIZZLE_NONE, 8x16B core matrices.
 // canonical layout (16-byte units) ((8,n),2):((1,SBO),LBO): LBO = byte distance between core
 // matrices adjacent in K, SBO = between 8-row groups.
@@ -221,7 +237,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) linear_tc_kernel(const TcParams p
     uint8_t* sA = smem + ((w_bytes + 127) & ~127);
     const int stage_bytes = SPLIT ? 2 * STAGE_HALF : STAGE_HALF;
     uint8_t* sRaw = sA + p.nstage * stage_bytes;
-    float* sEpi = reinterpret_cast<float*>(sRaw + RAW_DEPTH * RAW_STAGE);
+    const int raw_stage = RAW_STAGE * (p.has_aux ? 2 : 1);
+    float* sEpi = reinterpret_cast<float*>(sRaw + p.raw_depth * raw_stage);
     uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(sEpi) + EPI_BYTES);
     // bars: full[NSTAGE], empty[NSTAGE], tmem_full[2], tmem_empty[2]; then the TMEM base word
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NSTAGE + 4);
@@ -278,36 +295,64 @@ __global__ void __launch_bounds__(NTHREADS, 1) linear_tc_kernel(const TcParams p
                 const int64_t tile = blockIdx.x + (seq / nkb) * gridDim.x;
                 const int kb = (int)(seq % nkb);
                 const int k = kb * KC + kc * 8;
-                const int slot = (int)(seq % RAW_DEPTH);
+                const int slot = (int)(seq % p.raw_depth);
 #pragma unroll
                 for (int i = 0; i < GPW; ++i) {
                     const int64_t m = tile * BM + (warp * GPW + i) * 8 + r8;
-                    const TSrc* src = (m < p.M && k < p.K && !(p.debug & 2)) ? seg_ptr<TSrc>(p, m, k) : nullptr;
+                    const bool inb = (m < p.M && k < p.K && !(p.debug & 2));
+                    const TSrc* src = inb ? seg_ptr<TSrc>(p, m, k) : nullptr;
 #pragma unroll
                     for (int h = 0; h < CH; ++h) {
-                        const uint32_t dst = raw_u + (uint32_t)(((slot * 4 + i * CH + h) * 256 + threadIdx.x) * 16);
+                        const uint32_t dst = raw_u + (uint32_t)(slot * raw_stage + ((i * CH + h) * 256 + threadIdx.x) * 16);
                         const void* g = src ? (const void*)(reinterpret_cast<const uint8_t*>(src) + 16 * h) : p.Wpacked;
                         cp_async16(dst, g, src ? 16u : 0u);  // src-size 0 -> zero fill
+                    }
+                    if (p.has_aux) {
+                        const TSrc* ax = inb ? seg_aux_ptr<TSrc>(p, m, k) : nullptr;
+#pragma unroll
+                        for (int h = 0; h < CH; ++h) {
+                            const uint32_t dst = raw_u + (uint32_t)(slot * raw_stage + ((4 + i * CH + h) * 256 + threadIdx.x) * 16);
+                            const void* g = ax ? (const void*)(reinterpret_cast<const uint8_t*>(ax) + 16 * h) : p.Wpacked;
+                            cp_async16(dst, g, ax ? 16u : 0u);  // zero -> silu'(0) = 0.5 ... handled below
+                        }
                     }
                 }
             }
             cp_async_commit();  // always commit so that group counting stays uniform
         };
         auto fetch = [&](int64_t seq, float (&v)[GPW][8]) {
-            const int slot = (int)(seq % RAW_DEPTH);
-#pragma unroll
-            for (int i = 0; i < GPW; ++i) {
+            const int slot = (int)(seq % p.raw_depth);
+            const uint8_t* base = sRaw + slot * raw_stage;
+            auto rd8 = [&](int chunk0, float (&o)[8]) {
                 if constexpr (sizeof(TSrc) == 4) {
-                    const float4 x = *reinterpret_cast<const float4*>(sRaw + ((slot * 4 + i * 2 + 0) * 256 + threadIdx.x) * 16);
-                    const float4 y = *reinterpret_cast<const float4*>(sRaw + ((slot * 4 + i * 2 + 1) * 256 + threadIdx.x) * 16);
-                    v[i][0] = x.x; v[i][1] = x.y; v[i][2] = x.z; v[i][3] = x.w; v[i][4] = y.x; v[i][5] = y.y; v[i][6] = y.z; v[i][7] = y.w;
+                    const float4 x = *reinterpret_cast<const float4*>(base + ((chunk0 + 0) * 256 + threadIdx.x) * 16);
+                    const float4 y = *reinterpret_cast<const float4*>(base + ((chunk0 + 1) * 256 + threadIdx.x) * 16);
+                    o[0] = x.x; o[1] = x.y; o[2] = x.z; o[3] = x.w; o[4] = y.x; o[5] = y.y; o[6] = y.z; o[7] = y.w;
                 } else {
-                    const uint4 x = *reinterpret_cast<const uint4*>(sRaw + ((slot * 4 + i) * 256 + threadIdx.x) * 16);
+                    const uint4 x = *reinterpret_cast<const uint4*>(base + (chunk0 * 256 + threadIdx.x) * 16);
                     const __nv_bfloat162* hh = reinterpret_cast<const __nv_bfloat162*>(&x);
 #pragma unroll
                     for (int t = 0; t < 4; ++t) {
                         const float2 f = __bfloat1622float2(hh[t]);
-                        v[i][2 * t] = f.x; v[i][2 * t + 1] = f.y;
+                        o[2 * t] = f.x; o[2 * t + 1] = f.y;
+                    }
+                }
+            };
+#pragma unroll
+            for (int i = 0; i < GPW; ++i) {
+                rd8(i * CH, v[i]);
+                if (p.has_aux) {
+                    // plain segments (null aux) are zero-filled raw chunks; they must not scale A:
+                    // the issuing side encodes "no aux" by the segment table, so re-derive it here.
+                    float w[8];
+                    rd8(4 + i * CH, w);
+                    const int64_t tile = blockIdx.x + (seq / nkb) * gridDim.x;
+                    const int kk = (int)(seq % nkb) * KC + kc * 8;
+                    const int64_t m = tile * BM + (warp * GPW + i) * 8 + r8;
+                    const bool has = (m < p.M && kk < p.K) && seg_aux_ptr<TSrc>(p, m, kk) != nullptr;
+                    if (has) {
+#pragma unroll
+                        for (int t = 0; t < 8; ++t) v[i][t] *= dsilu_fast(w[t]);
                     }
                 }
             }
@@ -345,13 +390,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) linear_tc_kernel(const TcParams p
             if (++stage == p.nstage) { stage = 0; phase ^= 1; }
         };
         static_assert(GPW == 2, "raw slot layout assumes 2 row groups per producer warp");
-#pragma unroll
-        for (int d = 0; d < RAW_DEPTH; ++d) issue(d);
+        for (int d = 0; d < p.raw_depth; ++d) issue(d);
         for (int64_t seq = 0; seq < total; ++seq) {
-            cp_async_wait<RAW_DEPTH - 1>();  // the oldest group (= item seq) has landed
+            if (p.raw_depth == 4) cp_async_wait<3>();  // the oldest group (= item seq) has landed
+            else cp_async_wait<1>();
             float v[GPW][8];
             fetch(seq, v);
-            issue(seq + RAW_DEPTH);           // refill the slot just drained
+            issue(seq + p.raw_depth);         // refill the slot just drained
             emit(v);
         }
         cp_async_wait<0>();
@@ -602,7 +647,7 @@ extern "C" int ab2_linear_pack(int dtype, int K, int N, const void* W, void* pac
 
 // returns 0 if launched, -1 if this call is not eligible (caller falls back to linear.cu)
 int ab2_linear_tc_try(int dtype, int64_t M, int K, int N, int n_a, const void* const* a_ptr, const int64_t* a_ld,
-                      const int32_t* a_width, int act, const void* Wpacked, int n_o, void* const* o_ptr, const int64_t* o_ld,
+                      const int32_t* a_width, const void* const* a_aux, const int64_t* a_aux_ld, int act, const void* Wpacked, int n_o, void* const* o_ptr, const int64_t* o_ld,
                       const int32_t* o_width, const int32_t* o_accum, int epi, const void* aux, int64_t aux_ld, cudaStream_t st) {
     if (!g_ab2_opt_linear_tc || !Wpacked || dtype == AB2_F64) return -1;
     if (ab2_linear_packed_bytes(dtype, K, N) == 0) return -1;
@@ -610,7 +655,10 @@ int ab2_linear_tc_try(int dtype, int64_t M, int K, int N, int n_a, const void* c
     for (int s = 0; s < n_a; ++s) {
         if (a_width[s] % 8 != 0) return -1;
         if ((reinterpret_cast<uintptr_t>(a_ptr[s]) % 16) != 0 || (a_ld[s] * esz) % 16 != 0) return -1;
+        if (act == AB2_ACT_MUL_DSILU && a_aux && a_aux[s] &&
+            ((reinterpret_cast<uintptr_t>(a_aux[s]) % 16) != 0 || (a_aux_ld[s] * esz) % 16 != 0)) return -1;
     }
+    const int has_aux = (act == AB2_ACT_MUL_DSILU && a_aux) ? 1 : 0;
     static int num_sms = 0;
     static int max_smem = 0;
     if (num_sms == 0) {
@@ -623,19 +671,28 @@ int ab2_linear_tc_try(int dtype, int64_t M, int K, int N, int n_a, const void* c
     memset(&p, 0, sizeof(p));
     p.M = M; p.K = K; p.N = N; p.Npad = tc_npad(N); p.n_a = n_a; p.act = act; p.Wpacked = Wpacked; p.n_o = n_o;
     p.epi = epi; p.aux = aux; p.aux_ld = aux_ld; p.num_tiles = (M + BM - 1) / BM;
-    for (int s = 0; s < n_a; ++s) { p.a[s].ptr = a_ptr[s]; p.a[s].ld = a_ld[s]; p.a[s].width = a_width[s]; }
+    for (int s = 0; s < n_a; ++s) {
+        p.a[s].ptr = a_ptr[s]; p.a[s].ld = a_ld[s]; p.a[s].width = a_width[s];
+        p.a[s].aux = has_aux ? a_aux[s] : nullptr; p.a[s].aux_ld = has_aux ? a_aux_ld[s] : 0;
+    }
+    p.has_aux = has_aux;
     for (int s = 0; s < n_o; ++s) { p.o[s].ptr = o_ptr[s]; p.o[s].ld = o_ld[s]; p.o[s].width = o_width[s]; p.o[s].accum = o_accum ? o_accum[s] : 0; }
     const bool split = dtype == AB2_F32;
     const int w_bytes = p.Npad * K * 2 * (split ? 2 : 1);
     const int stage_bytes = STAGE_HALF * (split ? 2 : 1);
-    int nstage = NSTAGE;
+    // shared-memory plan: prefer deep raw prefetch (4) and 4 canonical stages; shrink until it fits
+    int nstage = 0, raw_depth = 0;
     size_t smem = 0;
-    for (; nstage >= 2; --nstage) {
-        smem = ((w_bytes + 127) & ~127) + (size_t)nstage * stage_bytes + RAW_DEPTH * RAW_STAGE + EPI_BYTES + (2 * NSTAGE + 4) * 8 + 16;
-        if ((int)smem <= max_smem) break;
+    const int raw_stage = RAW_STAGE * (has_aux ? 2 : 1);
+    const int plans[4][2] = {{4, NSTAGE}, {4, 2}, {2, NSTAGE}, {2, 2}};
+    for (int q = 0; q < 4 && !nstage; ++q) {
+        const size_t need = ((w_bytes + 127) & ~127) + (size_t)plans[q][1] * stage_bytes + (size_t)plans[q][0] * raw_stage + EPI_BYTES +
+                            (2 * NSTAGE + 4) * 8 + 16;
+        if ((int)need <= max_smem) { raw_depth = plans[q][0]; nstage = plans[q][1]; smem = need; }
     }
-    if (nstage < 2) return -1;
+    if (!nstage) return -1;
     p.nstage = nstage;
+    p.raw_depth = raw_depth;
     p.debug = g_ab2_opt_tc_debug;
     const unsigned grid = (unsigned)((p.num_tiles < num_sms) ? p.num_tiles : num_sms);
     cudaError_t e;

@@ -143,3 +143,21 @@ class PackedMLP:
                 else:
                     _lib.linear(cur, self.WT[k], [g], W_packed=self.WTp[k])
                 cur = [g]
+
+    # ---- "plain GEMM" backward for the common 2-layer SiLU MLP -------------------------------
+    @property
+    def is_two_layer_silu(self) -> bool:
+        return self.n_layers == 2 and self.silu
+
+    def hidden_grad(self, gout_segs: Sequence[torch.Tensor]) -> torch.Tensor:
+        """g_h = g_out @ W2^T (no epilogue): gradient w.r.t. the hidden layer's *output*.  The SiLU'
+        factor is applied by whichever GEMM consumes g_h (act=ACT_MUL_DSILU with aux=pre)."""
+        M = gout_segs[0].shape[0]
+        g_h = torch.empty(M, self.dims[1], dtype=self.dtype, device=self.device)
+        _lib.linear(list(gout_segs), self.WT[1], [g_h], W_packed=self.WTp[1])
+        return g_h
+
+    def backward_plain(self, gout_segs: Sequence[torch.Tensor], pre: List[torch.Tensor], gin_segs: Sequence[torch.Tensor]):
+        """Whole backward of a 2-layer SiLU MLP with two plain GEMMs (no epilogue-side global reads)."""
+        g_h = self.hidden_grad(gout_segs)
+        _lib.linear([g_h], self.WT[0], list(gin_segs), act=_lib.ACT_MUL_DSILU, a_aux=[pre[0]], W_packed=self.WTp[0])

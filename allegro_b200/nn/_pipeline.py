@@ -83,6 +83,23 @@ class AllegroCore:
             assert tp.base_dim2 == self.D
         self.readout = PackedMLP(edge_readout, dtype, device)
         self.nw = nw
+        # "plain GEMM" backward plan (all latent/readout MLPs are 2-layer SiLU): the gradient of the
+        # densenet block x_b is ONE GEMM over all its consumers (readout, latents m >= b), concatenated
+        # along K, each consumer's g_h scaled by silu'(pre) in the GEMM prologue -- no accumulation.
+        self.plain_ok = self.readout.is_two_layer_silu and all(ly["mlp"].is_two_layer_silu for ly in self.layers)
+        if self.plain_ok:
+            L = self.L
+            self.gxW, self.gxWp, self.gsW, self.gsWp = [], [], [], []
+            for b in range(L + 1):
+                blocks = [self.readout.WT[0][:, S * b : S * (b + 1)]]
+                blocks += [self.layers[mm]["mlp"].WT[0][:, S * b : S * (b + 1)] for mm in range(L - 1, b - 1, -1) if mm >= b]
+                Wg = torch.cat(blocks, dim=0).contiguous()
+                self.gxW.append(Wg)
+                self.gxWp.append(_lib.linear_pack(Wg))
+            for l in range(L):
+                Ws = self.layers[l]["mlp"].WT[0][:, S * (l + 1) : S * (l + 1) + U].contiguous()
+                self.gsW.append(Ws)
+                self.gsWp.append(_lib.linear_pack(Ws))
 
     # ------------------------------------------------------------------------------------
     def forward(self, csr: EdgeCSR, vec: torch.Tensor, x_emb: torch.Tensor, keep: bool = True):
@@ -125,6 +142,70 @@ class AllegroCore:
     # ------------------------------------------------------------------------------------
     def backward(self, sv: _Saved, gEi: torch.Tensor):
         """gEi [N] (acc dtype) -> (gvec [E,3] acc dtype, gx_emb [E,S_in] act dtype)."""
+        if self.plain_ok:
+            return self._backward_plain(sv, gEi)
+        return self._backward_legacy(sv, gEi)
+
+    def _backward_plain(self, sv: _Saved, gEi: torch.Tensor):
+        csr = sv.csr
+        E, N, U, S, L, D = csr.num_edges, csr.num_atoms, self.U, self.S, self.L, self.D
+        dt, dev = self.dtype, self.device
+        _lib.set_tag("bwd.readout")
+        gEz = _lib.edge_sum_bwd(gEi.contiguous(), csr.ctr, self.factor).to(dt).view(E, 1)
+        g_h = {"r": self.readout.hidden_grad([gEz])}
+        pre = {"r": sv.pre_read[0]}
+        for l in range(L):
+            pre[l] = sv.pre_lat[l][0]
+        gY = torch.zeros(E, D, dtype=self.acc, device=dev)
+        gV_next: Optional[torch.Tensor] = None
+        gomega_next: Optional[torch.Tensor] = None
+        gw0 = None
+
+        def block_grad(b: int) -> torch.Tensor:
+            cons = ["r"] + [mm for mm in range(L - 1, b - 1, -1) if mm >= b]
+            out = torch.empty(E, S, dtype=dt, device=dev)
+            _lib.linear([g_h[c] for c in cons], self.gxW[b], [out], act=_lib.ACT_MUL_DSILU, a_aux=[pre[c] for c in cons],
+                        W_packed=self.gxWp[b])
+            return out
+
+        for l in range(L - 1, -1, -1):
+            ly = self.layers[l]
+            _lib.set_tag(f"bwd.L{l}")
+            gouts = [block_grad(l + 1)]
+            if not ly["last"]:
+                gouts.append(gomega_next)
+            g_h[l] = ly["mlp"].hidden_grad(gouts)
+            if ly["last"]:
+                gV_next = torch.empty(E, ly["d_out"], U, dtype=dt, device=dev)
+                if ly["d_out"] > 1:
+                    gV_next.zero_()
+                gs_acc = False
+            else:
+                gs_acc = True
+            gs = gV_next.view(E, ly["d_out"] * U)[:, :U]
+            _lib.linear([g_h[l]], self.gsW[l], [gs], o_accum=[gs_acc], act=_lib.ACT_MUL_DSILU, a_aux=[pre[l]], W_packed=self.gsWp[l])
+            ggamma = torch.empty(N, D, U, dtype=self.acc, device=dev)
+            if l == 0:
+                gw0 = torch.empty(E, self.nw, dtype=dt, device=dev)
+                _lib.tp_bwd(dt, self.lmax, N, E, U, ly["d_in"], ly["d_out"], ly["tab"], ly["cgw"], csr.row_ptr, csr.ctr,
+                            sv.gamma[l], None, sv.Y, sv.w0, gV_next, None, gw0, gY, ggamma)
+                gV_in = None
+            else:
+                gV_in = torch.empty(E, ly["d_in"], U, dtype=dt, device=dev)
+                _lib.tp_bwd(dt, self.lmax, N, E, U, ly["d_in"], ly["d_out"], ly["tab"], ly["cgw"], csr.row_ptr, csr.ctr,
+                            sv.gamma[l], sv.V[l], None, None, gV_next, gV_in, None, None, ggamma)
+            gomega = torch.empty(E, self.nw, dtype=dt, device=dev)
+            _lib.env_bwd(dt, self.lmax, U, csr.ctr, sv.Y, sv.omega[l], ggamma, self.sf, gomega, gY, row_ptr=csr.row_ptr)
+            gV_next, gomega_next = gV_in, gomega
+        _lib.set_tag("bwd.embed")
+        g_x0 = block_grad(0)
+        gx_emb = torch.empty(E, self.S_in, dtype=dt, device=dev)
+        self.embed.backward([gw0, g_x0, gomega_next], [], [gx_emb], [False])
+        gvec = _lib.sh_bwd(sv.vec, gY, self.lmax)
+        return gvec, gx_emb
+
+    def _backward_legacy(self, sv: _Saved, gEi: torch.Tensor):
+        """General MLP depth / nonlinearity: SiLU' in the GEMM epilogue, gradient accumulation."""
         csr = sv.csr
         E, N, U, S, L, D = csr.num_edges, csr.num_atoms, self.U, self.S, self.L, self.D
         dt, dev = self.dtype, self.device
@@ -205,7 +286,10 @@ def energy_forces(core: "AllegroCore", up: UpstreamPack, csr: EdgeCSR, pos: torc
     gvec, gx_emb = core.backward(sv, gEi)
     _lib.set_tag("bwd.radial")
     g_e0 = torch.empty(E, up.S_rc, dtype=dt, device=pos.device)
-    up.mlp.backward([gx_emb], pre_se, [g_e0], [False])
+    if up.mlp.is_two_layer_silu:
+        up.mlp.backward_plain([gx_emb], pre_se, [g_e0])
+    else:
+        up.mlp.backward([gx_emb], pre_se, [g_e0], [False])
     _lib.radial_bwd(dt, up.S_rc, up.p, vec, csr.ctr, csr.nbr, types_i32, up.rmax_table, up.bessel_w, up.Wb, up.cemb, up.nemb, g_e0, gvec)
     F = _lib.force_scatter(gvec, csr.row_ptr, csr.nbr, pos.shape[0])
     return Ei, F, X, Ez

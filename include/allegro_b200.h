@@ -28,7 +28,7 @@ extern "C" {
 #endif
 
 enum { AB2_F64 = 0, AB2_F32 = 1, AB2_BF16 = 2 };
-enum { AB2_ACT_NONE = 0, AB2_ACT_SILU = 1 };
+enum { AB2_ACT_NONE = 0, AB2_ACT_SILU = 1, AB2_ACT_MUL_DSILU = 2 };
 enum { AB2_EPI_NONE = 0, AB2_EPI_MUL_DSILU = 1 };
 
 #define AB2_MAX_SEG 4
@@ -78,11 +78,15 @@ int ab2_sh_bwd(int acc_dtype, int lmax, int64_t E, const void* vec, const void* 
 /* Generic fused linear layer (nequip ScalarMLPFunction layer, _allegro.py:251,278;
  * tensorembed.py:88-89; allegro_models.py:231-241):
  *   Out[M][N] (split over <=4 column segments) (+)= epi( act(concat_k A_k)[M][K] @ W[K][N] )
- * act: AB2_ACT_SILU applies silu to A on load.  epi: AB2_EPI_MUL_DSILU multiplies by
- * silu'(aux[m][n]) (MLP backward).  W is [K][N] row-major in TAct (alpha pre-folded on host).
+ * act: AB2_ACT_SILU applies silu to A on load; AB2_ACT_MUL_DSILU multiplies segment s of A on
+ * load by silu'(a_aux[s][m][k]) (a_aux_ptr_host[s] may be NULL = plain segment): the MLP backward's
+ * g_pre = g_h * silu'(pre) formed inside the consuming GEMM's (prefetched) prologue.
+ * epi: AB2_EPI_MUL_DSILU multiplies the result by silu'(aux[m][n]).  W is [K][N] row-major in TAct (alpha pre-folded on host).
  * A segments: (ptr, leading dim in elements, width); widths sum to K; outputs likewise to N. */
 int ab2_linear(int dtype, int64_t M, int K, int N, int n_a, const void* const* a_ptr_host,
-               const int64_t* a_ld_host, const int32_t* a_width_host, int act, const void* W,
+               const int64_t* a_ld_host, const int32_t* a_width_host,
+               const void* const* a_aux_ptr_host /* nullable */, const int64_t* a_aux_ld_host,
+               int act, const void* W,
                const void* W_packed /* nullable: image from ab2_linear_pack -> tcgen05 path */,
                int n_o, void* const* o_ptr_host, const int64_t* o_ld_host,
                const int32_t* o_width_host, const int32_t* o_accum_host, int epi, const void* aux,

@@ -39,7 +39,7 @@ def test_header_symbols_are_exported(lib):
 
 def test_bad_argument_reports_error(lib):
     # M>0 with null W must fail before any launch (safe without a GPU)
-    rc = lib.ab2_linear(1, 4, 8, 8, 0, None, None, None, 0, None, None, 1, None, None, None, None, 0, None, 0, None)
+    rc = lib.ab2_linear(1, 4, 8, 8, 0, None, None, None, None, None, 0, None, None, 1, None, None, None, None, 0, None, 0, None)
     assert rc != 0
     assert b"segment" in lib.ab2_last_error()
 

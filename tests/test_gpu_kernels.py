@@ -137,6 +137,35 @@ def test_linear_tensor_core_path(dtype, shape, mode):
     assert (res["simt"] - exp).abs().max().item() / scale < (1e-5 if dtype == torch.float32 else 2e-2)
 
 
+@pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
+@pytest.mark.parametrize("shape", [(3000, [64, 64, 64], [64]), (130, [64, 32], [32]), (77, [16], [48])])
+def test_linear_prologue_mul_dsilu(dtype, shape):
+    """act=ACT_MUL_DSILU: segment s of A is scaled by silu'(aux_s) on load (aux may be None per
+    segment); tensor-core path (fp32) and CUDA-core path against an fp64 reference."""
+    M, awid, owid = shape
+    K, N = sum(awid), sum(owid)
+    g = torch.Generator().manual_seed(K + N)
+    A = [torch.randn(M, w, generator=g, dtype=torch.float64) for w in awid]
+    X = [torch.randn(M, w, generator=g, dtype=torch.float64) if i != 1 else None for i, w in enumerate(awid)]
+    W = torch.randn(K, N, generator=g, dtype=torch.float64) / math.sqrt(K)
+    segs = []
+    for a, x in zip(A, X):
+        a = a.to(dtype).double()
+        if x is not None:
+            xq = x.to(dtype).double()
+            sg = torch.sigmoid(xq)
+            a = a * (sg * (1 + xq * (1 - sg)))
+        segs.append(a)
+    ref = torch.cat(segs, -1) @ W.to(dtype).double()
+    Wd = W.to(DEV, dtype)
+    for pk in ([_lib.linear_pack(Wd), None] if dtype == torch.float32 else [None]):
+        out = torch.empty(M, N, device=DEV, dtype=dtype)
+        _lib.linear([a.to(DEV, dtype) for a in A], Wd, [out], act=_lib.ACT_MUL_DSILU,
+                    a_aux=[x.to(DEV, dtype) if x is not None else None for x in X], W_packed=pk)
+        tol = 1e-12 if dtype == torch.float64 else (1e-4 if pk is not None else 1e-5)
+        assert _rel(out, ref) < tol
+
+
 @pytest.mark.parametrize("lmax", [1, 2, 3])
 @pytest.mark.parametrize("U", [4, 32, 48])
 @pytest.mark.parametrize("dtype", [torch.float64, torch.float32, torch.bfloat16])
