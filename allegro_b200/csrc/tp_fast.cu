@@ -29,13 +29,23 @@ template <typename TAcc, int D_IN, int D_OUT, int DG>
 __device__ __forceinline__ void build_M(TAcc (&M)[D_IN][D_OUT], WarpSmem<TAcc, D_IN, D_OUT, DG>& sm, int lane, int nnz,
                                         const int32_t* __restrict__ tabp, const TAcc* __restrict__ cgw, int U, int u, bool live,
                                         const TAcc* __restrict__ gam_c /* gamma + c*D*U */) {
+    // (i,k)-sorted table: walk it once; each target's segment is accumulated in a register and stored
+    // once (no shared-memory read-modify-write chain), then M is pulled into registers.
 #pragma unroll
     for (int e = 0; e < D_IN * D_OUT; ++e) sm.M[e][lane] = TAcc(0);
-    if (live) {
+    if (live && nnz > 0) {
+        int t_prev = tabp[0] * D_OUT + tabp[2];
+        TAcc acc = TAcc(0);
         for (int n = 0; n < nnz; ++n) {
-            const int i = tabp[3 * n], j = tabp[3 * n + 1], k = tabp[3 * n + 2];
-            sm.M[i * D_OUT + k][lane] += cgw[(int64_t)n * U + u] * gam_c[(int64_t)j * U + u];
+            const int t = tabp[3 * n] * D_OUT + tabp[3 * n + 2];
+            if (t != t_prev) {
+                sm.M[t_prev][lane] = acc;
+                acc = TAcc(0);
+                t_prev = t;
+            }
+            acc += cgw[(int64_t)n * U + u] * gam_c[(int64_t)tabp[3 * n + 1] * U + u];
         }
+        sm.M[t_prev][lane] = acc;
     }
 #pragma unroll
     for (int i = 0; i < D_IN; ++i)
@@ -232,16 +242,30 @@ __global__ void __launch_bounds__(NS * 32, 8) tp_bwd_gm_split_kernel(int64_t N, 
 #pragma unroll
         for (int k = 0; k < D_OUT; ++k) sGM[(i0 + i) * D_OUT + k][lane] = gM[i][k];
     __syncthreads();
-    if (warp == 0) {
-        for (int j = 0; j < D; ++j) sG[j][lane] = TAcc(0);
-        if (live) {
-            for (int n = 0; n < nnz; ++n) {
-                const int i = tabp[3 * n], j = tabp[3 * n + 1], k = tabp[3 * n + 2];
-                sG[j][lane] += cgw[(int64_t)n * U + u] * sGM[i * D_OUT + k][lane];
+    // ggamma[c][j][u] = sum_nnz cgw * gM[i][k]: warp w owns j = w, w+NS, ...; accumulators stay in
+    // registers (selected by an if-chain), so there is no shared-memory read-modify-write chain.
+    constexpr int JW = (DG + NS - 1) / NS;
+    TAcc accj[JW];
+#pragma unroll
+    for (int q = 0; q < JW; ++q) accj[q] = TAcc(0);
+    if (live) {
+        for (int n = 0; n < nnz; ++n) {
+            const int i = tabp[3 * n], j = tabp[3 * n + 1], k = tabp[3 * n + 2];
+            if (j % NS == warp) {
+                const TAcc x = cgw[(int64_t)n * U + u] * sGM[i * D_OUT + k][lane];
+                const int q = j / NS;
+#pragma unroll
+                for (int qq = 0; qq < JW; ++qq)
+                    if (qq == q) accj[qq] += x;
             }
-            for (int j = 0; j < D; ++j) ggamma[(c * D + j) * U + u] = sG[j][lane];
+        }
+#pragma unroll
+        for (int q = 0; q < JW; ++q) {
+            const int j = q * NS + warp;
+            if (j < D) ggamma[(c * D + j) * U + u] = accj[q];
         }
     }
+    (void)sG;
 }
 
 template <typename TAct, typename TAcc, int D_IN, int D_OUT, int DG>

@@ -26,14 +26,16 @@ struct alignas(4 * sizeof(T)) Vec4 {
     T v[4];
 };
 
-template <typename TAct, typename TAcc, int D_IN, int D_OUT, bool IMPLICIT, int MODE, int MINB>
-__global__ void __launch_bounds__(256, MINB) tp_smem_kernel(int64_t N, int U, int D, int nnz, const int32_t* __restrict__ tab,
+template <typename TAct, typename TAcc, int D_IN, int D_OUT, bool IMPLICIT, int MODE, int MINB, int UT>
+__global__ void __launch_bounds__(256, MINB) tp_smem_kernel(int64_t N, int U_rt, int D, int nnz, const int32_t* __restrict__ tab,
                                                       const TAcc* __restrict__ cgw, const int32_t* __restrict__ row_ptr,
                                                       const TAcc* __restrict__ gamma, const TAct* __restrict__ Vin,
                                                       const TAcc* __restrict__ Y, const TAct* __restrict__ w0, int64_t w0_ld,
                                                       TAct* __restrict__ Vout, const TAct* __restrict__ gVout,
                                                       TAct* __restrict__ gVin, TAct* __restrict__ gw0, int64_t gw0_ld,
                                                       TAcc* __restrict__ gY) {
+    // UT == 32: the common channel count is a compile-time constant (immediate strides, no lane guards)
+    const int U = UT ? UT : U_rt;
     constexpr int KQ = (D_OUT + 3) / 4;  // output components in groups of 4 -> one 16-byte LDS per (i, group)
     __shared__ Vec4<TAcc> sM[CPB][D_IN * KQ][32];
     __shared__ int s_rp[CPB + 1];
@@ -42,157 +44,186 @@ __global__ void __launch_bounds__(256, MINB) tp_smem_kernel(int64_t N, int U, in
     const int u0 = blockIdx.y * 32;
     const int nchunk = gridDim.y;
     if (tid <= CPB) s_rp[tid] = row_ptr[min(c0 + tid, N)];
-    // ---- build M for (CPB centres) x (32 channels): one thread per column ----
-    if (tid < CPB * 32) {
-        const int cc = tid >> 5, lu = tid & 31;
+    // ---- per-target segment pointers of the (i,k)-sorted table ----
+    constexpr int T = D_IN * D_OUT;
+    __shared__ int s_ptr[T + 1];
+    for (int t = tid; t <= T; t += 256) s_ptr[t] = -1;
+    __syncthreads();
+    for (int n = tid; n < nnz; n += 256) {
+        const int t = tab[3 * n] * D_OUT + tab[3 * n + 2];
+        if (n == 0 || (tab[3 * n - 3] * D_OUT + tab[3 * n - 1]) != t) s_ptr[t] = n;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        s_ptr[T] = nnz;
+        for (int t = T - 1; t >= 0; --t)
+            if (s_ptr[t] < 0) s_ptr[t] = s_ptr[t + 1];
+    }
+    __syncthreads();
+    // ---- build M for (CPB centres) x (32 channels): every entry M[i][k] is a register gather over its
+    //      table segment (no shared-memory read-modify-write chain), all 256 threads busy ----
+    for (int idx = tid; idx < CPB * T * 32; idx += 256) {
+        const int lu = idx & 31;
+        const int t = (idx >> 5) % T;
+        const int cc = (idx >> 5) / T;
         const int64_t c = c0 + cc;
         const int u = u0 + lu;
-#pragma unroll
-        for (int e = 0; e < D_IN * KQ; ++e) {
-#pragma unroll
-            for (int t = 0; t < 4; ++t) sM[cc][e][lu].v[t] = TAcc(0);
-        }
+        TAcc acc = TAcc(0);
         if (c < N && u < U) {
             const TAcc* __restrict__ g = gamma + c * D * U + u;
-            for (int n = 0; n < nnz; ++n) {
-                const int i = tab[3 * n], j = tab[3 * n + 1], k = tab[3 * n + 2];
-                sM[cc][i * KQ + (k >> 2)][lu].v[k & 3] += cgw[(int64_t)n * U + u] * g[(int64_t)j * U];
-            }
+            for (int n = s_ptr[t]; n < s_ptr[t + 1]; ++n) acc += cgw[(int64_t)n * U + u] * g[(int64_t)tab[3 * n + 1] * U];
+        }
+        const int i = t / D_OUT, k = t - i * D_OUT;
+        sM[cc][i * KQ + (k >> 2)][lu].v[k & 3] = acc;
+    }
+    if constexpr (D_OUT % 4 != 0) {  // zero the padding lanes of the last k-quad (read by the 16-byte LDS)
+        for (int idx = tid; idx < CPB * D_IN * 32; idx += 256) {
+            const int lu = idx & 31, i = (idx >> 5) % D_IN, cc = (idx >> 5) / D_IN;
+#pragma unroll
+            for (int k = D_OUT; k < KQ * 4; ++k) sM[cc][i * KQ + (k >> 2)][lu].v[k & 3] = TAcc(0);
         }
     }
     __syncthreads();
     const int warp = tid >> 5, lane = tid & 31;
     const int u = u0 + lane;
-    const bool live = u < U;
-    // EPT consecutive edges of ONE centre per warp-item: every 16-byte LDS of M feeds EPT edges, which
-    // divides the shared-memory traffic (the limiter with one edge per item) by EPT.
-    constexpr int EPT = 1;
-    for (int cc = 0; cc < CPB; ++cc) {
-        const int e_beg = s_rp[cc], e_end = s_rp[cc + 1];
-        for (int64_t z0 = e_beg + warp * EPT; z0 < e_end; z0 += 8 * EPT) {
-            bool ok[EPT];
-            int64_t zz[EPT];
+    const bool live = UT ? true : (u < U);
+    // Work item = one warp per (edge, channel chunk).  The global inputs of item n+1 are loaded into
+    // registers before item n is computed (manual double buffering): the loads are few (<= 21 per
+    // lane) but their latency was the top stall of the single-buffered loop.
+    struct In {
+        TAcc a[(MODE == 0 && !IMPLICIT) ? D_IN : ((MODE == 1) ? D_OUT : 1)];
+        TAcc w0l[IMPLICIT ? 5 : 1];
+        TAcc Yz[IMPLICIT ? D_IN : 1];
+    };
+    auto load_in = [&](int64_t z, In& in) {
+        if constexpr (MODE == 0 && !IMPLICIT) {
 #pragma unroll
-            for (int e = 0; e < EPT; ++e) {
-                ok[e] = (z0 + e) < e_end;
-                zz[e] = ok[e] ? z0 + e : z0;  // clamp: loads stay in range, stores are predicated
+            for (int i = 0; i < D_IN; ++i) in.a[i] = live ? to_acc<TAcc>(Vin[(z * D_IN + i) * U + u]) : TAcc(0);
+        }
+        if constexpr (MODE == 1) {
+#pragma unroll
+            for (int k = 0; k < D_OUT; ++k) in.a[k] = live ? to_acc<TAcc>(gVout[(z * D_OUT + k) * U + u]) : TAcc(0);
+        }
+        if constexpr (IMPLICIT) {
+#pragma unroll
+            for (int l = 0; l * l < D_IN; ++l) in.w0l[l] = live ? to_acc<TAcc>(w0[z * w0_ld + l * U + u]) : TAcc(0);
+#pragma unroll
+            for (int i = 0; i < D_IN; ++i) in.Yz[i] = Y[z * D_IN + i];
+        }
+    };
+    const int e_beg = s_rp[0], e_end = s_rp[CPB];
+    auto compute = [&](const In& in, int64_t z) {
+        int cc = 0;
+#pragma unroll
+        for (int t = 1; t < CPB; ++t) cc += (z >= s_rp[t]) ? 1 : 0;
+        if constexpr (MODE == 0) {
+            TAcc v[D_IN];
+#pragma unroll
+            for (int i = 0; i < D_IN; ++i) {
+                if constexpr (IMPLICIT) v[i] = in.Yz[i] * in.w0l[sh_l_of(i)];
+                else v[i] = in.a[i];
             }
-            if constexpr (MODE == 0) {
-                TAcc v[EPT][D_IN];
+            TAcc out[D_OUT];
 #pragma unroll
-                for (int e = 0; e < EPT; ++e) {
-                    const int64_t z = zz[e];
-                    if constexpr (IMPLICIT) {
-                        TAcc w0l[5];
+            for (int k = 0; k < D_OUT; ++k) out[k] = TAcc(0);
 #pragma unroll
-                        for (int l = 0; l * l < D_IN; ++l) w0l[l] = live ? to_acc<TAcc>(w0[z * w0_ld + l * U + u]) : TAcc(0);
+            for (int i = 0; i < D_IN; ++i)
 #pragma unroll
-                        for (int i = 0; i < D_IN; ++i) v[e][i] = Y[z * D_IN + i] * w0l[sh_l_of(i)];
-                    } else {
+                for (int kq = 0; kq < KQ; ++kq) {
+                    const Vec4<TAcc> m4 = sM[cc][i * KQ + kq][lane];
 #pragma unroll
-                        for (int i = 0; i < D_IN; ++i) v[e][i] = live ? to_acc<TAcc>(Vin[(z * D_IN + i) * U + u]) : TAcc(0);
-                    }
+                    for (int t = 0; t < 4; ++t)
+                        if (kq * 4 + t < D_OUT) out[kq * 4 + t] += v[i] * m4.v[t];
                 }
-                TAcc out[EPT][D_OUT];
+            if (live) {
 #pragma unroll
-                for (int e = 0; e < EPT; ++e)
+                for (int k = 0; k < D_OUT; ++k) Vout[(z * D_OUT + k) * U + u] = from_acc<TAct>(out[k]);
+            }
+        } else {
+            TAcc gin[D_IN];
 #pragma unroll
-                    for (int k = 0; k < D_OUT; ++k) out[e][k] = TAcc(0);
+            for (int i = 0; i < D_IN; ++i) {
+                TAcc s = TAcc(0);
 #pragma unroll
-                for (int i = 0; i < D_IN; ++i)
+                for (int kq = 0; kq < KQ; ++kq) {
+                    const Vec4<TAcc> m4 = sM[cc][i * KQ + kq][lane];
 #pragma unroll
-                    for (int kq = 0; kq < KQ; ++kq) {
-                        const Vec4<TAcc> m4 = sM[cc][i * KQ + kq][lane];
+                    for (int t = 0; t < 4; ++t)
+                        if (kq * 4 + t < D_OUT) s += m4.v[t] * in.a[kq * 4 + t];
+                }
+                gin[i] = s;
+            }
+            if constexpr (IMPLICIT) {
+                TAcc part[D_IN];
 #pragma unroll
-                        for (int t = 0; t < 4; ++t)
-                            if (kq * 4 + t < D_OUT) {
+                for (int l = 0; l * l < D_IN; ++l) {
+                    TAcc s = TAcc(0);
 #pragma unroll
-                                for (int e = 0; e < EPT; ++e) out[e][kq * 4 + t] += v[e][i] * m4.v[t];
-                            }
+                    for (int i = l * l; i < (l + 1) * (l + 1); ++i) {
+                        s += in.Yz[i] * gin[i];
+                        part[i] = in.w0l[l] * gin[i];
                     }
-#pragma unroll
-                for (int e = 0; e < EPT; ++e)
-                    if (live && ok[e]) {
-#pragma unroll
-                        for (int k = 0; k < D_OUT; ++k) Vout[(zz[e] * D_OUT + k) * U + u] = from_acc<TAct>(out[e][k]);
-                    }
+                    if (live) gw0[z * gw0_ld + l * U + u] = from_acc<TAct>(s);
+                }
+                const TAcc tot = warp_multi_sum<TAcc, D_IN>(part, lane);
+                const int j = lane >> 1;
+                if (!(lane & 1) && j < D_IN) {
+                    if (nchunk == 1) gY[z * D_IN + j] += tot;  // single writer per (z, j)
+                    else atomicAdd(&gY[z * D_IN + j], tot);
+                }
             } else {
-                TAcc go[EPT][D_OUT];
+                if (live) {
 #pragma unroll
-                for (int e = 0; e < EPT; ++e)
-#pragma unroll
-                    for (int k = 0; k < D_OUT; ++k) go[e][k] = live ? to_acc<TAcc>(gVout[(zz[e] * D_OUT + k) * U + u]) : TAcc(0);
-                TAcc gin[EPT][D_IN];
-#pragma unroll
-                for (int i = 0; i < D_IN; ++i) {
-                    TAcc s[EPT];
-#pragma unroll
-                    for (int e = 0; e < EPT; ++e) s[e] = TAcc(0);
-#pragma unroll
-                    for (int kq = 0; kq < KQ; ++kq) {
-                        const Vec4<TAcc> m4 = sM[cc][i * KQ + kq][lane];
-#pragma unroll
-                        for (int t = 0; t < 4; ++t)
-                            if (kq * 4 + t < D_OUT) {
-#pragma unroll
-                                for (int e = 0; e < EPT; ++e) s[e] += m4.v[t] * go[e][kq * 4 + t];
-                            }
-                    }
-#pragma unroll
-                    for (int e = 0; e < EPT; ++e) gin[e][i] = s[e];
-                }
-#pragma unroll
-                for (int e = 0; e < EPT; ++e) {
-                    const int64_t z = zz[e];
-                    if constexpr (IMPLICIT) {
-                        TAcc part[D_IN];
-#pragma unroll
-                        for (int l = 0; l * l < D_IN; ++l) {
-                            const TAcc w0l = live ? to_acc<TAcc>(w0[z * w0_ld + l * U + u]) : TAcc(0);
-                            TAcc s = TAcc(0);
-#pragma unroll
-                            for (int i = l * l; i < (l + 1) * (l + 1); ++i) {
-                                s += Y[z * D_IN + i] * gin[e][i];
-                                part[i] = w0l * gin[e][i];
-                            }
-                            if (live && ok[e]) gw0[z * gw0_ld + l * U + u] = from_acc<TAct>(s);
-                        }
-                        const TAcc tot = warp_multi_sum<TAcc, D_IN>(part, lane);
-                        const int j = lane >> 1;
-                        if (ok[e] && !(lane & 1) && j < D_IN) {
-                            if (nchunk == 1) gY[z * D_IN + j] += tot;  // single writer per (z, j)
-                            else atomicAdd(&gY[z * D_IN + j], tot);
-                        }
-                    } else {
-                        if (live && ok[e]) {
-#pragma unroll
-                            for (int i = 0; i < D_IN; ++i) gVin[(z * D_IN + i) * U + u] = from_acc<TAct>(gin[e][i]);
-                        }
-                    }
+                    for (int i = 0; i < D_IN; ++i) gVin[(z * D_IN + i) * U + u] = from_acc<TAct>(gin[i]);
                 }
             }
         }
+    };
+    // two register buffers used alternately (loop unrolled by two, no buffer copy): the loads of the
+    // next item are in flight while the current one is computed
+    In bufA, bufB;
+    int64_t z = e_beg + warp;
+    if (z < e_end) load_in(z, bufA);
+    while (z < e_end) {
+        if (z + 8 < e_end) load_in(z + 8, bufB);
+        compute(bufA, z);
+        z += 8;
+        if (z >= e_end) break;
+        if (z + 8 < e_end) load_in(z + 8, bufA);
+        compute(bufB, z);
+        z += 8;
     }
 }
 
-template <typename TAct, typename TAcc, int D_IN, int D_OUT, int MODE, int MINB>
-int launch_v(int64_t N, int U, int D, int nnz, const int32_t* tab, const void* cgw, const int32_t* row_ptr, const void* gamma,
+template <typename TAct, typename TAcc, int D_IN, int D_OUT, int MODE, int MINB, int UT>
+int launch_u(int64_t N, int U, int D, int nnz, const int32_t* tab, const void* cgw, const int32_t* row_ptr, const void* gamma,
            const void* Vin, int implicit_v0, const void* Y, const void* w0, int64_t w0_ld, void* Vout, const void* gVout, void* gVin,
            void* gw0, int64_t gw0_ld, void* gY, cudaStream_t st) {
     dim3 grid(ab2_blocks(N, CPB), (unsigned)((U + 31) / 32));
     if (implicit_v0) {
         if constexpr (D_IN == 1 || D_IN == 4 || D_IN == 9 || D_IN == 16) {
-            tp_smem_kernel<TAct, TAcc, D_IN, D_OUT, true, MODE, MINB><<<grid, 256, 0, st>>>(
+            tp_smem_kernel<TAct, TAcc, D_IN, D_OUT, true, MODE, MINB, UT><<<grid, 256, 0, st>>>(
                 N, U, D, nnz, tab, (const TAcc*)cgw, row_ptr, (const TAcc*)gamma, nullptr, (const TAcc*)Y, (const TAct*)w0, w0_ld,
                 (TAct*)Vout, (const TAct*)gVout, nullptr, (TAct*)gw0, gw0_ld, (TAcc*)gY);
             return 0;
         }
         return -1;
     }
-    tp_smem_kernel<TAct, TAcc, D_IN, D_OUT, false, MODE, MINB><<<grid, 256, 0, st>>>(
+    tp_smem_kernel<TAct, TAcc, D_IN, D_OUT, false, MODE, MINB, UT><<<grid, 256, 0, st>>>(
         N, U, D, nnz, tab, (const TAcc*)cgw, row_ptr, (const TAcc*)gamma, (const TAct*)Vin, nullptr, nullptr, 0, (TAct*)Vout,
         (const TAct*)gVout, (TAct*)gVin, nullptr, 0, nullptr);
     return 0;
+}
+
+template <typename TAct, typename TAcc, int D_IN, int D_OUT, int MODE, int MINB>
+int launch_v(int64_t N, int U, int D, int nnz, const int32_t* tab, const void* cgw, const int32_t* row_ptr, const void* gamma,
+             const void* Vin, int implicit_v0, const void* Y, const void* w0, int64_t w0_ld, void* Vout, const void* gVout, void* gVin,
+             void* gw0, int64_t gw0_ld, void* gY, cudaStream_t st) {
+    if (U == 32)
+        return launch_u<TAct, TAcc, D_IN, D_OUT, MODE, MINB, 32>(N, U, D, nnz, tab, cgw, row_ptr, gamma, Vin, implicit_v0, Y, w0, w0_ld, Vout,
+                                                                gVout, gVin, gw0, gw0_ld, gY, st);
+    return launch_u<TAct, TAcc, D_IN, D_OUT, MODE, MINB, 0>(N, U, D, nnz, tab, cgw, row_ptr, gamma, Vin, implicit_v0, Y, w0, w0_ld, Vout,
+                                                           gVout, gVin, gw0, gw0_ld, gY, st);
 }
 
 template <typename TAct, typename TAcc, int D_IN, int D_OUT, int MODE, typename... A>
@@ -206,7 +237,7 @@ int launch(A... a) {
 
 }  // namespace
 
-int g_ab2_opt_tp_variant = 0;
+int g_ab2_opt_tp_variant = 1;  // 1: 3 CTAs/SM (80 registers), 0: 2 CTAs/SM (<=128 registers)
 
 int ab2_tp_smem(int mode, int dtype, int64_t N, int U, int D, int d_in, int d_out, int nnz, const int32_t* tab, const void* cgw,
                 const int32_t* row_ptr, const void* gamma, const void* Vin, int implicit_v0, const void* Y, const void* w0,

@@ -99,7 +99,9 @@ class Contracter(torch.nn.Module):
     # ---- tables for the kernels --------------------------------------------------------
     def sparse_table(self):
         """(ijk int32 [nnz,3], path int64 [nnz], value fp64 [nnz]) on the CPU."""
-        e = self.table.entries
+        # sorted by output target (i, k), then j: the fast kernels gather each M[i][k] entry from a
+        # contiguous table segment (include/allegro_b200.h, ab2_tp_fwd)
+        e = sorted(self.table.entries, key=lambda a: (a[0], a[2], a[1]))
         ijk = torch.tensor([[a[0], a[1], a[2]] for a in e], dtype=torch.int32)
         path = torch.tensor([a[3] for a in e], dtype=torch.long)
         val = torch.tensor([a[4] for a in e], dtype=torch.float64)

@@ -115,6 +115,8 @@ int ab2_env_bwd(int dtype, int lmax, int64_t N, int64_t E, int U, const int32_t*
 /* _contract.py:205-251 for one layer on the fused layout (a8, a10):
  *   Vout[z][k][u] = sum_i Vin[z][i][u] * M_c[u][i][k],
  *   M_c[u][i][k]  = sum_nnz cgw[nnz][u] * gamma[c][j_nnz][u]      (built once per centre)
+ * tab_ijk must be sorted by (i, k) (entries of one output target contiguous): the fast kernels
+ * gather every M[i][k] from its table segment.
  * implicit_v0 != 0: Vin[z][i][u] = Y[z][i] * w0[z][irrep(i)][u] is formed on the fly
  * (tensorembed.py:95) and never stored. */
 int ab2_tp_fwd(int dtype, int lmax, int64_t N, int64_t E, int U, int d_in, int d_out, int nnz,
