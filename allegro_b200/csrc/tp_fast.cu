@@ -203,8 +203,13 @@ __global__ void __launch_bounds__(NS * 32, 8) tp_bwd_gm_split_kernel(int64_t N, 
                                                                      const TAct* __restrict__ Vin, const TAcc* __restrict__ Y,
                                                                      const TAct* __restrict__ w0, int64_t w0_ld,
                                                                      const TAct* __restrict__ gVout, TAcc* __restrict__ ggamma) {
-    constexpr int IW = D_IN / NS;
-    static_assert(IW * NS == D_IN, "D_IN must be divisible by the split");
+    // explicit Vin: warp s owns input components i in [s*IW, (s+1)*IW) (Vin read once, gVout by all warps);
+    // implicit Vin = Y (x) w0 (cheap to rebuild): warp s owns OUTPUT components k instead, so the large
+    // gVout tensor is read exactly once and only the small w0 rows are re-read.
+    constexpr bool KSPLIT = IMPLICIT && (D_OUT % NS == 0);
+    constexpr int IW = KSPLIT ? D_IN : D_IN / NS;
+    constexpr int KW = KSPLIT ? D_OUT / NS : D_OUT;
+    static_assert(KSPLIT || IW * NS == D_IN, "D_IN must be divisible by the split");
     __shared__ TAcc sGM[D_IN * D_OUT][32];
     __shared__ TAcc sG[DG][32];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -213,34 +218,40 @@ __global__ void __launch_bounds__(NS * 32, 8) tp_bwd_gm_split_kernel(int64_t N, 
     const int u = (int)(blockIdx.x % nchunk) * 32 + lane;
     const bool live = u < U;
     const int beg = row_ptr[c], end = row_ptr[c + 1];
-    const int i0 = warp * IW;
-    TAcc gM[IW][D_OUT];
+    const int i0 = KSPLIT ? 0 : warp * IW;
+    const int k0 = KSPLIT ? warp * KW : 0;
+    TAcc gM[IW][KW];
 #pragma unroll
     for (int i = 0; i < IW; ++i)
 #pragma unroll
-        for (int k = 0; k < D_OUT; ++k) gM[i][k] = TAcc(0);
+        for (int k = 0; k < KW; ++k) gM[i][k] = TAcc(0);
 #pragma unroll 2
     for (int64_t z = beg; z < end; ++z) {
-        TAcc go[D_OUT], v[IW];
+        TAcc go[KW], v[IW];
 #pragma unroll
-        for (int k = 0; k < D_OUT; ++k) go[k] = live ? to_acc<TAcc>(gVout[(z * D_OUT + k) * U + u]) : TAcc(0);
+        for (int k = 0; k < KW; ++k) go[k] = live ? to_acc<TAcc>(gVout[(z * D_OUT + k0 + k) * U + u]) : TAcc(0);
+        if constexpr (IMPLICIT) {
+            TAcc w0l[5];
 #pragma unroll
-        for (int i = 0; i < IW; ++i) {
-            if constexpr (IMPLICIT) {
-                v[i] = live ? Y[z * D_IN + i0 + i] * to_acc<TAcc>(w0[z * w0_ld + sh_l_of(i0 + i) * U + u]) : TAcc(0);
-            } else {
-                v[i] = live ? to_acc<TAcc>(Vin[(z * D_IN + i0 + i) * U + u]) : TAcc(0);
-            }
+            for (int l = 0; l * l < D_IN; ++l) w0l[l] = TAcc(0);
+#pragma unroll
+            for (int l = 0; l * l < D_IN; ++l)
+                if (KSPLIT || (l * l < i0 + IW && (l + 1) * (l + 1) > i0)) w0l[l] = live ? to_acc<TAcc>(w0[z * w0_ld + l * U + u]) : TAcc(0);
+#pragma unroll
+            for (int i = 0; i < IW; ++i) v[i] = Y[z * D_IN + i0 + i] * w0l[sh_l_of(i0 + i)];
+        } else {
+#pragma unroll
+            for (int i = 0; i < IW; ++i) v[i] = live ? to_acc<TAcc>(Vin[(z * D_IN + i0 + i) * U + u]) : TAcc(0);
         }
 #pragma unroll
         for (int i = 0; i < IW; ++i)
 #pragma unroll
-            for (int k = 0; k < D_OUT; ++k) gM[i][k] += v[i] * go[k];
+            for (int k = 0; k < KW; ++k) gM[i][k] += v[i] * go[k];
     }
 #pragma unroll
     for (int i = 0; i < IW; ++i)
 #pragma unroll
-        for (int k = 0; k < D_OUT; ++k) sGM[(i0 + i) * D_OUT + k][lane] = gM[i][k];
+        for (int k = 0; k < KW; ++k) sGM[(i0 + i) * D_OUT + k0 + k][lane] = gM[i][k];
     __syncthreads();
     // ggamma[c][j][u] = sum_nnz cgw * gM[i][k]: warp w owns j = w, w+NS, ...; accumulators stay in
     // registers (selected by an if-chain), so there is no shared-memory read-modify-write chain.

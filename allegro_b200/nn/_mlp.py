@@ -105,6 +105,15 @@ class PackedMLP:
         # tcgen05 path: packed bf16 hi/lo images (None where the shape is not eligible)
         self.Wp = [_lib.linear_pack(w) for w in self.W]
         self.WTp = [_lib.linear_pack(w) for w in self.WT]
+        # a width-<16 output (the readout's single energy column) makes the backward GEMM's K < 16, which the
+        # tensor-core path cannot take: zero-pad K to 16 (the padded gradient columns are zero)
+        self.out_pad = None
+        n_out = ws[-1].shape[1]
+        if n_out < 16 and dtype != torch.float64:
+            wt = torch.zeros(16, ws[-1].shape[0], dtype=torch.float64)
+            wt[:n_out] = ws[-1].T
+            self.out_pad = wt.to(device=device, dtype=dtype).contiguous()
+            self.out_pad_p = _lib.linear_pack(self.out_pad)
         self.dims = [ws[0].shape[0]] + [w.shape[1] for w in ws]
         self.dtype = dtype
         self.device = device
@@ -133,15 +142,21 @@ class PackedMLP:
     def backward(self, gout_segs: Sequence[torch.Tensor], pre: List[torch.Tensor], gin_segs: Sequence[torch.Tensor], gin_accum: Sequence[bool]):
         M = gout_segs[0].shape[0]
         cur = list(gout_segs)
+        WT, WTp = list(self.WT), list(self.WTp)
+        if self.out_pad is not None and self.out_pad_p is not None and len(cur) == 1 and cur[0].is_contiguous():
+            pad = torch.zeros(M, 16, dtype=self.dtype, device=self.device)
+            pad[:, : cur[0].shape[1]] = cur[0]
+            cur = [pad]
+            WT[-1], WTp[-1] = self.out_pad, self.out_pad_p
         for k in range(self.n_layers - 1, -1, -1):
             if k == 0:
-                _lib.linear(cur, self.WT[0], gin_segs, o_accum=gin_accum, W_packed=self.WTp[0])
+                _lib.linear(cur, WT[0], gin_segs, o_accum=gin_accum, W_packed=WTp[0])
             else:
                 g = torch.empty(M, self.dims[k], dtype=self.dtype, device=self.device)
                 if self.silu:
-                    _lib.linear(cur, self.WT[k], [g], epi=_lib.EPI_MUL_DSILU, aux=pre[k - 1], W_packed=self.WTp[k])
+                    _lib.linear(cur, WT[k], [g], epi=_lib.EPI_MUL_DSILU, aux=pre[k - 1], W_packed=WTp[k])
                 else:
-                    _lib.linear(cur, self.WT[k], [g], W_packed=self.WTp[k])
+                    _lib.linear(cur, WT[k], [g], W_packed=WTp[k])
                 cur = [g]
 
     # ---- "plain GEMM" backward for the common 2-layer SiLU MLP -------------------------------
