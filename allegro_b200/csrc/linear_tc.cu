@@ -35,6 +35,7 @@ constexpr int RAW_DEPTH = 4;     // max cp.async stages in flight per producer t
 constexpr int RAW_STAGE = 256 * 4 * 16;  // bytes: 256 producer threads x 4 x 16-byte chunks (x2 with aux)
 constexpr int EPI_LD = 36;       // floats per staged row (32 + 4 pad): conflict-free 16-byte accesses
 constexpr int EPI_BYTES = 4 * 32 * EPI_LD * 4;  // 4 epilogue warps x 32 rows
+constexpr int PF_BYTES = 2 * EPI_BYTES;         // 2 prefetch buffers per epilogue warp (aux / old tiles)
 constexpr int STAGE_HALF = BM * KC * 2;  // bytes of one bf16 [128][32] operand image (8 KB)
 constexpr int NPROD = 8;                       // producer warps
 constexpr int NTHREADS = (NPROD + 1 + 4) * 32;  // producers + MMA issuer + epilogue
@@ -64,6 +65,7 @@ struct TcParams {
     int64_t num_tiles;
     int nstage;
     int debug;
+    int pf_mode;    // epilogue prefetch: 0 none, 1 aux (silu' epilogue), 2 old values (accumulate)
     int raw_depth;  // cp.async stages in flight per producer thread (2 or 4)
     int has_aux;    // act == AB2_ACT_MUL_DSILU: the raw slots carry A and aux chunks
 };
@@ -227,7 +229,7 @@ __device__ __forceinline__ void load8(const TcParams& p, int64_t m, int k, float
     for (int t = 0; t < 8; ++t) v[t] = 0.f;
 }
 
-template <typename TSrc, bool SPLIT>
+template <typename TSrc, bool SPLIT, int PF>
 __global__ void __launch_bounds__(NTHREADS, 1) linear_tc_kernel(const TcParams p) {
     extern __shared__ __align__(128) uint8_t smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -239,7 +241,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) linear_tc_kernel(const TcParams p
     uint8_t* sRaw = sA + p.nstage * stage_bytes;
     const int raw_stage = RAW_STAGE * (p.has_aux ? 2 : 1);
     float* sEpi = reinterpret_cast<float*>(sRaw + p.raw_depth * raw_stage);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(sEpi) + EPI_BYTES);
+    float* sPf = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(sEpi) + EPI_BYTES);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(sEpi) + EPI_BYTES + (PF ? PF_BYTES : 0));
     // bars: full[NSTAGE], empty[NSTAGE], tmem_full[2], tmem_empty[2]; then the TMEM base word
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NSTAGE + 4);
     const uint32_t bar0 = smem_u32(bars);
@@ -445,6 +448,53 @@ __global__ void __launch_bounds__(NTHREADS, 1) linear_tc_kernel(const TcParams p
         for (int64_t tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
             const int a = (int)(it & 1);
             const uint32_t aphase = (uint32_t)((it >> 1) & 1);
+            // ---- epilogue-side global reads (silu' aux or old values to accumulate) are prefetched with
+            //      cp.async into per-warp buffers, two 32-column chunks ahead, starting BEFORE the
+            //      accumulator is ready ----
+            const int64_t m_base0 = tile * BM + q * 32;
+            float* pfw = sPf + (warp & 3) * 2 * 32 * EPI_LD;
+            auto find_seg = [&](int c0, int& seg, int& seg_lo) {
+                seg = -1; seg_lo = 0;
+                if (!(sizeof(TSrc) == 4 && c0 + 32 <= p.N && !(p.debug & 64))) return;
+                int lo = 0;
+#pragma unroll
+                for (int s2 = 0; s2 < AB2_MAX_SEG; ++s2) {
+                    if (s2 < p.n_o) {
+                        if (c0 >= lo && c0 + 32 <= lo + p.o[s2].width) { seg = s2; seg_lo = lo; }
+                        lo += p.o[s2].width;
+                    }
+                }
+                if (seg >= 0) {
+                    const uintptr_t base = reinterpret_cast<uintptr_t>((const float*)p.o[seg].ptr + (c0 - seg_lo));
+                    if ((base & 15) || ((p.o[seg].ld * 4) & 15)) seg = -1;
+                    if (p.epi == AB2_EPI_MUL_DSILU &&
+                        ((reinterpret_cast<uintptr_t>((const float*)p.aux + c0) & 15) || ((p.aux_ld * 4) & 15))) seg = -1;
+                }
+            };
+            auto prefetch = [&](int c0) {
+                if constexpr (PF == 0) return;
+                if (c0 < p.Npad) {
+                    int seg, seg_lo;
+                    find_seg(c0, seg, seg_lo);
+                    if (seg >= 0 && (PF == 1 || p.o[seg].accum)) {
+                        const int rsub = lane >> 3, c4 = lane & 7;
+                        const float* gbase = (PF == 1) ? (const float*)p.aux + c0 + c4 * 4
+                                                              : (const float*)p.o[seg].ptr + (c0 - seg_lo) + c4 * 4;
+                        const int64_t gld = (PF == 1) ? p.aux_ld : p.o[seg].ld;
+                        float* dstb = pfw + ((c0 >> 5) & 1) * 32 * EPI_LD;
+#pragma unroll
+                        for (int itr = 0; itr < 8; ++itr) {
+                            const int row = itr * 4 + rsub;
+                            int64_t mr = m_base0 + row;
+                            if (mr >= p.M) mr = p.M - 1;
+                            cp_async16(smem_u32(dstb + row * EPI_LD + c4 * 4), gbase + mr * gld, 16u);
+                        }
+                    }
+                }
+                cp_async_commit();
+            };
+            prefetch(0);
+            prefetch(32);
             mbar_wait(tfull_bar(a), aphase);
             tc_fence_after();
             const int64_t m = tile * BM + q * 32 + lane;
@@ -517,22 +567,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) linear_tc_kernel(const TcParams p
                 tmem_ld_wait();
                 // coalesced path: the 32-column chunk lies inside one fp32 output segment, 16-byte aligned
                 int seg = -1, seg_lo = 0;
-                if (sizeof(TSrc) == 4 && two && c0 + 32 <= p.N && !(p.debug & 64)) {
-                    int lo = 0;
-#pragma unroll
-                    for (int s2 = 0; s2 < AB2_MAX_SEG; ++s2) {
-                        if (s2 < p.n_o) {
-                            if (c0 >= lo && c0 + 32 <= lo + p.o[s2].width) { seg = s2; seg_lo = lo; }
-                            lo += p.o[s2].width;
-                        }
-                    }
-                    if (seg >= 0) {
-                        const uintptr_t base = reinterpret_cast<uintptr_t>((const float*)p.o[seg].ptr + (c0 - seg_lo));
-                        if ((base & 15) || ((p.o[seg].ld * 4) & 15)) seg = -1;
-                        if (p.epi == AB2_EPI_MUL_DSILU &&
-                            ((reinterpret_cast<uintptr_t>((const float*)p.aux + c0) & 15) || ((p.aux_ld * 4) & 15))) seg = -1;
-                    }
-                }
+                if (two) find_seg(c0, seg, seg_lo);
+                if constexpr (PF != 0) cp_async_wait<1>();  // this chunk's prefetch group (if any) has landed
                 if (p.debug & 1) {
                 } else if (seg >= 0) {
                     // stage my row (lane) : 32 floats -> shared, then every global access covers 4 rows x 128 B
@@ -561,11 +597,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) linear_tc_kernel(const TcParams p
                         ok[itr] = mr < p.M;
                         mrc[itr] = ok[itr] ? mr : p.M - 1;
                     }
+                    const float* pfb = pfw + ((c0 >> 5) & 1) * 32 * EPI_LD;
                     if (epi) {
                         float4 ax[8];
 #pragma unroll
                         for (int itr = 0; itr < 8; ++itr)
-                            ax[itr] = __ldg(reinterpret_cast<const float4*>(abase + mrc[itr] * p.aux_ld));
+                            ax[itr] = (PF == 1) ? *reinterpret_cast<const float4*>(pfb + (itr * 4 + rsub) * EPI_LD + c4 * 4)
+                                                       : __ldg(reinterpret_cast<const float4*>(abase + mrc[itr] * p.aux_ld));
 #pragma unroll
                         for (int itr = 0; itr < 8; ++itr) {
                             x[itr].x *= dsilu_fast(ax[itr].x); x[itr].y *= dsilu_fast(ax[itr].y);
@@ -576,7 +614,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) linear_tc_kernel(const TcParams p
                         float4 old[8];
 #pragma unroll
                         for (int itr = 0; itr < 8; ++itr)
-                            old[itr] = *reinterpret_cast<const float4*>(obase + mrc[itr] * old_ld);
+                            old[itr] = (PF == 2) ? *reinterpret_cast<const float4*>(pfb + (itr * 4 + rsub) * EPI_LD + c4 * 4)
+                                                        : *reinterpret_cast<const float4*>(obase + mrc[itr] * old_ld);
 #pragma unroll
                         for (int itr = 0; itr < 8; ++itr) {
                             x[itr].x += old[itr].x; x[itr].y += old[itr].y; x[itr].z += old[itr].z; x[itr].w += old[itr].w;
@@ -589,6 +628,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) linear_tc_kernel(const TcParams p
                 } else {
                     process(c0, r0);
                     if (two) process(c0 + 16, r1);
+                }
+                if constexpr (PF != 0) {
+                    __syncwarp();
+                    prefetch(c0 + 64);  // refill the buffer just consumed (always commits a group)
                 }
             }
             tc_fence_before();
@@ -659,6 +702,11 @@ int ab2_linear_tc_try(int dtype, int64_t M, int K, int N, int n_a, const void* c
             ((reinterpret_cast<uintptr_t>(a_aux[s]) % 16) != 0 || (a_aux_ld[s] * esz) % 16 != 0)) return -1;
     }
     const int has_aux = (act == AB2_ACT_MUL_DSILU && a_aux) ? 1 : 0;
+    int pf_mode = 0;
+    if (dtype == AB2_F32) {
+        if (epi == AB2_EPI_MUL_DSILU) pf_mode = 1;
+        else if (o_accum) for (int s = 0; s < n_o; ++s) if (o_accum[s]) pf_mode = 2;
+    }
     static int num_sms = 0;
     static int max_smem = 0;
     if (num_sms == 0) {
@@ -687,23 +735,30 @@ int ab2_linear_tc_try(int dtype, int64_t M, int K, int N, int n_a, const void* c
     const int plans[4][2] = {{4, NSTAGE}, {4, 2}, {2, NSTAGE}, {2, 2}};
     for (int q = 0; q < 4 && !nstage; ++q) {
         const size_t need = ((w_bytes + 127) & ~127) + (size_t)plans[q][1] * stage_bytes + (size_t)plans[q][0] * raw_stage + EPI_BYTES +
-                            (2 * NSTAGE + 4) * 8 + 16;
+                            (pf_mode ? PF_BYTES : 0) + (2 * NSTAGE + 4) * 8 + 16;
         if ((int)need <= max_smem) { raw_depth = plans[q][0]; nstage = plans[q][1]; smem = need; }
     }
     if (!nstage) return -1;
     p.nstage = nstage;
     p.raw_depth = raw_depth;
+    p.pf_mode = pf_mode;
     p.debug = g_ab2_opt_tc_debug;
     const unsigned grid = (unsigned)((p.num_tiles < num_sms) ? p.num_tiles : num_sms);
     cudaError_t e;
+    auto go = [&](auto kern) -> int {
+        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+            cudaGetLastError();
+            return -1;
+        }
+        kern<<<grid, NTHREADS, smem, st>>>(p);
+        return 0;
+    };
+    (void)e;
     if (split) {
-        e = cudaFuncSetAttribute(linear_tc_kernel<float, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) { cudaGetLastError(); return -1; }
-        linear_tc_kernel<float, true><<<grid, NTHREADS, smem, st>>>(p);
-    } else {
-        e = cudaFuncSetAttribute(linear_tc_kernel<bf16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) { cudaGetLastError(); return -1; }
-        linear_tc_kernel<bf16, false><<<grid, NTHREADS, smem, st>>>(p);
+        if (pf_mode == 1) return go(linear_tc_kernel<float, true, 1>);
+        if (pf_mode == 2) return go(linear_tc_kernel<float, true, 2>);
+        return go(linear_tc_kernel<float, true, 0>);
     }
-    return 0;
+    return go(linear_tc_kernel<bf16, false, 0>);
 }
+

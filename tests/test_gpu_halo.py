@@ -1,0 +1,75 @@
+"""Multi-GPU parity (needs >= 2 CUDA devices, skipped otherwise): slab decomposition + NCCL halo with the
+CUDA model on every rank == the single-GPU periodic evaluation of the same frame."""
+import os
+import socket
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, q):
+    import torch.distributed as dist
+
+    from allegro_b200 import systems
+    from allegro_b200.halo import DistributedAllegro, SlabDecomposition
+    from allegro_b200.model import AllegroModel
+
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dev = torch.device("cuda", rank)
+    torch.cuda.set_device(dev)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    try:
+        pos, cell, types = systems.make_positions("c2", (6, 3, 3))
+        kw = systems.model_kwargs("c2", 42.0, "float64")
+        model = AllegroModel(**kw).to(dev).model
+        dec = SlabDecomposition(pos, cell, types, 5.0, rank, world)
+        pos_owned = dec.local_positions_from_global(pos)[: dec.n_owned].to(dev)
+        dec.to(dev)
+        e_tot, f_owned, e_atoms = DistributedAllegro(model, dec)(pos_owned)
+        q.put((rank, dec.owned.cpu(), f_owned.cpu(), e_atoms.cpu(), float(e_tot)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_nccl_halo_matches_single_gpu():
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import torch.multiprocessing as mp
+
+    from allegro_b200 import data as D
+    from allegro_b200 import systems
+    from allegro_b200.model import AllegroModel
+
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=600) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    d = systems.make_system("c2", (6, 3, 3))
+    kw = systems.model_kwargs("c2", 42.0, "float64")
+    ref = AllegroModel(**kw).to("cuda:0")({k: v.to("cuda:0") for k, v in d.items()})
+    n = d[D.POSITIONS_KEY].shape[0]
+    F = torch.zeros(n, 3, dtype=torch.float64)
+    Ea = torch.zeros(n, 1, dtype=torch.float64)
+    for rank, owned, f, ea, e_tot in res:
+        F[owned] = f.double()
+        Ea[owned] = ea.double()
+        assert e_tot == pytest.approx(ref[D.TOTAL_ENERGY_KEY].item(), rel=1e-10)
+    assert (Ea - ref[D.PER_ATOM_ENERGY_KEY].cpu()).abs().max() < 1e-9
+    assert (F - ref[D.FORCE_KEY].cpu()).abs().max() < 1e-9

@@ -37,8 +37,7 @@ def run(awid, owid, dtype, debug=0, tc=True, epi=0, accum=False, reps=10):
 for awid, owid in shapes:
     K, N = sum(awid), sum(owid)
     line = f"K={K:3d} N={N:3d}:"
-    for name, kw in [("full", {}), ("noStore", dict(debug=1)), ("noLoad", dict(debug=2)), ("noMMA", dict(debug=4)), ("direct", dict(debug=64)),
-                     ("none", dict(debug=7)), ("dsilu", dict(epi=1)), ("accum", dict(accum=True)), ("dsilu+acc", dict(epi=1, accum=True))]:
+    for name, kw in [("full", {}), ("dsilu", dict(epi=1)), ("accum", dict(accum=True)), ("dsilu+acc", dict(epi=1, accum=True))]:
         ms, gbs = run(awid, owid, torch.float32, **kw)
         line += f"  {name} {ms*1e3:6.0f}us ({gbs:5.0f}GB/s)"
     print(line, flush=True)
