@@ -35,10 +35,30 @@ def _worker(rank, world, port, q):
         dec = SlabDecomposition(pos, cell, types, 5.0, rank, world)
         pos_owned = dec.local_positions_from_global(pos)[: dec.n_owned].to(dev)
         dec.to(dev)
-        e_tot, f_owned, e_atoms = DistributedAllegro(model, dec)(pos_owned)
-        q.put((rank, dec.owned.cpu(), f_owned.cpu(), e_atoms.cpu(), float(e_tot)))
-    finally:
+        runner = DistributedAllegro(model, dec)
+        e_tot, f_owned, e_atoms = runner(pos_owned)
+        # the same step replayed from a CUDA graph (NCCL halo captured) on displaced positions
+        from allegro_b200.halo import GraphedDistributedAllegro
+
+        g = torch.Generator().manual_seed(7 + rank)
+        pos2 = pos_owned + 0.05 * torch.randn(pos_owned.shape, generator=g, dtype=pos_owned.dtype).to(dev)
+        e2, f2, _ = runner(pos2)
+        graphed = GraphedDistributedAllegro(runner, pos_owned)
+        eg, fg, _ = graphed(pos2)
+        torch.cuda.synchronize()
+        gerr = max(float((fg - f2).abs().max()), abs(float(eg) - float(e2)))
+        # plain numpy payloads: torch tensors travel as shared-memory handles that die with this process
+        q.put((rank, dec.owned.cpu().numpy(), f_owned.cpu().numpy(), e_atoms.cpu().numpy(), float(e_tot), gerr))
+        # a live graph with captured NCCL kernels blocks communicator teardown: flush the queue and
+        # leave without the destructors (the parent checks exit code 0)
+        dist.barrier()
+        torch.cuda.synchronize()
+        q.close()
+        q.join_thread()
+        os._exit(0)
+    except BaseException:
         dist.destroy_process_group()
+        raise
 
 
 def test_nccl_halo_matches_single_gpu():
@@ -67,9 +87,11 @@ def test_nccl_halo_matches_single_gpu():
     n = d[D.POSITIONS_KEY].shape[0]
     F = torch.zeros(n, 3, dtype=torch.float64)
     Ea = torch.zeros(n, 1, dtype=torch.float64)
-    for rank, owned, f, ea, e_tot in res:
-        F[owned] = f.double()
-        Ea[owned] = ea.double()
+    for rank, owned, f, ea, e_tot, gerr in res:
+        assert gerr < 1e-9
+        owned = torch.from_numpy(owned)
+        F[owned] = torch.from_numpy(f).double()
+        Ea[owned] = torch.from_numpy(ea).double()
         assert e_tot == pytest.approx(ref[D.TOTAL_ENERGY_KEY].item(), rel=1e-10)
     assert (Ea - ref[D.PER_ATOM_ENERGY_KEY].cpu()).abs().max() < 1e-9
     assert (F - ref[D.FORCE_KEY].cpu()).abs().max() < 1e-9
