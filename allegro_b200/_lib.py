@@ -81,6 +81,11 @@ def load() -> C.CDLL:
         fn.argtypes = args
         fn.restype = res
     _LIB = lib
+    # tuning switches for experiments: ALLEGRO_B200_OPTIONS="env_split=4,tp_variant=0"
+    for kv in filter(None, os.environ.get("ALLEGRO_B200_OPTIONS", "").split(",")):
+        k, v = kv.split("=")
+        if lib.ab2_set_option(k.strip().encode(), int(v)) != 0:
+            raise RuntimeError(f"ALLEGRO_B200_OPTIONS: unknown option {k!r}")
     return lib
 
 

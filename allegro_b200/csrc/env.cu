@@ -9,23 +9,31 @@
 // Layouts: Y[E][D] (TAcc), w[z][n_ir][U] (TAct, leading dim w_ld), gamma[N][D][U] (TAcc).
 #include "common.cuh"
 
-template <typename TAct, typename TAcc, int LMAX>
+extern int g_ab2_opt_env_split;  // warps per (centre, channel chunk) in env_sum / env_bwd: 1, 2 or 4
+
+// SPLIT warps of one CTA share a (centre, 32-channel chunk): each streams every SPLIT-th edge of the
+// row, the partial sums meet in shared memory.  One warp per centre (SPLIT = 1) leaves only ~2 waves
+// of long serial loops (42 edges/centre on c2) and is latency-bound at ~50 % of the HBM rate.
+template <typename TAct, typename TAcc, int LMAX, int SPLIT>
 __global__ void __launch_bounds__(128) env_sum_kernel(int64_t N, int U, const int32_t* __restrict__ row_ptr,
                                                       const TAcc* __restrict__ Y, const TAct* __restrict__ w, int64_t w_ld,
                                                       TAcc sf, TAcc* __restrict__ gamma) {
     constexpr int D = (LMAX + 1) * (LMAX + 1);
+    __shared__ TAcc red[SPLIT > 1 ? 4 : 1][SPLIT > 1 ? D : 1][32];
     const int nchunk = (U + 31) >> 5;
-    const int64_t wid = ((int64_t)blockIdx.x * 128 + threadIdx.x) >> 5;
-    const int lane = threadIdx.x & 31;
-    const int64_t c = wid / nchunk;
-    if (c >= N) return;
-    const int u = (int)(wid % nchunk) * 32 + lane;
-    const bool live = u < U;
-    const int beg = row_ptr[c], end = row_ptr[c + 1];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t grp = ((int64_t)blockIdx.x * 4 + warp) / SPLIT;
+    const int sub = warp % SPLIT;
+    const int64_t c = grp / nchunk;
+    const bool valid = c < N;
+    const int u = (int)(grp % nchunk) * 32 + lane;
+    const bool live = valid && u < U;
+    const int beg = valid ? row_ptr[c] : 0, end = valid ? row_ptr[c + 1] : 0;
     TAcc acc[D];
 #pragma unroll
     for (int j = 0; j < D; ++j) acc[j] = TAcc(0);
-    for (int z = beg; z < end; ++z) {
+#pragma unroll 2
+    for (int z = beg + sub; z < end; z += SPLIT) {
         const TAcc* __restrict__ Yz = Y + (int64_t)z * D;
         const TAct* __restrict__ wz = w + (int64_t)z * w_ld;
 #pragma unroll
@@ -35,7 +43,21 @@ __global__ void __launch_bounds__(128) env_sum_kernel(int64_t N, int U, const in
             for (int j = l * l; j < (l + 1) * (l + 1); ++j) acc[j] += Yz[j] * wl;
         }
     }
-    if (live) {
+    if constexpr (SPLIT > 1) {
+        if (sub != 0) {
+#pragma unroll
+            for (int j = 0; j < D; ++j) red[warp][j][lane] = acc[j];
+        }
+        __syncthreads();
+        if (sub == 0) {
+#pragma unroll
+            for (int t = 1; t < SPLIT; ++t) {
+#pragma unroll
+                for (int j = 0; j < D; ++j) acc[j] += red[warp + t][j][lane];
+            }
+        }
+    }
+    if (live && sub == 0) {
 #pragma unroll
         for (int j = 0; j < D; ++j) gamma[((int64_t)c * D + j) * U + u] = sf * acc[j];
     }
@@ -81,7 +103,7 @@ __global__ void __launch_bounds__(128) env_bwd_kernel(int64_t E, int U, const in
 
 // Warp per (centre, 32-channel chunk): ggamma[c][.][u] is loaded once into registers and the
 // centre's edges are streamed (two in flight).  Same arithmetic as env_bwd_kernel.
-template <typename TAct, typename TAcc, int LMAX>
+template <typename TAct, typename TAcc, int LMAX, int SPLIT>
 __global__ void __launch_bounds__(128) env_bwd_fast_kernel(int64_t N, int U, const int32_t* __restrict__ row_ptr,
                                                            const TAcc* __restrict__ Y, const TAct* __restrict__ w, int64_t w_ld,
                                                            const TAcc* __restrict__ ggamma, TAcc sf, TAct* __restrict__ gw,
@@ -90,16 +112,18 @@ __global__ void __launch_bounds__(128) env_bwd_fast_kernel(int64_t N, int U, con
     const int nchunk = (U + 31) >> 5;
     const int64_t wid = ((int64_t)blockIdx.x * 128 + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
-    const int64_t c = wid / nchunk;
+    const int64_t grp = wid / SPLIT;  // SPLIT warps stream interleaved edges of one (centre, chunk)
+    const int sub = (int)(wid % SPLIT);
+    const int64_t c = grp / nchunk;
     if (c >= N) return;
-    const int u = (int)(wid % nchunk) * 32 + lane;
+    const int u = (int)(grp % nchunk) * 32 + lane;
     const bool live = u < U;
     const int beg = row_ptr[c], end = row_ptr[c + 1];
     TAcc gg[D];
 #pragma unroll
     for (int j = 0; j < D; ++j) gg[j] = live ? sf * ggamma[(c * D + j) * U + u] : TAcc(0);
 #pragma unroll 2
-    for (int64_t z = beg; z < end; ++z) {
+    for (int64_t z = beg + sub; z < end; z += SPLIT) {
         TAcc Yz[D], wl[LMAX + 1];
 #pragma unroll
         for (int j = 0; j < D; ++j) Yz[j] = Y[z * D + j];
@@ -131,9 +155,20 @@ extern "C" int ab2_env_sum(int dtype, int lmax, int64_t N, int U, const int32_t*
     AB2_CHECK_ARG(row_ptr && Y && w && gamma && U > 0, "null pointer / U");
     AB2_CHECK_ARG(w_ld >= (int64_t)(lmax + 1) * U, "w_ld too small");
     cudaStream_t st = (cudaStream_t)stream;
-    const int64_t warps = N * ((U + 31) / 32);
-    AB2_DISPATCH_DTYPE(dtype, AB2_DISPATCH_LMAX(lmax, env_sum_kernel<TAct, TAcc, LMAX><<<ab2_blocks(warps * 32, 128), 128, 0, st>>>(
-                                                          N, U, row_ptr, (const TAcc*)Y, (const TAct*)w, w_ld, (TAcc)sf, (TAcc*)gamma)));
+    const int64_t groups = N * ((U + 31) / 32);
+    // auto (0): 4 warps per centre when one warp would cover all channels (U <= 32: +85 % on c2),
+    // one otherwise (U = 64 measured slower when split)
+    const int split = g_ab2_opt_env_split ? g_ab2_opt_env_split : (U <= 32 ? 4 : 1);
+    if (split >= 4) {
+        AB2_DISPATCH_DTYPE(dtype, AB2_DISPATCH_LMAX(lmax, env_sum_kernel<TAct, TAcc, LMAX, 4><<<ab2_blocks(groups * 4 * 32, 128), 128, 0, st>>>(
+                                                              N, U, row_ptr, (const TAcc*)Y, (const TAct*)w, w_ld, (TAcc)sf, (TAcc*)gamma)));
+    } else if (split >= 2) {
+        AB2_DISPATCH_DTYPE(dtype, AB2_DISPATCH_LMAX(lmax, env_sum_kernel<TAct, TAcc, LMAX, 2><<<ab2_blocks(groups * 2 * 32, 128), 128, 0, st>>>(
+                                                              N, U, row_ptr, (const TAcc*)Y, (const TAct*)w, w_ld, (TAcc)sf, (TAcc*)gamma)));
+    } else {
+        AB2_DISPATCH_DTYPE(dtype, AB2_DISPATCH_LMAX(lmax, env_sum_kernel<TAct, TAcc, LMAX, 1><<<ab2_blocks(groups * 32, 128), 128, 0, st>>>(
+                                                              N, U, row_ptr, (const TAcc*)Y, (const TAct*)w, w_ld, (TAcc)sf, (TAcc*)gamma)));
+    }
     AB2_CUDA_LAUNCH_CHECK();
     return 0;
 }
@@ -147,20 +182,25 @@ extern "C" int ab2_env_bwd(int dtype, int lmax, int64_t N, int64_t E, int U, con
     AB2_CHECK_ARG(ctr && Y && w && ggamma && gw && gY && U > 0, "null pointer / U");
     cudaStream_t st = (cudaStream_t)stream;
     if (g_ab2_opt_tp_fast && row_ptr && lmax <= 3) {
-        const int64_t warps = N * ((U + 31) / 32);
-        if (lmax == 3) {
-            AB2_DISPATCH_DTYPE(dtype, env_bwd_fast_kernel<TAct, TAcc, 3><<<ab2_blocks(warps * 32, 128), 128, 0, st>>>(
-                                          N, U, row_ptr, (const TAcc*)Y, (const TAct*)w, w_ld, (const TAcc*)ggamma, (TAcc)sf, (TAct*)gw, gw_ld, (TAcc*)gY));
-        } else if (lmax == 2) {
-            AB2_DISPATCH_DTYPE(dtype, env_bwd_fast_kernel<TAct, TAcc, 2><<<ab2_blocks(warps * 32, 128), 128, 0, st>>>(
-                                          N, U, row_ptr, (const TAcc*)Y, (const TAct*)w, w_ld, (const TAcc*)ggamma, (TAcc)sf, (TAct*)gw, gw_ld, (TAcc*)gY));
-        } else if (lmax == 1) {
-            AB2_DISPATCH_DTYPE(dtype, env_bwd_fast_kernel<TAct, TAcc, 1><<<ab2_blocks(warps * 32, 128), 128, 0, st>>>(
-                                          N, U, row_ptr, (const TAcc*)Y, (const TAct*)w, w_ld, (const TAcc*)ggamma, (TAcc)sf, (TAct*)gw, gw_ld, (TAcc*)gY));
-        } else {
-            AB2_DISPATCH_DTYPE(dtype, env_bwd_fast_kernel<TAct, TAcc, 0><<<ab2_blocks(warps * 32, 128), 128, 0, st>>>(
-                                          N, U, row_ptr, (const TAcc*)Y, (const TAct*)w, w_ld, (const TAcc*)ggamma, (TAcc)sf, (TAct*)gw, gw_ld, (TAcc*)gY));
-        }
+        // auto (0): split only when a centre needs several channel chunks (U = 64: 500 -> 345 us; U = 32: no gain)
+        const int opt = g_ab2_opt_env_split ? g_ab2_opt_env_split : (U > 32 && dtype != AB2_F64 ? 4 : 1);
+        const int split = opt >= 4 ? 4 : opt >= 2 ? 2 : 1;
+        const int64_t warps = N * ((U + 31) / 32) * split;
+#define AB2_ENV_BWD(L, SP)                                                                                              \
+    AB2_DISPATCH_DTYPE(dtype, env_bwd_fast_kernel<TAct, TAcc, L, SP><<<ab2_blocks(warps * 32, 128), 128, 0, st>>>(           \
+                                  N, U, row_ptr, (const TAcc*)Y, (const TAct*)w, w_ld, (const TAcc*)ggamma, (TAcc)sf, (TAct*)gw, gw_ld, (TAcc*)gY))
+#define AB2_ENV_BWD_L(L)                                  \
+    do {                                                  \
+        if (split == 4) { AB2_ENV_BWD(L, 4); }            \
+        else if (split == 2) { AB2_ENV_BWD(L, 2); }       \
+        else { AB2_ENV_BWD(L, 1); }                       \
+    } while (0)
+        if (lmax == 3) AB2_ENV_BWD_L(3);
+        else if (lmax == 2) AB2_ENV_BWD_L(2);
+        else if (lmax == 1) AB2_ENV_BWD_L(1);
+        else AB2_ENV_BWD_L(0);
+#undef AB2_ENV_BWD_L
+#undef AB2_ENV_BWD
         AB2_CUDA_LAUNCH_CHECK();
         return 0;
     }

@@ -40,6 +40,11 @@ constexpr int STAGE_HALF = BM * KC * 2;  // bytes of one bf16 [128][32] operand 
 constexpr int NPROD = 8;                       // producer warps
 constexpr int NTHREADS = (NPROD + 1 + 4) * 32;  // producers + MMA issuer + epilogue
 constexpr int MAX_W_BYTES = 128 * 1024;
+constexpr int MAX_K = 512;                     // k-chunk table size (MAX_K / 8 entries)
+constexpr int MAX_CHUNK = 8;                   // 32-column output chunks (Npad <= 256)
+// tail of the shared-memory plan: barriers | TMEM base word | output chunk table | A / aux k-chunk tables
+constexpr int TAIL_BARS = 96, TAIL_SLOT = 16, TAIL_CHUNK = MAX_CHUNK * 32, TAIL_KMAP = (MAX_K / 8) * 16;
+constexpr int TAIL_BYTES = TAIL_BARS + TAIL_SLOT + TAIL_CHUNK + 2 * TAIL_KMAP;
 
 struct TcSeg {
     const void* ptr;
@@ -69,6 +74,23 @@ struct TcParams {
     int raw_depth;  // cp.async stages in flight per producer thread (2 or 4)
     int has_aux;    // act == AB2_ACT_MUL_DSILU: the raw slots carry A and aux chunks
 };
+
+// Address tables built once per CTA so that the per-item / per-chunk code of the producer and
+// epilogue warps is a shared-memory lookup plus 32-bit offsets.  (Walking the segment list and doing
+// 64-bit index arithmetic per access made both warp groups instruction-latency bound: ~1 us per
+// 32x32 output chunk on a single warp, a third of the HBM write rate.)
+struct KEnt {        // source of concat columns [8e, 8e+8): pointer to (row 0, that column), row stride
+    const void* ptr; // null: beyond K (or, in the aux table, a segment without silu' multiplier)
+    int64_t ld;      // elements
+};
+struct ChunkInfo {   // 32-column output chunk c0 = 32*i
+    float* optr;       // (row 0, column c0) of the output segment that contains the chunk
+    const float* aptr; // (row 0, column c0) of the silu' aux matrix
+    int64_t ld;        // output row stride (elements)
+    int32_t accum;
+    int32_t ok;        // 1: chunk lies inside one fp32 segment, 16-byte aligned -> coalesced path
+};
+static_assert(sizeof(KEnt) == 16 && sizeof(ChunkInfo) == 32, "table entry sizes");
 
 // ---- PTX wrappers ---------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -148,6 +170,22 @@ __device__ __forceinline__ void cp_async16(uint32_t dst_smem, const void* src, u
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// explicit global-space accesses (table pointers come out of shared memory, so the compiler would
+// otherwise emit generic LD/ST)
+__device__ __forceinline__ void stg128(float* p, const float4& v) {
+    asm volatile("st.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ float4 ldg128(const float* p) {
+    float4 v;
+    asm volatile("ld.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ float4 ldg128_nc(const float* p) {
+    float4 v;
+    asm volatile("ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+    return v;
+}
 
 // global address of concat columns [k, k+8) of row m (nullptr if outside K)
 template <typename TSrc>
@@ -245,6 +283,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) linear_tc_kernel(const TcParams p
     uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(sEpi) + EPI_BYTES + (PF ? PF_BYTES : 0));
     // bars: full[NSTAGE], empty[NSTAGE], tmem_full[2], tmem_empty[2]; then the TMEM base word
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NSTAGE + 4);
+    static_assert((2 * NSTAGE + 4) * 8 == TAIL_BARS, "barrier block size");
+    ChunkInfo* sChunk = reinterpret_cast<ChunkInfo*>(reinterpret_cast<uint8_t*>(bars) + TAIL_BARS + TAIL_SLOT);
+    KEnt* sKmap = reinterpret_cast<KEnt*>(reinterpret_cast<uint8_t*>(sChunk) + TAIL_CHUNK);
+    KEnt* sKaux = sKmap + MAX_K / 8;
     const uint32_t bar0 = smem_u32(bars);
     auto full_bar = [&](int s) { return bar0 + 8u * s; };
     auto empty_bar = [&](int s) { return bar0 + 8u * (NSTAGE + s); };
@@ -264,6 +306,56 @@ __global__ void __launch_bounds__(NTHREADS, 1) linear_tc_kernel(const TcParams p
         fence_barrier_init();
     }
     if (warp == NPROD) tmem_alloc(smem_u32(tmem_slot), 512);
+    if (threadIdx.x < MAX_K / 8) {
+        // k-chunk tables: which A segment (and aux segment) holds concat columns [8e, 8e+8)
+        const int e = threadIdx.x;
+        KEnt ent{nullptr, 0}, aent{nullptr, 0};
+        int kk = e * 8;
+        bool found = kk >= p.K;
+#pragma unroll
+        for (int sgi = 0; sgi < AB2_MAX_SEG; ++sgi) {
+            if (sgi < p.n_a && !found) {
+                if (kk < p.a[sgi].width) {
+                    ent.ptr = (const TSrc*)p.a[sgi].ptr + kk;
+                    ent.ld = p.a[sgi].ld;
+                    if (p.a[sgi].aux) {
+                        aent.ptr = (const TSrc*)p.a[sgi].aux + kk;
+                        aent.ld = p.a[sgi].aux_ld;
+                    }
+                    found = true;
+                }
+                kk -= p.a[sgi].width;
+            }
+        }
+        sKmap[e] = ent;
+        sKaux[e] = aent;
+    } else if (threadIdx.x < MAX_K / 8 + MAX_CHUNK) {
+        // output chunk table
+        const int c0 = (threadIdx.x - MAX_K / 8) * 32;
+        ChunkInfo info{nullptr, nullptr, 0, 0, 0};
+        if (sizeof(TSrc) == 4 && c0 + 32 <= p.N && !(p.debug & 64)) {
+            int lo = 0, seg = -1, seg_lo = 0;
+#pragma unroll
+            for (int s2 = 0; s2 < AB2_MAX_SEG; ++s2) {
+                if (s2 < p.n_o) {
+                    if (c0 >= lo && c0 + 32 <= lo + p.o[s2].width) { seg = s2; seg_lo = lo; }
+                    lo += p.o[s2].width;
+                }
+            }
+            if (seg >= 0) {
+                float* base = (float*)p.o[seg].ptr + (c0 - seg_lo);
+                bool ok = !(reinterpret_cast<uintptr_t>(base) & 15) && !((p.o[seg].ld * 4) & 15);
+                if (p.epi == AB2_EPI_MUL_DSILU &&
+                    ((reinterpret_cast<uintptr_t>((const float*)p.aux + c0) & 15) || ((p.aux_ld * 4) & 15))) ok = false;
+                info.optr = base;
+                info.aptr = (const float*)p.aux + c0;
+                info.ld = p.o[seg].ld;
+                info.accum = p.o[seg].accum;
+                info.ok = ok ? 1 : 0;
+            }
+        }
+        sChunk[threadIdx.x - MAX_K / 8] = info;
+    }
     // stage W (pre-packed canonical image) with plain 16-byte copies
     {
         const uint4* src = reinterpret_cast<const uint4*>(p.Wpacked);
@@ -292,40 +384,52 @@ __global__ void __launch_bounds__(NTHREADS, 1) linear_tc_kernel(const TcParams p
         uint32_t phase = 0;
         constexpr int CH = (sizeof(TSrc) == 4) ? 2 : 1;  // 16-byte chunks per 8 elements
         const uint32_t raw_u = smem_u32(sRaw);
-        // issue the asynchronous copies of work item `seq` into this thread's private raw slot
-        auto issue = [&](int64_t seq) {
-            if (seq < total) {
-                const int64_t tile = blockIdx.x + (seq / nkb) * gridDim.x;
-                const int kb = (int)(seq % nkb);
-                const int k = kb * KC + kc * 8;
-                const int slot = (int)(seq % p.raw_depth);
+        // Cursors of the next work item to issue / to fetch (tile, k block, raw slot): plain counters,
+        // no 64-bit div/mod per item.
+        int64_t i_tile = blockIdx.x, i_seq = 0;
+        int i_kb = 0, i_slot = 0, f_kb = 0, f_slot = 0;
+        // issue the asynchronous copies of the next work item into this thread's private raw slot
+        auto issue = [&]() {
+            if (i_seq < total) {
+                const int64_t row0 = i_tile * BM;
+                const int64_t left = p.M - row0;
+                const int rows_left = left < BM ? (int)left : BM;
+                const KEnt e = sKmap[i_kb * (KC / 8) + kc];
+                const bool kok = e.ptr != nullptr && !(p.debug & 2);
+                const uint8_t* tb = reinterpret_cast<const uint8_t*>(e.ptr) + row0 * e.ld * (int64_t)sizeof(TSrc);
+                const uint32_t pitch = (uint32_t)e.ld * (uint32_t)sizeof(TSrc);
+                KEnt ea{nullptr, 0};
+                if (p.has_aux) ea = sKaux[i_kb * (KC / 8) + kc];
+                const uint8_t* tba = reinterpret_cast<const uint8_t*>(ea.ptr) + row0 * ea.ld * (int64_t)sizeof(TSrc);
+                const uint32_t pitch_a = (uint32_t)ea.ld * (uint32_t)sizeof(TSrc);
 #pragma unroll
                 for (int i = 0; i < GPW; ++i) {
-                    const int64_t m = tile * BM + (warp * GPW + i) * 8 + r8;
-                    const bool inb = (m < p.M && k < p.K && !(p.debug & 2));
-                    const TSrc* src = inb ? seg_ptr<TSrc>(p, m, k) : nullptr;
+                    const int row = (warp * GPW + i) * 8 + r8;
+                    const bool inb = kok && row < rows_left;
+                    const uint8_t* src = tb + (uint32_t)row * pitch;
 #pragma unroll
                     for (int h = 0; h < CH; ++h) {
-                        const uint32_t dst = raw_u + (uint32_t)(slot * raw_stage + ((i * CH + h) * 256 + threadIdx.x) * 16);
-                        const void* g = src ? (const void*)(reinterpret_cast<const uint8_t*>(src) + 16 * h) : p.Wpacked;
-                        cp_async16(dst, g, src ? 16u : 0u);  // src-size 0 -> zero fill
+                        const uint32_t dst = raw_u + (uint32_t)(i_slot * raw_stage + ((i * CH + h) * 256 + threadIdx.x) * 16);
+                        cp_async16(dst, inb ? (const void*)(src + 16 * h) : p.Wpacked, inb ? 16u : 0u);  // src-size 0 -> zero fill
                     }
                     if (p.has_aux) {
-                        const TSrc* ax = inb ? seg_aux_ptr<TSrc>(p, m, k) : nullptr;
+                        const bool ain = inb && ea.ptr != nullptr;
+                        const uint8_t* ax = tba + (uint32_t)row * pitch_a;
 #pragma unroll
                         for (int h = 0; h < CH; ++h) {
-                            const uint32_t dst = raw_u + (uint32_t)(slot * raw_stage + ((4 + i * CH + h) * 256 + threadIdx.x) * 16);
-                            const void* g = ax ? (const void*)(reinterpret_cast<const uint8_t*>(ax) + 16 * h) : p.Wpacked;
-                            cp_async16(dst, g, ax ? 16u : 0u);  // zero -> silu'(0) = 0.5 ... handled below
+                            const uint32_t dst = raw_u + (uint32_t)(i_slot * raw_stage + ((4 + i * CH + h) * 256 + threadIdx.x) * 16);
+                            cp_async16(dst, ain ? (const void*)(ax + 16 * h) : p.Wpacked, ain ? 16u : 0u);
                         }
                     }
                 }
             }
             cp_async_commit();  // always commit so that group counting stays uniform
+            ++i_seq;
+            if (++i_slot == p.raw_depth) i_slot = 0;
+            if (++i_kb == nkb) { i_kb = 0; i_tile += gridDim.x; }
         };
-        auto fetch = [&](int64_t seq, float (&v)[GPW][8]) {
-            const int slot = (int)(seq % p.raw_depth);
-            const uint8_t* base = sRaw + slot * raw_stage;
+        auto fetch = [&](float (&v)[GPW][8]) {
+            const uint8_t* base = sRaw + f_slot * raw_stage;
             auto rd8 = [&](int chunk0, float (&o)[8]) {
                 if constexpr (sizeof(TSrc) == 4) {
                     const float4 x = *reinterpret_cast<const float4*>(base + ((chunk0 + 0) * 256 + threadIdx.x) * 16);
@@ -341,24 +445,22 @@ __global__ void __launch_bounds__(NTHREADS, 1) linear_tc_kernel(const TcParams p
                     }
                 }
             };
+            // segments without an aux matrix have zero-filled aux chunks; they must not scale A
+            const bool has = p.has_aux && sKaux[f_kb * (KC / 8) + kc].ptr != nullptr;
 #pragma unroll
             for (int i = 0; i < GPW; ++i) {
                 rd8(i * CH, v[i]);
                 if (p.has_aux) {
-                    // plain segments (null aux) are zero-filled raw chunks; they must not scale A:
-                    // the issuing side encodes "no aux" by the segment table, so re-derive it here.
                     float w[8];
                     rd8(4 + i * CH, w);
-                    const int64_t tile = blockIdx.x + (seq / nkb) * gridDim.x;
-                    const int kk = (int)(seq % nkb) * KC + kc * 8;
-                    const int64_t m = tile * BM + (warp * GPW + i) * 8 + r8;
-                    const bool has = (m < p.M && kk < p.K) && seg_aux_ptr<TSrc>(p, m, kk) != nullptr;
                     if (has) {
 #pragma unroll
                         for (int t = 0; t < 8; ++t) v[i][t] *= dsilu_fast(w[t]);
                     }
                 }
             }
+            if (++f_slot == p.raw_depth) f_slot = 0;
+            if (++f_kb == nkb) f_kb = 0;
         };
         auto emit = [&](float (&v)[GPW][8]) {
             mbar_wait(empty_bar(stage), phase ^ 1);
@@ -393,13 +495,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) linear_tc_kernel(const TcParams p
             if (++stage == p.nstage) { stage = 0; phase ^= 1; }
         };
         static_assert(GPW == 2, "raw slot layout assumes 2 row groups per producer warp");
-        for (int d = 0; d < p.raw_depth; ++d) issue(d);
+        for (int d = 0; d < p.raw_depth; ++d) issue();
         for (int64_t seq = 0; seq < total; ++seq) {
             if (p.raw_depth == 4) cp_async_wait<3>();  // the oldest group (= item seq) has landed
             else cp_async_wait<1>();
             float v[GPW][8];
-            fetch(seq, v);
-            issue(seq + p.raw_depth);         // refill the slot just drained
+            fetch(v);
+            issue();          // item seq + raw_depth refills the slot just drained
             emit(v);
         }
         cp_async_wait<0>();
@@ -451,44 +553,26 @@ __global__ void __launch_bounds__(NTHREADS, 1) linear_tc_kernel(const TcParams p
             // ---- epilogue-side global reads (silu' aux or old values to accumulate) are prefetched with
             //      cp.async into per-warp buffers, two 32-column chunks ahead, starting BEFORE the
             //      accumulator is ready ----
-            const int64_t m_base0 = tile * BM + q * 32;
-            float* pfw = sPf + (warp & 3) * 2 * 32 * EPI_LD;
-            auto find_seg = [&](int c0, int& seg, int& seg_lo) {
-                seg = -1; seg_lo = 0;
-                if (!(sizeof(TSrc) == 4 && c0 + 32 <= p.N && !(p.debug & 64))) return;
-                int lo = 0;
-#pragma unroll
-                for (int s2 = 0; s2 < AB2_MAX_SEG; ++s2) {
-                    if (s2 < p.n_o) {
-                        if (c0 >= lo && c0 + 32 <= lo + p.o[s2].width) { seg = s2; seg_lo = lo; }
-                        lo += p.o[s2].width;
-                    }
-                }
-                if (seg >= 0) {
-                    const uintptr_t base = reinterpret_cast<uintptr_t>((const float*)p.o[seg].ptr + (c0 - seg_lo));
-                    if ((base & 15) || ((p.o[seg].ld * 4) & 15)) seg = -1;
-                    if (p.epi == AB2_EPI_MUL_DSILU &&
-                        ((reinterpret_cast<uintptr_t>((const float*)p.aux + c0) & 15) || ((p.aux_ld * 4) & 15))) seg = -1;
-                }
-            };
+            const int64_t m_base = tile * BM + q * 32;
+            const int64_t left64 = p.M - m_base;  // <= 0: this warp's 32 rows lie beyond M
+            const int rows_left = left64 >= 32 ? 32 : (left64 > 0 ? (int)left64 : 0);
+            const bool full = rows_left == 32;
+            const int rsub = lane >> 3, c4 = lane & 7;
+            // row handled in slot itr: itr*4 + rsub; loads of a partial tile read a clamped (valid) row
+            auto row_of = [&](int itr) { const int r = itr * 4 + rsub; return full ? r : (r < rows_left ? r : rows_left - 1); };
+            float* pfw = sPf + q * 2 * 32 * EPI_LD;
             auto prefetch = [&](int c0) {
                 if constexpr (PF == 0) return;
-                if (c0 < p.Npad) {
-                    int seg, seg_lo;
-                    find_seg(c0, seg, seg_lo);
-                    if (seg >= 0 && (PF == 1 || p.o[seg].accum)) {
-                        const int rsub = lane >> 3, c4 = lane & 7;
-                        const float* gbase = (PF == 1) ? (const float*)p.aux + c0 + c4 * 4
-                                                              : (const float*)p.o[seg].ptr + (c0 - seg_lo) + c4 * 4;
-                        const int64_t gld = (PF == 1) ? p.aux_ld : p.o[seg].ld;
-                        float* dstb = pfw + ((c0 >> 5) & 1) * 32 * EPI_LD;
+                if (c0 < p.Npad && rows_left > 0) {
+                    const ChunkInfo ci = sChunk[c0 >> 5];
+                    if (ci.ok && (PF == 1 || ci.accum)) {
+                        const int64_t gld = (PF == 1) ? p.aux_ld : ci.ld;
+                        const float* tb = ((PF == 1) ? ci.aptr : (const float*)ci.optr) + m_base * gld + c4 * 4;
+                        const uint32_t gl = (uint32_t)gld;
+                        float* dstb = pfw + ((c0 >> 5) & 1) * 32 * EPI_LD + c4 * 4;
 #pragma unroll
-                        for (int itr = 0; itr < 8; ++itr) {
-                            const int row = itr * 4 + rsub;
-                            int64_t mr = m_base0 + row;
-                            if (mr >= p.M) mr = p.M - 1;
-                            cp_async16(smem_u32(dstb + row * EPI_LD + c4 * 4), gbase + mr * gld, 16u);
-                        }
+                        for (int itr = 0; itr < 8; ++itr)
+                            cp_async16(smem_u32(dstb + (itr * 4 + rsub) * EPI_LD), tb + (uint32_t)row_of(itr) * gl, 16u);
                     }
                 }
                 cp_async_commit();
@@ -557,21 +641,19 @@ __global__ void __launch_bounds__(NTHREADS, 1) linear_tc_kernel(const TcParams p
                     }
                 }
             };
-            float* stg = sEpi + (warp & 3) * 32 * EPI_LD;
-            const int64_t m_base = tile * BM + q * 32;
+            float* stg = sEpi + q * 32 * EPI_LD;
             for (int c0 = 0; c0 < p.Npad; c0 += 32) {
                 uint32_t r0[16], r1[16];
                 const bool two = c0 + 16 < p.Npad;
                 tmem_ld16_nowait(t_row + c0, r0);
                 if (two) tmem_ld16_nowait(t_row + c0 + 16, r1);
                 tmem_ld_wait();
-                // coalesced path: the 32-column chunk lies inside one fp32 output segment, 16-byte aligned
-                int seg = -1, seg_lo = 0;
-                if (two) find_seg(c0, seg, seg_lo);
+                const ChunkInfo ci = sChunk[c0 >> 5];
                 if constexpr (PF != 0) cp_async_wait<1>();  // this chunk's prefetch group (if any) has landed
-                if (p.debug & 1) {
-                } else if (seg >= 0) {
-                    // stage my row (lane) : 32 floats -> shared, then every global access covers 4 rows x 128 B
+                if ((p.debug & 1) || rows_left == 0) {
+                } else if (ci.ok) {
+                    // coalesced path (ok implies two): stage my row (lane): 32 floats -> shared, then every
+                    // global access covers 4 rows x 128 B
                     float4* srow = reinterpret_cast<float4*>(stg + lane * EPI_LD);
 #pragma unroll
                     for (int t = 0; t < 4; ++t) {
@@ -579,51 +661,50 @@ __global__ void __launch_bounds__(NTHREADS, 1) linear_tc_kernel(const TcParams p
                         srow[4 + t] = make_float4(__uint_as_float(r1[4 * t]), __uint_as_float(r1[4 * t + 1]), __uint_as_float(r1[4 * t + 2]), __uint_as_float(r1[4 * t + 3]));
                     }
                     __syncwarp();
-                    const int rsub = lane >> 3, c4 = lane & 7;
-                    float* obase = (float*)p.o[seg].ptr + (c0 - seg_lo) + c4 * 4;
-                    const float* abase = (const float*)p.aux + c0 + c4 * 4;
-                    const int acc = p.o[seg].accum;
                     // 1) all shared-memory reads, 2) (uniform) epilogue variants with all global loads
-                    //    issued before use, 3) predicated 4-rows-x-128-B stores.
-                    const bool epi = p.epi == AB2_EPI_MUL_DSILU;
-                    const int64_t old_ld = p.o[seg].ld;
+                    //    issued before use, 3) stores: tile base pointer + 32-bit row offsets.
                     float4 x[8];
-                    bool ok[8];
-                    int64_t mrc[8];  // row index clamped into range: loads are unconditional (no divergence)
 #pragma unroll
-                    for (int itr = 0; itr < 8; ++itr) {
-                        x[itr] = *reinterpret_cast<const float4*>(stg + (itr * 4 + rsub) * EPI_LD + c4 * 4);
-                        const int64_t mr = m_base + itr * 4 + rsub;
-                        ok[itr] = mr < p.M;
-                        mrc[itr] = ok[itr] ? mr : p.M - 1;
-                    }
+                    for (int itr = 0; itr < 8; ++itr) x[itr] = *reinterpret_cast<const float4*>(stg + (itr * 4 + rsub) * EPI_LD + c4 * 4);
+                    float* tb = ci.optr + m_base * ci.ld + c4 * 4;
+                    const uint32_t ol = (uint32_t)ci.ld;
+                    uint32_t off[8];
+#pragma unroll
+                    for (int itr = 0; itr < 8; ++itr) off[itr] = (uint32_t)row_of(itr) * ol;
                     const float* pfb = pfw + ((c0 >> 5) & 1) * 32 * EPI_LD;
-                    if (epi) {
+                    if (p.epi == AB2_EPI_MUL_DSILU) {
                         float4 ax[8];
+                        const float* ab = ci.aptr + m_base * p.aux_ld + c4 * 4;
+                        const uint32_t al = (uint32_t)p.aux_ld;
 #pragma unroll
                         for (int itr = 0; itr < 8; ++itr)
                             ax[itr] = (PF == 1) ? *reinterpret_cast<const float4*>(pfb + (itr * 4 + rsub) * EPI_LD + c4 * 4)
-                                                       : __ldg(reinterpret_cast<const float4*>(abase + mrc[itr] * p.aux_ld));
+                                                       : ldg128_nc(ab + (uint32_t)row_of(itr) * al);
 #pragma unroll
                         for (int itr = 0; itr < 8; ++itr) {
                             x[itr].x *= dsilu_fast(ax[itr].x); x[itr].y *= dsilu_fast(ax[itr].y);
                             x[itr].z *= dsilu_fast(ax[itr].z); x[itr].w *= dsilu_fast(ax[itr].w);
                         }
                     }
-                    if (acc) {
+                    if (ci.accum) {
                         float4 old[8];
 #pragma unroll
                         for (int itr = 0; itr < 8; ++itr)
                             old[itr] = (PF == 2) ? *reinterpret_cast<const float4*>(pfb + (itr * 4 + rsub) * EPI_LD + c4 * 4)
-                                                        : *reinterpret_cast<const float4*>(obase + mrc[itr] * old_ld);
+                                                        : ldg128(tb + off[itr]);
 #pragma unroll
                         for (int itr = 0; itr < 8; ++itr) {
                             x[itr].x += old[itr].x; x[itr].y += old[itr].y; x[itr].z += old[itr].z; x[itr].w += old[itr].w;
                         }
                     }
+                    if (full) {
 #pragma unroll
-                    for (int itr = 0; itr < 8; ++itr)
-                        if (ok[itr]) *reinterpret_cast<float4*>(obase + mrc[itr] * old_ld) = x[itr];
+                        for (int itr = 0; itr < 8; ++itr) stg128(tb + off[itr], x[itr]);
+                    } else {
+#pragma unroll
+                        for (int itr = 0; itr < 8; ++itr)
+                            if (itr * 4 + rsub < rows_left) stg128(tb + off[itr], x[itr]);
+                    }
                     __syncwarp();
                 } else {
                     process(c0, r0);
@@ -693,7 +774,7 @@ int ab2_linear_tc_try(int dtype, int64_t M, int K, int N, int n_a, const void* c
                       const int32_t* a_width, const void* const* a_aux, const int64_t* a_aux_ld, int act, const void* Wpacked, int n_o, void* const* o_ptr, const int64_t* o_ld,
                       const int32_t* o_width, const int32_t* o_accum, int epi, const void* aux, int64_t aux_ld, cudaStream_t st) {
     if (!g_ab2_opt_linear_tc || !Wpacked || dtype == AB2_F64) return -1;
-    if (ab2_linear_packed_bytes(dtype, K, N) == 0) return -1;
+    if (ab2_linear_packed_bytes(dtype, K, N) == 0 || K > MAX_K) return -1;
     const int esz = (dtype == AB2_F32) ? 4 : 2;
     for (int s = 0; s < n_a; ++s) {
         if (a_width[s] % 8 != 0) return -1;
@@ -735,7 +816,7 @@ int ab2_linear_tc_try(int dtype, int64_t M, int K, int N, int n_a, const void* c
     const int plans[4][2] = {{4, NSTAGE}, {4, 2}, {2, NSTAGE}, {2, 2}};
     for (int q = 0; q < 4 && !nstage; ++q) {
         const size_t need = ((w_bytes + 127) & ~127) + (size_t)plans[q][1] * stage_bytes + (size_t)plans[q][0] * raw_stage + EPI_BYTES +
-                            (pf_mode ? PF_BYTES : 0) + (2 * NSTAGE + 4) * 8 + 16;
+                            (pf_mode ? PF_BYTES : 0) + TAIL_BYTES;
         if ((int)need <= max_smem) { raw_depth = plans[q][0]; nstage = plans[q][1]; smem = need; }
     }
     if (!nstage) return -1;
