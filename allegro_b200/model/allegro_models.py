@@ -102,9 +102,10 @@ class FusedAllegroEnergy(torch.nn.Module):
             self.radial_chemical_embed.out_dim, S, scalar_embed_mlp_hidden_layers_depth,
             scalar_embed_mlp_hidden_layers_width, scalar_embed_mlp_nonlinearity, forward_weight_init=forward_normalize,
         )
+        # like the reference builder (allegro_models.py:185-193), `weight_individual_irreps` is NOT forwarded to the
+        # tensor embedding: the initial features always carry per-irrep weights
         self.tensor_embed = TwoBodySphericalHarmonicTensorEmbed(
             irreps_edge_sh, num_tensor_features, S, forward_weight_init=forward_normalize,
-            weight_individual_irreps=weight_individual_irreps,
         )
         self.allegro = Allegro_Module(
             num_layers=num_layers, num_scalar_features=S, num_tensor_features=num_tensor_features,

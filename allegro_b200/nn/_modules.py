@@ -29,14 +29,16 @@ class MakeWeightedChannels(torch.nn.Module):
         super().__init__()
         irreps_in = Irreps(irreps_in)
         assert all(m == 1 for m, _ in irreps_in) and multiplicity_out >= 1
-        if not weight_individual_irreps:
-            raise NotImplementedError("weight_individual_irreps=False has no CUDA path yet")
         if alpha != 1.0:
             raise NotImplementedError("alpha != 1")
         self._num_irreps = len(irreps_in)
         self.multiplicity_out = multiplicity_out
-        self.weight_individual_irreps = True
-        self.weight_numel = len(irreps_in) * multiplicity_out
+        # weight_individual_irreps=False (one weight per channel shared by all irreps, _channels.py:56-63) runs on
+        # the same kernels: the pipeline replicates the U weight columns over the irreps when it packs the linears
+        self.weight_individual_irreps = bool(weight_individual_irreps)
+        self.weight_numel = (len(irreps_in) if weight_individual_irreps else 1) * multiplicity_out
+        if not weight_individual_irreps:
+            self.register_buffer("_rtoi", torch.Tensor())  # the reference keeps this empty buffer in its state_dict (_channels.py:31)
         self.irreps_in = irreps_in
 
 

@@ -26,10 +26,15 @@ from ..data import EdgeCSR
 from ._mlp import PackedMLP
 
 
-def _env_perm(U: int, n_ir: int) -> torch.Tensor:
-    """internal column r*U+u  <-  reference column u*n_ir+r  (_channels.py:46-51)."""
+def _env_perm(U: int, n_ir: int, individual: bool = True) -> torch.Tensor:
+    """Column gather that brings the reference's env-weight columns into the internal [r][u] order.
+    individual weights: internal column r*U+u <- reference column u*n_ir+r (_channels.py:46-51);
+    shared weights (weight_individual_irreps=False, _channels.py:56-63): every irrep r reads the
+    same reference column u, i.e. the U columns are replicated n_ir times."""
     r = torch.arange(n_ir).view(-1, 1)
     u = torch.arange(U).view(1, -1)
+    if not individual:
+        return (u + 0 * r).reshape(-1)
     return (u * n_ir + r).reshape(-1)
 
 
@@ -55,14 +60,18 @@ class AllegroCore:
         self.sf = 1.0 / math.sqrt(avg_num_neighbors)
         self.factor = 1.0 / math.sqrt(2.0 * avg_num_neighbors)
         U, n_ir, S = self.U, self.n_ir, self.S
-        perm = _env_perm(U, n_ir)
-        nw = n_ir * U
+        # the two weighters are configured independently (the reference builder only forwards
+        # weight_individual_irreps to Allegro_Module, allegro_models.py:185-216)
+        perm = _env_perm(U, n_ir, allegro._env_weighter.weight_individual_irreps)         # omega columns
+        perm_w0 = _env_perm(U, n_ir, tensor_embed._edge_weighter.weight_individual_irreps)  # w0 columns
+        nw = n_ir * U                                          # internal env-weight width
+        nw0_ref = tensor_embed._edge_weighter.weight_numel     # reference width of the w0 linear
         # one GEMM for both linears that read the two-body embedding:
         #   [ w0 (tensorembed.py:88-89) | x_0 | omega_0 (_allegro.py:251-258) ]
         proj = allegro.first_layer_env_embed_projection.folded_weights()[0]
         proj_perm = torch.cat([torch.arange(S), S + perm])
         self.embed = PackedMLP(
-            tensor_embed.env_embed_linear, dtype, device, out_perm=torch.cat([perm, nw + proj_perm]),
+            tensor_embed.env_embed_linear, dtype, device, out_perm=torch.cat([perm_w0, nw0_ref + proj_perm]),
             extra_first=[proj],
         )
         self.layers = []

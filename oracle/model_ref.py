@@ -91,9 +91,10 @@ class AllegroEnergyOracle(torch.nn.Module):
                 scalar_embed_mlp_nonlinearity,
                 forward_weight_init=forward_normalize,
             )
+            # NOTE the reference builder does not forward `weight_individual_irreps` to the tensor embedding
+            # (allegro_models.py:185-193): the initial features always use per-irrep weights.
             self.tensor_embed = R.TwoBodySphericalHarmonicTensorEmbed(
                 l_max, num_tensor_features, S, forward_weight_init=forward_normalize,
-                weight_individual_irreps=weight_individual_irreps,
             )
             self.allegro = R.Allegro_Module(
                 num_layers=num_layers,

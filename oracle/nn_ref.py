@@ -108,6 +108,7 @@ class MakeWeightedChannels(torch.nn.Module):
         self.alpha = alpha
         if not weight_individual_irreps:
             self.weight_numel = multiplicity_out
+            self.register_buffer("_rtoi", torch.Tensor())  # persistent, empty (_channels.py:31)
             return
         self.weight_numel = len(irreps_in) * multiplicity_out
         rtoi = torch.zeros(self._num_irreps, irreps_in.dim)
