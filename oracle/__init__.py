@@ -10,11 +10,22 @@ Only ``tests/``, ``__graft_entry__.smoke()`` and the ``cpu_baseline`` /
 ``allegro_b200`` never imports it; its CUDA path raises if the extension is
 missing instead of falling back here.
 
-PARITY UNPINNED: the reference's own tests hold no golden vectors and compare
-against e3nn at run time (tests/nn/test_contract_basic.py:120-211,
-tests/nn/test_weighter.py:12-54); neither e3nn nor nequip is installed in this
-image, so the oracle cannot be executed against the real reference here.  It is
-pinned instead by the known-answer values and self-consistency identities in
-``tests/golden/o3_known_answers.json`` and by the
-property tests the reference uses (equivariance, gradcheck, strict locality).
+PARITY -- what is pinned and what is not:
+
+* PINNED to the reference's own code: everything mir-group/allegro implements itself
+  (allegro/nn/_strided/_contract.py, _channels.py, allegro/nn/_allegro.py, tensorembed.py,
+  _edgeembed.py, scalarembed.py, edgewise.py and the assembly in allegro/model/allegro_models.py).
+  ``tests/golden/make_reference_vectors.py`` EXECUTES those unmodified modules from
+  /root/reference in the build container and records inputs, state_dicts and outputs in
+  ``tests/golden/ref_models.pt`` / ``ref_ops.pt``; ``tests/test_reference_golden.py`` checks this
+  oracle against them (strict state_dict load, 1e-12 relative in fp64) on every box.
+* PARITY UNPINNED for the third-party primitives those modules import: e3nn (wigner_3j,
+  SphericalHarmonics, Irreps) and nequip (ScalarMLPFunction, Bessel/cutoff embedding,
+  scale/shift, force output).  Neither package is installable in this image and the reference's
+  tests hold no golden vectors for them (they compare with e3nn at run time,
+  tests/nn/test_contract_basic.py:120-211, tests/nn/test_weighter.py:12-54), so while the
+  fixtures above were generated the imports resolved to stand-ins backed by THIS oracle's
+  restatements (tests/golden/_stubs/).  Those primitives are pinned only by the known-answer
+  values and identities in ``tests/golden/o3_known_answers.json`` and by
+  the property tests the reference uses (equivariance, gradcheck, strict locality).
 """
