@@ -378,7 +378,21 @@ def run_ours_multi(args, rank, world):
 # --------------------------------------------------------------------------------------
 # CPU reference arm / baseline: the oracle port on the host cores
 # --------------------------------------------------------------------------------------
+def _host_threads() -> int:
+    """CPU threads this process may really use: affinity mask capped by the cgroup CPU quota.  torchrun exports
+    OMP_NUM_THREADS=1 to its workers; the CPU arm is a single process (rank 0), so it takes the whole allowance."""
+    n = len(os.sched_getaffinity(0))
+    try:
+        quota, period = open("/sys/fs/cgroup/cpu.max").read().split()
+        if quota != "max":
+            n = max(1, min(n, int(int(quota) / int(period))))
+    except (OSError, ValueError):
+        pass
+    return n
+
+
 def _oracle_setup(cfg: str, scale: int):
+    torch.set_num_threads(_host_threads())
     from allegro_b200 import data as D
     from allegro_b200 import systems
     from oracle.model_ref import AllegroOracle
