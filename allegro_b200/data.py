@@ -35,6 +35,8 @@ EDGE_ENERGY_KEY = "edge_energy"
 PER_ATOM_ENERGY_KEY = "atomic_energy"
 TOTAL_ENERGY_KEY = "total_energy"
 FORCE_KEY = "forces"
+STRESS_KEY = "stress"
+VIRIAL_KEY = "virial"
 
 Type = Dict[str, torch.Tensor]
 

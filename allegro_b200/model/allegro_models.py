@@ -146,9 +146,11 @@ class FusedAllegroEnergy(torch.nn.Module):
             self._core_key = key
         return self._core
 
-    def energy_and_forces(self, data: D.Type) -> D.Type:
+    def energy_and_forces(self, data: D.Type, stress: bool = False) -> D.Type:
         """Energies AND forces in one pass of hand-written kernels (no torch autograd anywhere):
-        what ForceStressOutput(AllegroEnergyModel) computes (allegro_models.py:101-103)."""
+        what ForceStressOutput(AllegroEnergyModel) computes (allegro_models.py:101-103).  With
+        ``stress=True`` and a cell in ``data`` also nequip's ``stress`` = sym(sum_z r_z (x) dE/dr_z)/V and
+        ``virial`` = -sym(...) ([1,3,3] each), from the same per-edge gradients."""
         pos = data[D.POSITIONS_KEY]
         if not pos.is_cuda:
             raise RuntimeError("allegro_b200: inputs must be CUDA tensors (no CPU fallback on the hot path)")
@@ -169,7 +171,9 @@ class FusedAllegroEnergy(torch.nn.Module):
             self._types_cache = (tkey, types.to(torch.int32).contiguous())
         ss = self.per_type_energy_scale_shift
         gscale = ss.scales[types].to(core.acc)
-        Ei, F, X, Ez = energy_forces(core, self._upstream, csr, pos.detach().contiguous(), self._types_cache[1], shift_vec, gscale)
+        want_virial = bool(stress) and D.CELL_KEY in data
+        Ei, F, X, Ez, virial = energy_forces(core, self._upstream, csr, pos.detach().contiguous(), self._types_cache[1], shift_vec,
+                                             gscale, want_virial)
         e_atom = ss(Ei.unsqueeze(-1), types)
         out = dict(data)
         if csr.perm is not None:
@@ -180,6 +184,12 @@ class FusedAllegroEnergy(torch.nn.Module):
         out[D.PER_ATOM_ENERGY_KEY] = e_atom
         out[D.TOTAL_ENERGY_KEY] = e_atom.sum(dim=0, keepdim=True)
         out[D.FORCE_KEY] = F.to(pos.dtype)
+        if want_virial:
+            cell = data[D.CELL_KEY].view(3, 3).to(virial.dtype)
+            volume = torch.dot(cell[0], torch.linalg.cross(cell[1], cell[2])).abs()
+            sym = 0.5 * (virial + virial.T)
+            out[D.STRESS_KEY] = (sym / volume).to(pos.dtype).unsqueeze(0)
+            out[D.VIRIAL_KEY] = (-sym).to(pos.dtype).unsqueeze(0)
         return out
 
     def _csr(self, edge_index: torch.Tensor, n: int):
@@ -236,7 +246,8 @@ class ForceStressOutput(torch.nn.Module):
 
     def forward(self, data: D.Type) -> D.Type:
         if hasattr(self.model, "energy_and_forces") and not getattr(self, "use_autograd", False):
-            return self.model.energy_and_forces(data)
+            # like nequip's ForceStressOutput, stress/virial come with the forces whenever a cell is given
+            return self.model.energy_and_forces(data, stress=getattr(self, "compute_stress", True))
         data = dict(data)
         pos = data[D.POSITIONS_KEY].detach().clone().requires_grad_(True)
         data[D.POSITIONS_KEY] = pos

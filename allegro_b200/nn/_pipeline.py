@@ -285,9 +285,11 @@ class UpstreamPack:
 
 
 def energy_forces(core: "AllegroCore", up: UpstreamPack, csr: EdgeCSR, pos: torch.Tensor, types_i32: torch.Tensor,
-                  shift_vec: Optional[torch.Tensor], gEi_scale: Optional[torch.Tensor]):
-    """Whole path with no torch autograd: positions -> (Ei [N], forces [n_atoms,3], X, Ez).
-    ``gEi_scale`` = d E_total / d Ei (per-type scales), None = ones."""
+                  shift_vec: Optional[torch.Tensor], gEi_scale: Optional[torch.Tensor], want_virial: bool = False):
+    """Whole path with no torch autograd: positions -> (Ei [N], forces [n_atoms,3], X, Ez, virial).
+    ``gEi_scale`` = d E_total / d Ei (per-type scales), None = ones.  ``virial`` (only if asked for) is
+    sum_z r_z (x) dE/dr_z [3,3] = dE/d(strain) before symmetrisation, from the per-edge gradients the
+    force scatter consumes anyway."""
     dt, acc = core.dtype, core.acc
     E = csr.num_edges
     _lib.set_tag("fwd.radial")
@@ -305,8 +307,9 @@ def energy_forces(core: "AllegroCore", up: UpstreamPack, csr: EdgeCSR, pos: torc
     else:
         up.mlp.backward([gx_emb], pre_se, [g_e0], [False])
     _lib.radial_bwd(dt, up.S_rc, up.p, vec, csr.ctr, csr.nbr, types_i32, up.rmax_table, up.bessel_w, up.Wb, up.cemb, up.nemb, g_e0, gvec)
+    virial = (vec.T @ gvec.to(vec.dtype)) if want_virial else None
     F = _lib.force_scatter(gvec, csr.row_ptr, csr.nbr, pos.shape[0])
-    return Ei, F, X, Ez
+    return Ei, F, X, Ez, virial
 
 
 class _CoreFn(torch.autograd.Function):

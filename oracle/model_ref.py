@@ -150,14 +150,30 @@ class AllegroOracle(torch.nn.Module):
         self.model = AllegroEnergyOracle(**kwargs)
 
     def forward(self, data: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
+        """nequip ForceStressOutput: forces = -dE/dpos; with a cell also stress = (dE/d eps)/V and
+        virial = -dE/d eps, eps a symmetric infinitesimal strain applied to positions and cell."""
         data = dict(data)
         for k in (R.EDGE_VECTORS_KEY, R.EDGE_LENGTH_KEY):
             data.pop(k, None)
         pos = data[R.POSITIONS_KEY].detach().clone().requires_grad_(True)
-        data[R.POSITIONS_KEY] = pos
+        has_cell = R.CELL_KEY in data
         with torch.enable_grad():
-            data = self.model(data)
-            (g,) = torch.autograd.grad(data[R.TOTAL_ENERGY_KEY].sum(), pos)
+            if has_cell:
+                cell0 = data[R.CELL_KEY].view(3, 3).to(pos.dtype)
+                disp = torch.zeros(3, 3, dtype=pos.dtype, requires_grad=True)
+                sym = 0.5 * (disp + disp.T)
+                data[R.POSITIONS_KEY] = pos + pos @ sym
+                data[R.CELL_KEY] = cell0 + cell0 @ sym
+                data = self.model(data)
+                g, gd = torch.autograd.grad(data[R.TOTAL_ENERGY_KEY].sum(), (pos, disp))
+                volume = torch.linalg.det(cell0).abs()
+                data[R.STRESS_KEY] = (gd / volume).unsqueeze(0)
+                data[R.VIRIAL_KEY] = (-gd).unsqueeze(0)
+                data[R.CELL_KEY] = cell0
+            else:
+                data[R.POSITIONS_KEY] = pos
+                data = self.model(data)
+                (g,) = torch.autograd.grad(data[R.TOTAL_ENERGY_KEY].sum(), pos)
         data[R.FORCE_KEY] = -g
         data[R.POSITIONS_KEY] = pos.detach()
         return {k: (v.detach() if isinstance(v, torch.Tensor) else v) for k, v in data.items()}

@@ -184,3 +184,35 @@ def test_model_runs_all_layer_shapes(cfg):
     m, d = _model_and_data(name, scale, **over)
     out = m(d)
     assert torch.isfinite(out[D.FORCE_KEY]).all() and out[D.FORCE_KEY].abs().max() > 0
+
+
+def test_stress_is_the_edge_virial_over_volume():
+    """nequip ForceStressOutput's strain derivative (restated in AllegroOracle) equals the per-edge form the CUDA
+    path uses: stress = sym(sum_z r_z (x) dE/dr_z) / V, virial = -sym(...)  (allegro_b200 energy_and_forces)."""
+    import torch
+
+    from allegro_b200 import systems
+    from oracle import nn_ref as R
+    from oracle.model_ref import AllegroOracle
+
+    d = systems.make_system("c5", 2)
+    kw = systems.model_kwargs("c5", 42.0, "float64")
+    kw.update(num_scalar_features=8, num_tensor_features=4, radial_chemical_embed_dim=8, scalar_embed_mlp_hidden_layers_width=8,
+              allegro_mlp_hidden_layers_width=8, readout_mlp_hidden_layers_width=8, l_max=2, num_layers=2,
+              per_type_energy_scales=[1.0, 0.5, 2.0, 1.5, 0.25])
+    oracle = AllegroOracle(**kw)
+    out = oracle(d)
+    pos, ei = d[R.POSITIONS_KEY], d[R.EDGE_INDEX_KEY]
+    vec = (pos[ei[1]] - pos[ei[0]] + d[R.EDGE_CELL_SHIFT_KEY] @ d[R.CELL_KEY]).clone().requires_grad_(True)
+    dd = {k: v for k, v in d.items()}
+    dd[R.EDGE_VECTORS_KEY] = vec
+    dd[R.EDGE_LENGTH_KEY] = vec.norm(dim=-1)
+    with torch.enable_grad():
+        e = oracle.model(dd)[R.TOTAL_ENERGY_KEY].sum()
+        (g,) = torch.autograd.grad(e, vec)
+    m = vec.detach().T @ g
+    sym = 0.5 * (m + m.T)
+    vol = torch.linalg.det(d[R.CELL_KEY]).abs()
+    assert (sym / vol - out[R.STRESS_KEY][0]).abs().max() < 1e-12
+    assert (-sym - out[R.VIRIAL_KEY][0]).abs().max() < 1e-10
+    assert (m - m.T).abs().max() < 1e-10  # rotation invariance makes the raw edge virial symmetric already
