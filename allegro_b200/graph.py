@@ -17,7 +17,7 @@ from . import data as D
 
 
 class GraphedEnergyForces:
-    def __init__(self, model: torch.nn.Module, data: D.Type, warmup: int = 3):
+    def __init__(self, model: torch.nn.Module, data: D.Type, warmup: int = 3, stress: bool = False):
         inner = getattr(model, "model", model)  # ForceStressOutput(FusedAllegroEnergy) or the energy model itself
         if not hasattr(inner, "energy_and_forces"):
             raise TypeError("model has no fused energy_and_forces path")
@@ -25,19 +25,20 @@ class GraphedEnergyForces:
         self.data = dict(data)
         self.static_pos = data[D.POSITIONS_KEY].detach().clone()
         self.data[D.POSITIONS_KEY] = self.static_pos
+        kw = {"stress": True} if stress else {}  # stress / virial captured into the graph only on request
         prof = _lib.PROF.enabled
         _lib.PROF.enabled = False
         s = torch.cuda.Stream()
         s.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(s), torch.no_grad():
             for _ in range(warmup):
-                self.inner.energy_and_forces(self.data)
+                self.inner.energy_and_forces(self.data, **kw)
         torch.cuda.current_stream().wait_stream(s)
         torch.cuda.synchronize()
         self.graph = torch.cuda.CUDAGraph()
         n0 = _lib.PROF.launches
         with torch.no_grad(), torch.cuda.graph(self.graph):
-            self.out = self.inner.energy_and_forces(self.data)
+            self.out = self.inner.energy_and_forces(self.data, **kw)
         self.launches_per_replay = _lib.PROF.launches - n0
         _lib.PROF.enabled = prof
 
