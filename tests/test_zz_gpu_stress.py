@@ -26,4 +26,5 @@ def test_stress_and_virial(cfg, scale, dtype, tol):
     # opt-out: no stress keys, same forces
     model.compute_stress = False
     out2 = model(_to_dev(d))
-    assert D.STRESS_KEY not in out2 and torch.equal(out2[D.FORCE_KEY], out[D.FORCE_KEY])
+    assert D.STRESS_KEY not in out2
+    assert (out2[D.FORCE_KEY] - out[D.FORCE_KEY]).abs().max() <= 1e-6 * out[D.FORCE_KEY].abs().max()  # atomics: not bitwise
