@@ -38,8 +38,14 @@ const char* ab2_last_error(void);
 int ab2_version(void);
 /* 1 if a CUDA device with compute capability 10.x is current, else 0 (no error). */
 int ab2_device_ok(void);
-/* Kernel-selection switches (for A/B tests): "tp_fast" (register-tiled tensor product, default 1),
- * "linear_tc" (tcgen05 tensor-core linear, default 1).  0 forces the shape-generic kernels. */
+/* Kernel-selection switches (for A/B tests and tuning; process-global, not thread-safe):
+ *   "tp_fast"    1 shared-memory / register-tiled tensor product (default), 2 register-M variants, 0 shape-generic kernels
+ *   "linear_tc"  1 tcgen05 tensor-core linear (default), 0 CUDA-core tile kernel
+ *   "tp_variant" 1: 3 CTAs/SM (default), 0: 2 CTAs/SM for the shared-memory tensor-product kernel
+ *   "env_split"  warps per (centre, channel chunk) in ab2_env_sum / ab2_env_bwd: 0 auto (default), 1, 2, 4
+ *   "tc_debug"   stage knock-out mask of the tcgen05 linear (bit0 no stores, bit1 no loads, bit2 no MMA); results are
+ *                wrong when non-zero -- for tools/exp_env.py only
+ * Returns 1 (and sets ab2_last_error) for an unknown key. */
 int ab2_set_option(const char* key, int value);
 
 /* ---- operator level: the reference's own kernel plug-in point ----------------------- */
