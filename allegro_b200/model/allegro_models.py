@@ -26,6 +26,7 @@ from ..nn._modules import (
     EdgewiseReduce,
     PerTypeScaleShift,
     TwoBodyBesselScalarEmbed,
+    TwoBodySplineScalarEmbed,
     TwoBodySphericalHarmonicTensorEmbed,
 )
 from ..nn._mlp import ScalarMLPFunction
@@ -36,6 +37,8 @@ _DTYPES = {"float32": torch.float32, "float64": torch.float64, "bfloat16": torch
 _EMBED_TARGETS = {
     "allegro.nn.TwoBodyBesselScalarEmbed": TwoBodyBesselScalarEmbed,
     "allegro_b200.nn.TwoBodyBesselScalarEmbed": TwoBodyBesselScalarEmbed,
+    "allegro.nn.TwoBodySplineScalarEmbed": TwoBodySplineScalarEmbed,
+    "allegro_b200.nn.TwoBodySplineScalarEmbed": TwoBodySplineScalarEmbed,
 }
 
 
@@ -43,7 +46,7 @@ def _instantiate_embed(cfg: Dict, **kw):
     cfg = dict(cfg or {"_target_": "allegro.nn.TwoBodyBesselScalarEmbed"})
     target = cfg.pop("_target_", "allegro.nn.TwoBodyBesselScalarEmbed")
     if target not in _EMBED_TARGETS:
-        raise NotImplementedError(f"radial_chemical_embed target {target!r} (spline embedding is SURVEY row f4, not built)")
+        raise NotImplementedError(f"radial_chemical_embed target {target!r}: only the reference's Bessel and spline embeddings exist")
     return _EMBED_TARGETS[target](**cfg, **kw)
 
 

@@ -8,5 +8,7 @@ from ._modules import (  # noqa: F401
     PerTypeScaleShift,
     ProductTypeEmbedding,
     TwoBodyBesselScalarEmbed,
+    TwoBodySplineScalarEmbed,
+    PerClassSpline,
     TwoBodySphericalHarmonicTensorEmbed,
 )

@@ -120,6 +120,49 @@ class TwoBodyBesselScalarEmbed(torch.nn.Module):
         return self.type_embed(self.bessel_encode(x_norm).to(model_dtype), type_c, type_n)
 
 
+class PerClassSpline(torch.nn.Module):
+    """allegro/nn/spline.py:8-89 (same buffers / parameter: lower, upper, class_embed.weight in fp64)."""
+
+    def __init__(self, num_classes: int, num_channels: int, num_splines: int, spline_span: int, dtype=torch.float64):
+        super().__init__()
+        assert 0 <= spline_span <= num_splines and num_splines > 0
+        self.num_classes, self.num_channels, self.num_splines, self.spline_span = num_classes, num_channels, num_splines, spline_span
+        lower = torch.arange(-spline_span, num_splines - spline_span, dtype=dtype) / num_splines
+        diff = (spline_span + 1) / num_splines
+        self.register_buffer("lower", lower)
+        self.register_buffer("upper", lower + diff)
+        self._const = 2 * math.pi / diff
+        self.class_embed = torch.nn.Embedding(num_classes, num_channels * num_splines, dtype=dtype)
+
+    def flat_weights(self) -> torch.Tensor:
+        """[(class, k), channel] view of class_embed.weight ([class, channel*K + k]) for the one-GEMM evaluation."""
+        w = self.class_embed.weight.detach().view(self.num_classes, self.num_channels, self.num_splines)
+        return w.permute(0, 2, 1).reshape(self.num_classes * self.num_splines, self.num_channels).contiguous()
+
+    def forward(self, x: torch.Tensor, classes: torch.Tensor) -> torch.Tensor:
+        from ._spline import spline_basis
+
+        basis, _ = spline_basis(x.reshape(-1).to(self.lower.dtype), self.lower, self.upper, self._const)
+        w = self.class_embed(classes).view(classes.size(0), self.num_channels, self.num_splines)
+        return torch.bmm(w, basis.unsqueeze(-1)).squeeze(-1)
+
+
+class TwoBodySplineScalarEmbed(torch.nn.Module):
+    """allegro/nn/scalarembed.py:84-175."""
+
+    def __init__(self, type_names, num_splines: int = 16, spline_span: int = 12, module_output_dim: int = 64,
+                 forward_weight_init: bool = True, **_unused):
+        super().__init__()
+        self.num_types = len(type_names)
+        self.spline = PerClassSpline(self.num_types * self.num_types, module_output_dim, num_splines, spline_span, dtype=torch.float64)
+        bound = math.sqrt(3 / spline_span) if forward_weight_init else math.sqrt(3 / module_output_dim)
+        torch.nn.init.uniform_(self.spline.class_embed.weight, a=-bound, b=bound)
+        self.out_dim = module_output_dim
+
+    def forward(self, x_norm: torch.Tensor, type_c: torch.Tensor, type_n: torch.Tensor, model_dtype: torch.dtype) -> torch.Tensor:
+        return self.spline(x_norm, type_c * self.num_types + type_n).to(model_dtype)
+
+
 class TwoBodySphericalHarmonicTensorEmbed(torch.nn.Module):
     """allegro/nn/tensorembed.py:16-96 (holder; arithmetic in ab2_sh_fwd + fused kernels)."""
 

@@ -272,6 +272,20 @@ class UpstreamPack:
 
     def __init__(self, edge_norm, radial, scalar_embed_mlp, dtype, device):
         acc = _lib.ACC_DTYPE[dtype]
+        self.mlp = PackedMLP(scalar_embed_mlp, dtype, device)
+        self.dtype = dtype
+        self.S_rc = radial.out_dim
+        self.kind = "spline" if hasattr(radial, "spline") else "bessel"
+        if self.kind == "spline":
+            # spline embedding (scalarembed.py:84-175): torch ops in fp64 with a hand-written adjoint (nn/_spline.py)
+            sp = radial.spline
+            self.num_types = radial.num_types
+            self.rmax64 = edge_norm.rmax_table.detach().to(device=device, dtype=torch.float64).contiguous()
+            self.sp_lower = sp.lower.detach().to(device=device, dtype=torch.float64)
+            self.sp_upper = sp.upper.detach().to(device=device, dtype=torch.float64)
+            self.sp_const = float(sp._const)
+            self.sp_w = sp.flat_weights().to(device=device, dtype=torch.float64)
+            return
         te = radial.type_embed
         self.p = float(radial.bessel_encode.p)
         self.S_rc = radial.out_dim
@@ -280,8 +294,6 @@ class UpstreamPack:
         self.Wb = te.basis_linear.folded_weights()[0].to(device=device, dtype=acc).contiguous()
         self.cemb = te.center_embed.weight.detach().to(device=device, dtype=acc).contiguous()
         self.nemb = te.neighbor_embed.weight.detach().to(device=device, dtype=acc).contiguous()
-        self.mlp = PackedMLP(scalar_embed_mlp, dtype, device)
-        self.dtype = dtype
 
 
 def energy_forces(core: "AllegroCore", up: UpstreamPack, csr: EdgeCSR, pos: torch.Tensor, types_i32: torch.Tensor,
@@ -294,7 +306,15 @@ def energy_forces(core: "AllegroCore", up: UpstreamPack, csr: EdgeCSR, pos: torc
     E = csr.num_edges
     _lib.set_tag("fwd.radial")
     vec = _lib.edge_vec(pos, csr.ctr, csr.nbr, shift_vec, acc)
-    e0 = _lib.radial_fwd(dt, up.S_rc, up.p, vec, csr.ctr, csr.nbr, types_i32, up.rmax_table, up.bessel_w, up.Wb, up.cemb, up.nemb)
+    sp_saved = None
+    if up.kind == "spline":
+        from ._spline import spline_backward, spline_forward
+
+        t64 = types_i32.long()
+        e0, sp_saved = spline_forward(vec, t64[csr.ctr.long()], t64[csr.nbr.long()], up.rmax64, up.sp_lower, up.sp_upper, up.sp_const,
+                                      up.sp_w, up.num_types, dt)
+    else:
+        e0 = _lib.radial_fwd(dt, up.S_rc, up.p, vec, csr.ctr, csr.nbr, types_i32, up.rmax_table, up.bessel_w, up.Wb, up.cemb, up.nemb)
     x_emb = torch.empty(E, core.S_in, dtype=dt, device=pos.device)
     pre_se = up.mlp.forward([e0], [x_emb])
     Ei, X, Ez, sv = core.forward(csr, vec, x_emb)
@@ -306,7 +326,10 @@ def energy_forces(core: "AllegroCore", up: UpstreamPack, csr: EdgeCSR, pos: torc
         up.mlp.backward_plain([gx_emb], pre_se, [g_e0])
     else:
         up.mlp.backward([gx_emb], pre_se, [g_e0], [False])
-    _lib.radial_bwd(dt, up.S_rc, up.p, vec, csr.ctr, csr.nbr, types_i32, up.rmax_table, up.bessel_w, up.Wb, up.cemb, up.nemb, g_e0, gvec)
+    if up.kind == "spline":
+        gvec += spline_backward(sp_saved, g_e0, up.sp_w, up.num_types).to(gvec.dtype)
+    else:
+        _lib.radial_bwd(dt, up.S_rc, up.p, vec, csr.ctr, csr.nbr, types_i32, up.rmax_table, up.bessel_w, up.Wb, up.cemb, up.nemb, g_e0, gvec)
     virial = (vec.T @ gvec.to(vec.dtype)) if want_virial else None
     F = _lib.force_scatter(gvec, csr.row_ptr, csr.nbr, pos.shape[0])
     return Ei, F, X, Ez, virial

@@ -74,10 +74,11 @@ class AllegroEnergyOracle(torch.nn.Module):
             else:
                 allowed = irreps_edge_sh
             rc = dict(radial_chemical_embed or {})
-            rc.pop("_target_", None)
+            target = rc.pop("_target_", "allegro.nn.TwoBodyBesselScalarEmbed").rsplit(".", 1)[-1]
+            embed_cls = {"TwoBodyBesselScalarEmbed": R.TwoBodyBesselScalarEmbed, "TwoBodySplineScalarEmbed": R.TwoBodySplineScalarEmbed}[target]
             S = num_scalar_features
             self.edge_norm = R.EdgeLengthNormalizer(r_max, type_names, per_edge_type_cutoff)
-            self.radial_chemical_embed = R.TwoBodyBesselScalarEmbed(
+            self.radial_chemical_embed = embed_cls(
                 type_names=type_names,
                 module_output_dim=S if radial_chemical_embed_dim is None else radial_chemical_embed_dim,
                 forward_weight_init=forward_normalize,

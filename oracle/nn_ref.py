@@ -337,6 +337,47 @@ class TwoBodyBesselScalarEmbed(torch.nn.Module):
         return self.type_embed(self.bessel_encode(data, model_dtype))
 
 
+class PerClassSpline(torch.nn.Module):
+    """allegro/nn/spline.py:8-89: per-class weighted sum of finite-support cos^2-type bumps on [0, 1];
+    every bump (hence the embedding and its derivative) vanishes at x = 1."""
+
+    def __init__(self, num_classes: int, num_channels: int, num_splines: int, spline_span: int, dtype=torch.float64):
+        super().__init__()
+        assert 0 <= spline_span <= num_splines and num_splines > 0
+        self.num_classes, self.num_channels, self.num_splines, self.spline_span = num_classes, num_channels, num_splines, spline_span
+        lower = torch.arange(-spline_span, num_splines - spline_span, dtype=dtype) / num_splines
+        diff = (spline_span + 1) / num_splines
+        self.register_buffer("lower", lower)
+        self.register_buffer("upper", lower + diff)
+        self._const = 2 * math.pi / diff
+        self.class_embed = torch.nn.Embedding(num_classes, num_channels * num_splines, dtype=dtype)
+
+    def _get_basis(self, x):
+        t = self._const * (torch.clamp(x, min=self.lower, max=self.upper) - self.lower)
+        return 0.25 * (1 - torch.cos(t)).square()
+
+    def forward(self, x, classes):
+        w = self.class_embed(classes).view(classes.size(0), self.num_channels, self.num_splines)
+        return torch.bmm(w, self._get_basis(x).unsqueeze(-1)).squeeze(-1)
+
+
+class TwoBodySplineScalarEmbed(torch.nn.Module):
+    """allegro/nn/scalarembed.py:84-175 (weights and evaluation in the global dtype fp64, output cast to the model dtype)."""
+
+    def __init__(self, type_names, num_splines=16, spline_span=12, module_output_dim=64, forward_weight_init=True):
+        super().__init__()
+        self.num_types = len(type_names)
+        self.spline = PerClassSpline(self.num_types * self.num_types, module_output_dim, num_splines, spline_span, dtype=torch.float64)
+        bound = math.sqrt(3 / spline_span) if forward_weight_init else math.sqrt(3 / module_output_dim)
+        torch.nn.init.uniform_(self.spline.class_embed.weight, a=-bound, b=bound)
+        self.out_dim = module_output_dim
+
+    def forward(self, data, model_dtype):
+        et = data[EDGE_TYPE_KEY]
+        data[EDGE_EMBEDDING_KEY] = self.spline(data[NORM_LENGTH_KEY], et[0] * self.num_types + et[1]).to(model_dtype)
+        return data
+
+
 class TwoBodySphericalHarmonicTensorEmbed(torch.nn.Module):
     """allegro/nn/tensorembed.py:16-96."""
 

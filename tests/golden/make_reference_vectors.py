@@ -97,6 +97,21 @@ def model_cases():
     add("per_edge_type_cutoff", c5, type_names=["A", "B", "C", "D", "E"], r_max=5.0, l_max=2, num_layers=2,
         per_edge_type_cutoff={"A": 4.0, "B": {"A": 3.5, "B": 4.5, "C": 5.0, "D": 5.0, "E": 4.0}}, **small)
     add("cluster_open_unsorted", _cluster(20, 6.0, 3), type_names=["X", "Y"], r_max=3.5, l_max=2, num_layers=2, **small)
+    # the reference's own model-test configuration (tests/model/test_allegro.py:27-44: 3 types, r_max 4, avgN 20, L 2,
+    # l_max 2, S 32, U 4, latent depth 2) with the SPLINE two-body embedding (:76-117 grid), with and without
+    # per-edge-type cutoffs
+    c3 = systems.make_system("c3", 3)  # 27 atoms, 3 species, r_max 6 list ...
+    ei, sh = D.neighbor_list(c3[D.POSITIONS_KEY], 4.0, c3[D.CELL_KEY], (True, True, True))  # ... re-listed at r_max 4
+    c3 = dict(c3)
+    c3[D.EDGE_INDEX_KEY], c3[D.EDGE_CELL_SHIFT_KEY] = ei, sh
+    ref_cfg = dict(type_names=["H", "C", "O"], r_max=4.0, l_max=2, num_layers=2, num_scalar_features=32, num_tensor_features=4,
+                   allegro_mlp_hidden_layers_depth=2, allegro_mlp_hidden_layers_width=32, scalar_embed_mlp_hidden_layers_width=32,
+                   readout_mlp_hidden_layers_width=8)
+    spline = {"_target_": "allegro.nn.TwoBodySplineScalarEmbed", "num_splines": 8, "spline_span": 6}
+    add("spline_embed_reftest_cfg", c3, radial_chemical_embed=dict(spline), **ref_cfg)
+    add("spline_embed_per_edge_type_cutoff", c3, radial_chemical_embed=dict(spline), per_edge_type_cutoff={"H": 2.0, "C": {"H": 4.0, "C": 3.5, "O": 3.7}, "O": 3.9},
+        tp_path_channel_coupling=False, **ref_cfg)
+    add("spline_embed_f32", c3, dtype="float32", radial_chemical_embed=dict(spline), **ref_cfg)
     return cases
 
 

@@ -191,3 +191,41 @@ def test_shared_irrep_weights_column_replication():
     U, n_ir = ci["mul"], 3
     w_int = ci["weights"][:, _env_perm(U, n_ir)].view(-1, n_ir, U)
     assert torch.equal(w_int, ci["weights"].view(-1, U, n_ir).transpose(1, 2))
+
+
+def test_product_spline_embedding_matches_reference_weights_and_oracle_gradient():
+    """allegro_b200/nn/_spline.py (device-agnostic torch ops, hand-written adjoint) with the reference's spline weights:
+    forward == the reference-pinned oracle module, adjoint == autograd through it; includes edges beyond the cutoff."""
+    from allegro_b200.nn import TwoBodySplineScalarEmbed
+    from allegro_b200.nn._spline import spline_backward, spline_forward
+
+    rec = MODELS["spline_embed_per_edge_type_cutoff"]
+    sd = {k[len("model.radial_chemical_embed."):]: v for k, v in unpack_state_dict(rec["state_dict"]).items() if "radial_chemical_embed" in k}
+    names = rec["kwargs"]["type_names"]
+    cfg = dict(rec["kwargs"]["radial_chemical_embed"])
+    cfg.pop("_target_")
+    S = rec["kwargs"]["num_scalar_features"]
+    mine = TwoBodySplineScalarEmbed(names, module_output_dim=S, **cfg)
+    mine.load_state_dict(sd, strict=True)
+    ora = R.TwoBodySplineScalarEmbed(names, module_output_dim=S, **cfg)
+    ora.load_state_dict(sd, strict=True)
+    g = torch.Generator().manual_seed(0)
+    E, T = 500, len(names)
+    vec = torch.randn(E, 3, generator=g, dtype=torch.float64) * 2.2  # lengths 0..~8 A: inside and beyond r_max = 4
+    tc, tn = torch.randint(0, T, (E,), generator=g), torch.randint(0, T, (E,), generator=g)
+    rmax = torch.full((T, T), 4.0, dtype=torch.float64)
+    rmax[0, :] = 2.0
+    rmax[1, 0], rmax[1, 1], rmax[1, 2] = 4.0, 3.5, 3.7
+    sp = mine.spline
+    e0, saved = spline_forward(vec, tc, tn, rmax, sp.lower, sp.upper, sp._const, sp.flat_weights(), T, torch.float64)
+    v = vec.clone().requires_grad_(True)
+    x = (v.norm(dim=-1) / rmax[tc, tn]).unsqueeze(-1)
+    ref = ora({R.NORM_LENGTH_KEY: x, R.EDGE_TYPE_KEY: torch.stack([tc, tn])}, torch.float64)[R.EDGE_EMBEDDING_KEY]
+    assert _rel(e0, ref) < 1e-13
+    assert float(e0[(x.squeeze(-1) >= 1.0).detach()].abs().max()) == 0.0  # beyond the cutoff: exactly zero
+    gout = torch.randn(ref.shape, generator=g, dtype=torch.float64)
+    (gv,) = torch.autograd.grad(ref, v, gout)
+    assert _rel(spline_backward(saved, gout, sp.flat_weights(), T), gv) < 1e-12
+    # module forward used by the torch-autograd path of the product model
+    out = mine(x.detach().squeeze(-1), tc, tn, torch.float32)
+    assert out.dtype == torch.float32 and _rel(out, ref) < 1e-6
