@@ -87,9 +87,11 @@ class AllegroCalculator:
         else:
             d = dict(self._data)
             d[D.POSITIONS_KEY] = pos
-            if hasattr(self.model, "compute_stress"):
-                self.model.compute_stress = self.compute_stress
-            out = self.model(d)
+            inner = getattr(self.model, "model", self.model)
+            if hasattr(inner, "energy_and_forces"):
+                out = inner.energy_and_forces(d, stress=self.compute_stress)
+            else:
+                out = self.model(d)
         self.n_evaluations += 1
         res = {"energy": out[D.TOTAL_ENERGY_KEY], "forces": out[D.FORCE_KEY], "atomic_energy": out[D.PER_ATOM_ENERGY_KEY]}
         if self.compute_stress and D.STRESS_KEY in out:
