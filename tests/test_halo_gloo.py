@@ -39,7 +39,8 @@ def _worker(rank, world, port, name, reps, q):
         runner = DistributedAllegro(model, dec)
         pos_owned = dec.local_positions_from_global(pos)[: dec.n_owned]
         e_tot, f_owned, e_atoms = runner(pos_owned)
-        q.put((rank, dec.owned.clone(), f_owned.clone(), e_atoms.clone(), float(e_tot), dec.n_ghost))
+        # plain numpy payloads: torch tensors cross the queue as shared-memory handles that can die with this process
+        q.put((rank, dec.owned.numpy().copy(), f_owned.detach().numpy().copy(), e_atoms.detach().numpy().copy(), float(e_tot), dec.n_ghost))
     finally:
         dist.destroy_process_group()
 
@@ -70,8 +71,9 @@ def test_slab_decomposition_matches_periodic_reference(world, name, reps):
     Ea = torch.zeros(n, 1, dtype=torch.float64)
     seen = torch.zeros(n, dtype=torch.long)
     for rank, owned, f, ea, e_tot, n_ghost in res:
-        F[owned] = f
-        Ea[owned] = ea
+        owned = torch.from_numpy(owned)
+        F[owned] = torch.from_numpy(f)
+        Ea[owned] = torch.from_numpy(ea)
         seen[owned] += 1
         assert n_ghost > 0
         assert e_tot == pytest.approx(ref[D.TOTAL_ENERGY_KEY].item(), rel=1e-11)
