@@ -97,3 +97,37 @@ def test_env_perm_is_a_transpose():
     U, n_ir = 5, 3
     ref = torch.arange(U * n_ir).view(U, n_ir)  # ref index u*n_ir + r
     assert torch.equal(ref.T.reshape(-1), _env_perm(U, n_ir))
+
+
+def test_header_is_plain_c_and_links_from_c(tmp_path):
+    """The boundary is a C ABI: include/allegro_b200.h must compile as C99 (no C++/torch types) and a C program must
+    link against liballegro_b200.so and reach the error plumbing without a GPU (no kernel is launched)."""
+    import shutil
+    import subprocess
+
+    from allegro_b200._lib import lib_path
+
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("no gcc")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    inc = os.path.join(root, "include")
+    so = lib_path()
+    assert os.path.exists(so), "build the extension first (__graft_entry__.build())"
+    src = tmp_path / "consumer.c"
+    src.write_text(
+        '#include <stdio.h>\n#include <string.h>\n#include "allegro_b200.h"\n'
+        "int main(void) {\n"
+        "  if (ab2_version() <= 0) return 1;\n"
+        '  if (ab2_set_option("no_such_option", 1) == 0) return 2;\n'
+        '  if (!ab2_last_error() || !strstr(ab2_last_error(), "no_such_option")) return 3;\n'
+        '  if (ab2_set_option("tp_fast", 1) != 0) return 4;\n'
+        "  /* null-pointer call: argument validation must refuse before any launch */\n"
+        "  if (ab2_sh_fwd(AB2_F32, 2, 10, NULL, NULL, NULL) == 0) return 5;\n"
+        '  printf("ok %d\\n", ab2_version());\n  return 0;\n}\n'
+    )
+    exe = tmp_path / "consumer"
+    subprocess.run([gcc, "-std=c99", "-Wall", "-Werror", "-I", inc, str(src), "-o", str(exe), so, f"-Wl,-rpath,{os.path.dirname(so)}"],
+                   check=True, capture_output=True, text=True)
+    p = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert p.returncode == 0 and p.stdout.startswith("ok"), (p.returncode, p.stdout, p.stderr)
