@@ -25,7 +25,13 @@ PARITY -- what is pinned and what is not:
   tests hold no golden vectors for them (they compare with e3nn at run time,
   tests/nn/test_contract_basic.py:120-211, tests/nn/test_weighter.py:12-54), so while the
   fixtures above were generated the imports resolved to stand-ins backed by THIS oracle's
-  restatements (tests/golden/_stubs/).  Those primitives are pinned only by the known-answer
+  restatements (tests/golden/_stubs/).  Independent implementations available in this image pin part
+  of them: the spherical harmonics equal scipy's Y_l^m in the standard real basis with e3nn's axis
+  convention (y polar), exactly and for every (l, m) up to l = 4, and the real Wigner 3j are
+  proportional, triple by triple, to sympy's real Gaunt integrals (tests/test_oracle_o3.py).  What
+  stays unpinned: the overall sign of each 3j block and the odd-sum blocks (absorbed by the path
+  weights; matters only for loading trained checkpoints) and nequip's MLP normalisation constants.
+  Beyond that the primitives are pinned only by the known-answer
   values and identities in ``tests/golden/o3_known_answers.json`` and by
   the property tests the reference uses (equivariance, gradcheck, strict locality).
 """

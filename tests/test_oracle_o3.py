@@ -114,3 +114,63 @@ def test_irreps_parsing():
     assert o3.Irrep("2e") in o3.Irreps("2o + 1e + 2e")
     assert [repr(i) for i in o3.Irrep("1o") * o3.Irrep("2e")] == ["1o", "2o", "3o"]
     assert o3.Irreps.spherical_harmonics(2).comp_to_irrep() == [0, 1, 1, 1, 2, 2, 2, 2, 2]
+
+
+def test_spherical_harmonics_against_scipy():
+    """Independent implementation check: the oracle's (and the CUDA generator's) real spherical harmonics equal scipy's
+    complex Y_l^m turned into the standard real basis, evaluated with e3nn's axis convention (y polar: physics
+    (x, y, z) = e3nn (z, x, y)), component normalisation, m = -l..l."""
+    import numpy as np
+    import torch
+    from scipy.special import sph_harm_y
+
+    from oracle import o3_ref
+
+    lmax = 4
+    g = torch.Generator().manual_seed(3)
+    v = torch.randn(400, 3, generator=g, dtype=torch.float64)
+    v = v / v.norm(dim=-1, keepdim=True)
+    mine = o3_ref.spherical_harmonics(lmax, v, method="recursive").numpy()
+    x, y, z = v[:, 0].numpy(), v[:, 1].numpy(), v[:, 2].numpy()
+    xp, yp, zp = z, x, y
+    theta, phi = np.arccos(np.clip(zp, -1, 1)), np.arctan2(yp, xp)
+    col = 0
+    for l in range(lmax + 1):
+        for m in range(-l, l + 1):
+            c = sph_harm_y(l, abs(m), theta, phi)
+            if m > 0:
+                ref = np.sqrt(2) * (-1) ** m * c.real
+            elif m < 0:
+                ref = np.sqrt(2) * (-1) ** m * c.imag
+            else:
+                ref = c.real
+            ref = ref * np.sqrt(4 * np.pi)
+            a = mine[:, col]
+            big = np.abs(ref) > 1e-3
+            ratio = a[big] / ref[big]
+            assert np.allclose(np.abs(ratio), 1.0, atol=1e-10), (l, m)
+            assert np.all(ratio > 0), (l, m)  # no extra sign: exactly the standard real harmonics in e3nn's axes
+            assert np.allclose(a, ref, atol=1e-10), (l, m)
+            col += 1
+    # explicit l <= 3 polynomials (the ones tools/gen_sh.py turns into CUDA) agree with the recursive construction
+    assert np.allclose(o3_ref.spherical_harmonics(3, v, method="explicit").numpy(), mine[:, :16], atol=1e-12)
+
+
+def test_wigner_3j_against_sympy_real_gaunt():
+    """Independent check of the real-basis Wigner 3j: for l1+l2+l3 even it must be proportional to the integral of three
+    real spherical harmonics (sympy's real Gaunt coefficients, an unrelated implementation), one constant per triple."""
+    import numpy as np
+    from sympy.physics.wigner import real_gaunt
+
+    from oracle import o3_ref
+
+    for l1, l2, l3 in [(0, 0, 0), (1, 1, 0), (1, 1, 2), (2, 1, 1), (2, 2, 2), (2, 2, 0), (1, 2, 3), (3, 3, 2), (2, 2, 4)]:
+        w = np.array(o3_ref.wigner_3j(l1, l2, l3))
+        gnt = np.zeros_like(w)
+        for a in range(2 * l1 + 1):
+            for b in range(2 * l2 + 1):
+                for c in range(2 * l3 + 1):
+                    gnt[a, b, c] = float(real_gaunt(l1, l2, l3, a - l1, b - l2, c - l3))
+        assert (np.abs(gnt) > 1e-12).sum() == (w != 0).sum(), (l1, l2, l3)          # same sparsity pattern
+        scale = (w * gnt).sum() / (gnt * gnt).sum()
+        assert abs(scale) > 1e-6 and np.allclose(w, scale * gnt, atol=1e-12), (l1, l2, l3)
