@@ -304,6 +304,13 @@ def energy_forces(core: "AllegroCore", up: UpstreamPack, csr: EdgeCSR, pos: torc
     force scatter consumes anyway."""
     dt, acc = core.dtype, core.acc
     E = csr.num_edges
+    if E == 0:
+        # a frame without a single edge (every atom isolated): zero energies before scale/shift, zero forces, empty
+        # per-edge outputs -- what the reference's modules produce on empty edge tensors
+        dev = pos.device
+        return (torch.zeros(csr.num_atoms, dtype=acc, device=dev), torch.zeros(pos.shape[0], 3, dtype=acc, device=dev),
+                torch.empty(0, core.S * (core.L + 1), dtype=dt, device=dev), torch.empty(0, 1, dtype=dt, device=dev),
+                torch.zeros(3, 3, dtype=acc, device=dev) if want_virial else None)
     _lib.set_tag("fwd.radial")
     vec = _lib.edge_vec(pos, csr.ctr, csr.nbr, shift_vec, acc)
     sp_saved = None

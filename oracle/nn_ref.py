@@ -222,14 +222,14 @@ class Contracter(torch.nn.Module):
                 if self.path_channel_coupling:
                     out = torch.sum(outer.unsqueeze(-1) * ww3j, 2)
                 else:
-                    out = torch.mm(outer.reshape(-1, outer.size(2)), ww3j).view(outer.size(0), outer.size(1), ww3j.size(1))
+                    out = torch.mm(outer.reshape(outer.size(0) * outer.size(1), outer.size(2)), ww3j).view(outer.size(0), outer.size(1), ww3j.size(1))
             else:
                 outer = c1.unsqueeze(-1) * c2.unsqueeze(-2)
                 if self.path_channel_coupling:
                     out = torch.sum(outer.unsqueeze(-1) * ww3j, (2, 3))
                 else:
                     out = torch.mm(
-                        outer.reshape(outer.size(0) * outer.size(1), -1), ww3j.reshape(-1, ww3j.size(2))
+                        outer.reshape(outer.size(0) * outer.size(1), outer.size(2) * outer.size(3)), ww3j.reshape(-1, ww3j.size(2))
                     ).view(-1, self.mul, ww3j.size(2))
             outs.append(out)
         return torch.cat(outs, 0)
@@ -490,7 +490,7 @@ class Allegro_Module(torch.nn.Module):
         for layer, (latent, tp) in enumerate(zip(self.latents, self.tps)):
             env_w_edges = self._env_weighter(tensor_basis, env_w)
             tensor_features = tp(tensor_features, env_w_edges, edge_center, num_atoms)
-            scalars = tensor_features[:, :, :1].reshape(tensor_features.shape[0], -1)
+            scalars = tensor_features[:, :, :1].reshape(tensor_features.shape[0], tensor_features.shape[1])  # explicit sizes: E may be 0
             latents = latent(torch.cat(acc + [scalars], dim=-1))
             acc.append(latents.narrow(-1, 0, S))
             if layer < self.num_layers - 1:

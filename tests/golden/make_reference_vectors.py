@@ -97,6 +97,19 @@ def model_cases():
     add("per_edge_type_cutoff", c5, type_names=["A", "B", "C", "D", "E"], r_max=5.0, l_max=2, num_layers=2,
         per_edge_type_cutoff={"A": 4.0, "B": {"A": 3.5, "B": 4.5, "C": 5.0, "D": 5.0, "E": 4.0}}, **small)
     add("cluster_open_unsorted", _cluster(20, 6.0, 3), type_names=["X", "Y"], r_max=3.5, l_max=2, num_layers=2, **small)
+    # ragged / empty inputs: atoms without any neighbour in the middle of the index range, and a frame with no edge at all
+    cl = _cluster(22, 6.0, 5)
+    far = torch.tensor([[90.0, 0, 0], [0, 95.0, 0], [0, 0, 99.0]], dtype=torch.float64)
+    pos = torch.cat([cl[D.POSITIONS_KEY][:4], far[:1], cl[D.POSITIONS_KEY][4:15], far[1:2], cl[D.POSITIONS_KEY][15:], far[2:]], 0)
+    types = torch.cat([cl[D.ATOM_TYPE_KEY][:4], torch.tensor([1]), cl[D.ATOM_TYPE_KEY][4:15], torch.tensor([0]), cl[D.ATOM_TYPE_KEY][15:], torch.tensor([1])])
+    ei, _ = D.neighbor_list(pos, 3.5, None, (False, False, False))
+    ragged = {D.POSITIONS_KEY: pos, D.ATOM_TYPE_KEY: types, D.EDGE_INDEX_KEY: ei}
+    add("isolated_atoms_ragged_rows", ragged, type_names=["X", "Y"], r_max=3.5, l_max=2, num_layers=2, avg_num_neighbors=9.0,
+        per_type_energy_shifts=[0.5, -1.0], **small)
+    ei0, _ = D.neighbor_list(far, 3.5, None, (False, False, False))
+    assert ei0.shape[1] == 0
+    add("no_edges_at_all", {D.POSITIONS_KEY: far, D.ATOM_TYPE_KEY: torch.tensor([0, 1, 1]), D.EDGE_INDEX_KEY: ei0}, type_names=["X", "Y"],
+        r_max=3.5, l_max=2, num_layers=2, avg_num_neighbors=9.0, per_type_energy_shifts=[0.5, -1.0], **small)
     # the reference's own model-test configuration (tests/model/test_allegro.py:27-44: 3 types, r_max 4, avgN 20, L 2,
     # l_max 2, S 32, U 4, latent depth 2) with the SPLINE two-body embedding (:76-117 grid), with and without
     # per-edge-type cutoffs

@@ -22,7 +22,11 @@ OPS = load_ops()
 
 def _rel(a, b):
     a, b = a.detach().double(), b.detach().double()
-    return float((a - b).abs().max() / b.abs().max().clamp_min(1e-300))
+    assert a.shape == b.shape, (a.shape, b.shape)
+    if b.numel() == 0:
+        return 0.0
+    den = float(b.abs().max())
+    return float((a - b).abs().max()) / (den if den > 0 else 1.0)  # all-zero reference (isolated atoms): absolute error
 
 
 # ---------------------------------------------------------------------------------------
