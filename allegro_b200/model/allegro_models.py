@@ -157,6 +157,10 @@ class FusedAllegroEnergy(torch.nn.Module):
         pos = data[D.POSITIONS_KEY]
         if not pos.is_cuda:
             raise RuntimeError("allegro_b200: inputs must be CUDA tensors (no CPU fallback on the hot path)")
+        return self._energy_and_forces(data, stress)
+
+    def _energy_and_forces(self, data: D.Type, stress: bool) -> D.Type:
+        pos = data[D.POSITIONS_KEY]
         core = self.core()
         n = pos.shape[0]
         csr = self._csr(data[D.EDGE_INDEX_KEY], n)
