@@ -79,3 +79,35 @@ def test_host_pipeline_stress_matches_oracle(spec_kernels):
     assert _rel(out["stress"], ref["stress"]) < 1e-10 and _rel(out["virial"], ref["virial"]) < 1e-10
     _, out2 = _run("c5_lmax3_L3_5species", stress=False)
     assert "stress" not in out2
+
+
+def test_host_pipeline_under_the_md_driver(spec_kernels, monkeypatch):
+    """AllegroCalculator (Verlet skin list, eager mode) driving the product model: equals the reference-pinned oracle on
+    exact r_max lists along a short random walk, including the stress."""
+    from allegro_b200 import data as D
+    from allegro_b200.calculator import AllegroCalculator
+    from allegro_b200.model import AllegroModel
+    from allegro_b200.model.allegro_models import FusedAllegroEnergy
+    from oracle.model_ref import AllegroOracle
+
+    monkeypatch.setattr(FusedAllegroEnergy, "energy_and_forces", lambda self, data, stress=False: self._energy_and_forces(data, stress))
+    rec = MODELS["per_edge_type_cutoff"]
+    sd = unpack_state_dict(rec["state_dict"])
+    model = AllegroModel(**rec["kwargs"])
+    model.load_state_dict(sd, strict=True)
+    oracle = AllegroOracle(**rec["kwargs"])
+    oracle.load_state_dict(sd, strict=True)
+    d = rec["data"]
+    pos, cell, types = d[D.POSITIONS_KEY], d[D.CELL_KEY], d[D.ATOM_TYPE_KEY]
+    calc = AllegroCalculator(model, rec["kwargs"]["r_max"], skin=0.5, use_graph=False, compute_stress=True)
+    g = torch.Generator().manual_seed(8)
+    p = pos.clone()
+    for _ in range(3):
+        out = calc.compute(p, cell, types)
+        ei, sh = D.neighbor_list(p, rec["kwargs"]["r_max"], cell, (True, True, True))
+        ref = oracle({D.POSITIONS_KEY: p, D.CELL_KEY: cell, D.ATOM_TYPE_KEY: types, D.EDGE_INDEX_KEY: ei, D.EDGE_CELL_SHIFT_KEY: sh})
+        assert _rel(out["forces"], ref["forces"]) < 1e-10
+        assert _rel(out["atomic_energy"], ref["atomic_energy"]) < 1e-10
+        assert _rel(out["stress"], ref["stress"]) < 1e-10
+        p = p + 0.1 * torch.randn(p.shape, generator=g, dtype=p.dtype)
+    assert calc.n_rebuilds >= 1 and calc.n_evaluations == 3
