@@ -145,7 +145,11 @@ class FusedAllegroEnergy(torch.nn.Module):
                 raise RuntimeError("allegro_b200: the model must live on a CUDA device (no CPU path for the hot path)")
             self._core = AllegroCore(self.tensor_embed, self.allegro, self.edge_readout, self.avg_num_neighbors,
                                      self.model_dtype, dev)
-            self._upstream = UpstreamPack(self.edge_norm, self.radial_chemical_embed, self.scalar_embed_mlp, self.model_dtype, dev)
+            import os
+
+            fold = self._core if os.environ.get("ALLEGRO_B200_FOLD_EMBED", "0") == "1" else None
+            self._upstream = UpstreamPack(self.edge_norm, self.radial_chemical_embed, self.scalar_embed_mlp, self.model_dtype, dev,
+                                          fold_embed_of=fold)
             self._core_key = key
         return self._core
 

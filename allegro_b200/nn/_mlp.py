@@ -90,7 +90,7 @@ class PackedMLP:
     ``in_perm``: likewise for the input rows of the first layer.
     """
 
-    def __init__(self, mlp: ScalarMLPFunction, dtype: torch.dtype, device, out_perm=None, in_perm=None, extra_first=None):
+    def __init__(self, mlp: ScalarMLPFunction, dtype: torch.dtype, device, out_perm=None, in_perm=None, extra_first=None, post=None):
         ws = mlp.folded_weights()
         if extra_first is not None:  # horizontally fused sibling linears sharing the input
             assert len(ws) == 1
@@ -99,6 +99,9 @@ class PackedMLP:
             ws[0] = ws[0][in_perm, :]
         if out_perm is not None:
             ws[-1] = ws[-1][:, out_perm]
+        if post is not None:  # a following LINEAR map folded into the (linear) output layer: x W_last post
+            ws[-1] = ws[-1].to(torch.float64) @ post.to(torch.float64)
+        self.W64 = [w.detach().to(torch.float64).cpu() for w in ws]
         self.silu = mlp.nonlinearity == "silu"
         self.W = [w.to(device=device, dtype=dtype).contiguous() for w in ws]
         self.WT = [w.T.to(device=device, dtype=dtype).contiguous() for w in ws]

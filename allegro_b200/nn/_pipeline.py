@@ -39,7 +39,7 @@ def _env_perm(U: int, n_ir: int, individual: bool = True) -> torch.Tensor:
 
 
 class _Saved:
-    __slots__ = ("csr", "vec", "Y", "w0", "omega", "V", "gamma", "pre_lat", "pre_read", "X")
+    __slots__ = ("csr", "vec", "Y", "w0", "omega", "V", "gamma", "pre_lat", "pre_read", "X", "fold")
 
 
 class AllegroCore:
@@ -116,20 +116,26 @@ class AllegroCore:
                 self.gsWp.append(_lib.linear_pack(Ws))
 
     # ------------------------------------------------------------------------------------
-    def forward(self, csr: EdgeCSR, vec: torch.Tensor, x_emb: torch.Tensor, keep: bool = True):
+    def forward(self, csr: EdgeCSR, vec: torch.Tensor, x_emb: Optional[torch.Tensor], keep: bool = True, fill_embed=None):
         """vec [E,3] (acc dtype), x_emb [E,S_in] (act dtype), both in CSR edge order.
-        Returns (Ei [N] acc dtype, X [E,S(L+1)], Ez [E,1], saved-for-backward)."""
+        Returns (Ei [N] acc dtype, X [E,S(L+1)], Ez [E,1], saved-for-backward).
+        ``fill_embed(w0, x0, omega0)``: instead of x_emb, a callback that fills the three outputs of the embed GEMM
+        (the upstream MLP with the embed linears folded into its last layer, energy_forces)."""
         E, N, U, S, L, D = csr.num_edges, csr.num_atoms, self.U, self.S, self.L, self.D
         dt, dev = self.dtype, self.device
-        assert vec.dtype == self.acc and x_emb.dtype == dt
+        assert vec.dtype == self.acc and (fill_embed is not None or x_emb.dtype == dt)
         sv = _Saved()
+        sv.fold = fill_embed is not None
         sv.csr, sv.vec = csr, vec
         _lib.set_tag("fwd.embed")
         Y = _lib.sh_fwd(vec, self.lmax)
         X = torch.empty(E, S * (L + 1), dtype=dt, device=dev)
         w0 = torch.empty(E, self.nw, dtype=dt, device=dev)
         omega = [torch.empty(E, self.nw, dtype=dt, device=dev)]
-        self.embed.forward([x_emb], [w0, X[:, :S], omega[0]])
+        if fill_embed is not None:
+            fill_embed(w0, X[:, :S], omega[0])
+        else:
+            self.embed.forward([x_emb], [w0, X[:, :S], omega[0]])
         V: List[Optional[torch.Tensor]] = [None]
         gammas, pre_lat = [], []
         for l, ly in enumerate(self.layers):
@@ -213,9 +219,11 @@ class AllegroCore:
             gV_next, gomega_next = gV_in, gomega
         _lib.set_tag("bwd.embed")
         g_x0 = block_grad(0)
+        gvec = _lib.sh_bwd(sv.vec, gY, self.lmax)
+        if sv.fold:  # the caller back-propagates the three embed-output gradients through its folded MLP
+            return gvec, [gw0, g_x0, gomega_next]
         gx_emb = torch.empty(E, self.S_in, dtype=dt, device=dev)
         self.embed.backward([gw0, g_x0, gomega_next], [], [gx_emb], [False])
-        gvec = _lib.sh_bwd(sv.vec, gY, self.lmax)
         return gvec, gx_emb
 
     def _backward_legacy(self, sv: _Saved, gEi: torch.Tensor):
@@ -260,9 +268,11 @@ class AllegroCore:
             _lib.env_bwd(dt, self.lmax, U, csr.ctr, sv.Y, sv.omega[l], ggamma, self.sf, gomega, gY, row_ptr=csr.row_ptr)
             gV_next, gomega_next = gV_in, gomega
         _lib.set_tag("bwd.embed")
+        gvec = _lib.sh_bwd(sv.vec, gY, self.lmax)
+        if sv.fold:
+            return gvec, [gw0, gX[:, :S], gomega_next]
         gx_emb = torch.empty(E, self.S_in, dtype=dt, device=dev)
         self.embed.backward([gw0, gX[:, :S], gomega_next], [], [gx_emb], [False])
-        gvec = _lib.sh_bwd(sv.vec, gY, self.lmax)
         return gvec, gx_emb
 
 
@@ -270,9 +280,14 @@ class UpstreamPack:
     """Device constants of the two-body scalar embedding (edge_norm, radial_chemical_embed,
     scalar_embed_mlp) for ab2_radial_fwd/bwd + the packed scalar-embed MLP."""
 
-    def __init__(self, edge_norm, radial, scalar_embed_mlp, dtype, device):
+    def __init__(self, edge_norm, radial, scalar_embed_mlp, dtype, device, fold_embed_of: Optional["AllegroCore"] = None):
         acc = _lib.ACC_DTYPE[dtype]
-        self.mlp = PackedMLP(scalar_embed_mlp, dtype, device)
+        # fold_embed_of: x_emb only feeds two LINEAR maps (tensorembed.py:88-89 env_embed_linear, _allegro.py:251
+        # first_layer_env_embed_projection), and the scalar-embed MLP ends in a linear layer, so their product is
+        # one matrix: [w0 | x_0 | omega_0] = silu(h) @ (W_last @ W_embed).  One GEMM and the x_emb round trip less
+        # in each direction.  Opt-in (ALLEGRO_B200_FOLD_EMBED=1) until measured on the GPU.
+        self.fold = fold_embed_of is not None
+        self.mlp = PackedMLP(scalar_embed_mlp, dtype, device, post=fold_embed_of.embed.W64[0] if self.fold else None)
         self.dtype = dtype
         self.S_rc = radial.out_dim
         self.kind = "spline" if hasattr(radial, "spline") else "bessel"
@@ -322,17 +337,23 @@ def energy_forces(core: "AllegroCore", up: UpstreamPack, csr: EdgeCSR, pos: torc
                                       up.sp_w, up.num_types, dt)
     else:
         e0 = _lib.radial_fwd(dt, up.S_rc, up.p, vec, csr.ctr, csr.nbr, types_i32, up.rmax_table, up.bessel_w, up.Wb, up.cemb, up.nemb)
-    x_emb = torch.empty(E, core.S_in, dtype=dt, device=pos.device)
-    pre_se = up.mlp.forward([e0], [x_emb])
-    Ei, X, Ez, sv = core.forward(csr, vec, x_emb)
+    if up.fold:
+        pre_box = []
+        Ei, X, Ez, sv = core.forward(csr, vec, None, fill_embed=lambda w0, x0, om0: pre_box.append(up.mlp.forward([e0], [w0, x0, om0])))
+        pre_se = pre_box[0]
+    else:
+        x_emb = torch.empty(E, core.S_in, dtype=dt, device=pos.device)
+        pre_se = up.mlp.forward([e0], [x_emb])
+        Ei, X, Ez, sv = core.forward(csr, vec, x_emb)
     gEi = gEi_scale if gEi_scale is not None else torch.ones_like(Ei)
     gvec, gx_emb = core.backward(sv, gEi)
+    gouts = gx_emb if up.fold else [gx_emb]
     _lib.set_tag("bwd.radial")
     g_e0 = torch.empty(E, up.S_rc, dtype=dt, device=pos.device)
     if up.mlp.is_two_layer_silu:
-        up.mlp.backward_plain([gx_emb], pre_se, [g_e0])
+        up.mlp.backward_plain(gouts, pre_se, [g_e0])
     else:
-        up.mlp.backward([gx_emb], pre_se, [g_e0], [False])
+        up.mlp.backward(gouts, pre_se, [g_e0], [False])
     if up.kind == "spline":
         gvec += spline_backward(sp_saved, g_e0, up.sp_w, up.num_types).to(gvec.dtype)
     else:

@@ -28,7 +28,11 @@ def spec_kernels(monkeypatch):
     def core(self):  # FusedAllegroEnergy.core without the "must live on a CUDA device" gate
         if getattr(self, "_core", None) is None:
             self._core = AllegroCore(self.tensor_embed, self.allegro, self.edge_readout, self.avg_num_neighbors, self.model_dtype, "cpu")
-            self._upstream = UpstreamPack(self.edge_norm, self.radial_chemical_embed, self.scalar_embed_mlp, self.model_dtype, "cpu")
+            import os
+
+            fold = self._core if os.environ.get("ALLEGRO_B200_FOLD_EMBED", "0") == "1" else None
+            self._upstream = UpstreamPack(self.edge_norm, self.radial_chemical_embed, self.scalar_embed_mlp, self.model_dtype, "cpu",
+                                          fold_embed_of=fold)
         return self._core
 
     monkeypatch.setattr(FusedAllegroEnergy, "core", core)
@@ -111,3 +115,18 @@ def test_host_pipeline_under_the_md_driver(spec_kernels, monkeypatch):
         assert _rel(out["stress"], ref["stress"]) < 1e-10
         p = p + 0.1 * torch.randn(p.shape, generator=g, dtype=p.dtype)
     assert calc.n_rebuilds >= 1 and calc.n_evaluations == 3
+
+
+@pytest.mark.parametrize("plain", [False, True], ids=["legacy_bwd", "plain_bwd"])
+@pytest.mark.parametrize("name", model_case_ids())
+def test_host_pipeline_with_folded_embed_linears(name, plain, spec_kernels, monkeypatch):
+    """ALLEGRO_B200_FOLD_EMBED=1: the two linear maps that consume the two-body embedding are folded into the last layer
+    of the scalar-embed MLP (one GEMM less per direction).  Same energies, forces and per-edge outputs."""
+    monkeypatch.setenv("ALLEGRO_B200_FOLD_EMBED", "1")
+    if plain:
+        monkeypatch.setenv("ALLEGRO_B200_PLAIN_BWD", "1")
+    rec, out = _run(name)
+    tol = 1e-10 if rec["kwargs"]["model_dtype"] == "float64" else 5e-5
+    for key in ("atomic_energy", "forces", "edge_energy", "edge_features"):
+        if key in rec:
+            assert _rel(out[key], rec[key]) < tol, (key, _rel(out[key], rec[key]))
