@@ -44,7 +44,7 @@ _SIGNATURES = {
     "ab2_tp_bwd": ([_i32, _i32, _i64, _i64, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _i64, _vp, _vp, _vp, _i64, _vp, _vp, _vp], C.c_int),
     "ab2_edge_sum": ([_i32, _i64, _vp, _vp, _dbl, _vp, _vp], C.c_int),
     "ab2_edge_sum_bwd": ([_i32, _i64, _vp, _vp, _dbl, _vp, _vp], C.c_int),
-    "ab2_force_scatter": ([_i32, _i64, _i64, _vp, _vp, _vp, _vp, _vp], C.c_int),
+    "ab2_force_scatter": ([_i32, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp], C.c_int),
     "ab2_transpose_ui": ([_i32, _i64, _i32, _i32, _vp, _vp, _i32, _vp], C.c_int),
     "ab2_edge_vec": ([_i32, _i32, _i64, _vp, _vp, _vp, _vp, _vp, _vp], C.c_int),
     "ab2_radial_fwd": ([_i32, _i64, _i32, _i32, _dbl, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp], C.c_int),
@@ -334,12 +334,16 @@ def edge_sum_bwd(gEi: torch.Tensor, ctr: torch.Tensor, factor: float) -> torch.T
     return gEz
 
 
-def force_scatter(gvec: torch.Tensor, row_ptr: torch.Tensor, nbr: torch.Tensor, num_atoms_total: int) -> torch.Tensor:
-    N = row_ptr.shape[0] - 1
-    E = nbr.shape[0]
-    F = torch.zeros(num_atoms_total, 3, dtype=gvec.dtype, device=gvec.device)
+def force_scatter(gvec: torch.Tensor, csr, num_atoms_total: int) -> torch.Tensor:
+    """F[a] = sum of gvec over the edges centred on a  -  sum over the edges whose neighbour is a
+    (deterministic segmented sums over the CSR and its transpose, ``csr.transposed``)."""
+    N = csr.row_ptr.shape[0] - 1
+    E = csr.nbr.shape[0]
+    col_ptr, col_perm = csr.transposed(num_atoms_total)
+    F = torch.empty(num_atoms_total, 3, dtype=gvec.dtype, device=gvec.device)
     with _timed("force_scatter"):
-        _check(load().ab2_force_scatter(DTYPE_ENUM[gvec.dtype], N, E, _ptr(row_ptr), _ptr(nbr), _ptr(_contig(gvec, "gvec")), _ptr(F), _stream()))
+        _check(load().ab2_force_scatter(DTYPE_ENUM[gvec.dtype], N, num_atoms_total, E, _ptr(csr.row_ptr), _ptr(col_ptr), _ptr(col_perm),
+                                        _ptr(_contig(gvec, "gvec")), _ptr(F), _stream()))
     return F
 
 

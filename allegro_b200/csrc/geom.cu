@@ -164,41 +164,52 @@ extern "C" int ab2_edge_sum_bwd(int acc_dtype, int64_t E, const int32_t* ctr, co
 // ---------------------------------------------------------------------------------------
 // Force assembly.  gvec[z] = dE/d r_z with r_z = pos[nbr] - pos[ctr]:
 //   dE/dpos[ctr] -= gvec,  dE/dpos[nbr] += gvec;   F = -dE/dpos
-// so F[ctr] += gvec (segmented sum, one warp per centre, no atomics) and F[nbr] -= gvec
-// (atomics; neighbours of one centre are distinct atoms so no intra-warp collisions).
+// so F[a] = sum_{z in row a} gvec[z] - sum_{z : nbr[z] = a} gvec[z].  Both sums are SEGMENTED
+// reductions: the first over the centre-sorted CSR row, the second over the transposed CSR
+// (edges grouped by neighbour: col_ptr[n_total+1], col_perm[E] = edge ids sorted by neighbour,
+// built once per neighbour list).  One warp per atom, fixed summation order, no atomics: forces
+// are bitwise reproducible from run to run, and F needs no zero-fill.
 // ---------------------------------------------------------------------------------------
 template <typename TAcc>
-__global__ void __launch_bounds__(256) force_scatter_kernel(int64_t N, const int32_t* __restrict__ row_ptr,
-                                                            const int32_t* __restrict__ nbr, const TAcc* __restrict__ gvec,
+__global__ void __launch_bounds__(256) force_scatter_kernel(int64_t N, int64_t n_total, const int32_t* __restrict__ row_ptr,
+                                                            const int32_t* __restrict__ col_ptr,
+                                                            const int32_t* __restrict__ col_perm, const TAcc* __restrict__ gvec,
                                                             TAcc* __restrict__ F) {
-    const int64_t c = ((int64_t)blockIdx.x * 256 + threadIdx.x) >> 5;
+    const int64_t a = ((int64_t)blockIdx.x * 256 + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
-    if (c >= N) return;
-    const int beg = row_ptr[c], end = row_ptr[c + 1];
+    if (a >= n_total) return;
     TAcc sx = 0, sy = 0, sz = 0;
-    for (int z = beg + lane; z < end; z += 32) {
-        TAcc gx = gvec[(int64_t)z * 3 + 0], gy = gvec[(int64_t)z * 3 + 1], gz = gvec[(int64_t)z * 3 + 2];
-        sx += gx; sy += gy; sz += gz;
-        const int64_t j = nbr[z];
-        atomicAdd(&F[j * 3 + 0], -gx);
-        atomicAdd(&F[j * 3 + 1], -gy);
-        atomicAdd(&F[j * 3 + 2], -gz);
+    if (a < N) {
+        const int beg = row_ptr[a], end = row_ptr[a + 1];
+        for (int z = beg + lane; z < end; z += 32) {
+            sx += gvec[(int64_t)z * 3 + 0];
+            sy += gvec[(int64_t)z * 3 + 1];
+            sz += gvec[(int64_t)z * 3 + 2];
+        }
+    }
+    const int cb = col_ptr[a], ce = col_ptr[a + 1];
+    for (int t = cb + lane; t < ce; t += 32) {
+        const int64_t z = col_perm[t];
+        sx -= gvec[z * 3 + 0];
+        sy -= gvec[z * 3 + 1];
+        sz -= gvec[z * 3 + 2];
     }
     sx = warp_sum(sx); sy = warp_sum(sy); sz = warp_sum(sz);
     if (lane == 0) {
-        atomicAdd(&F[c * 3 + 0], sx);
-        atomicAdd(&F[c * 3 + 1], sy);
-        atomicAdd(&F[c * 3 + 2], sz);
+        F[a * 3 + 0] = sx;
+        F[a * 3 + 1] = sy;
+        F[a * 3 + 2] = sz;
     }
 }
 
-extern "C" int ab2_force_scatter(int acc_dtype, int64_t N, int64_t E, const int32_t* row_ptr, const int32_t* nbr,
-                                 const void* gvec, void* F, void* stream) {
-    if (N == 0 || E == 0) return 0;
-    AB2_CHECK_ARG(row_ptr && nbr && gvec && F, "null pointer");
+extern "C" int ab2_force_scatter(int acc_dtype, int64_t N, int64_t n_total, int64_t E, const int32_t* row_ptr,
+                                 const int32_t* col_ptr, const int32_t* col_perm, const void* gvec, void* F, void* stream) {
+    if (n_total == 0) return 0;
+    AB2_CHECK_ARG(row_ptr && col_ptr && gvec && F && (E == 0 || col_perm), "null pointer");
+    AB2_CHECK_ARG(N <= n_total, "more centres than atoms");
     cudaStream_t st = (cudaStream_t)stream;
-    AB2_DISPATCH_ACC(acc_dtype, force_scatter_kernel<TAcc><<<ab2_blocks(N * 32, 256), 256, 0, st>>>(N, row_ptr, nbr,
-                                                                                                      (const TAcc*)gvec, (TAcc*)F));
+    AB2_DISPATCH_ACC(acc_dtype, force_scatter_kernel<TAcc><<<ab2_blocks(n_total * 32, 256), 256, 0, st>>>(
+                                    N, n_total, row_ptr, col_ptr, col_perm, (const TAcc*)gvec, (TAcc*)F));
     AB2_CUDA_LAUNCH_CHECK();
     return 0;
 }

@@ -49,13 +49,23 @@ def num_nodes(data: Type) -> int:
 # neighbour lists
 # --------------------------------------------------------------------------- #
 def _brute_force(pos, cell, pbc, r_max):
-    n = pos.shape[0]
+    """All-pairs search over the periodic images within r_max.  Positions are first wrapped into the
+    cell along the periodic axes (MD drivers hand over unwrapped coordinates; without the wrap, atoms
+    that diffused by a lattice vector would lose neighbours) and the integer image offsets are folded
+    back into the returned shifts, so  r = pos[j] + shift @ cell - pos[i]  holds for the RAW
+    positions -- the same convention as ``_cell_list``."""
     dev = pos.device
     if cell is None or not any(pbc):
         shifts = torch.zeros(1, 3, dtype=torch.long, device=dev)
         cell_m = torch.zeros(3, 3, dtype=pos.dtype, device=dev)
+        img0 = torch.zeros(pos.shape[0], 3, dtype=torch.long, device=dev)
+        wrapped = pos
     else:
         cell_m = cell.view(3, 3).to(pos.dtype)
+        pbc_t = torch.tensor([bool(p) for p in pbc], device=dev)
+        frac = torch.linalg.solve(cell_m.T, pos.T).T  # pos = frac @ cell
+        img0 = torch.where(pbc_t, torch.floor(frac), torch.zeros_like(frac)).to(torch.long)
+        wrapped = pos - img0.to(pos.dtype) @ cell_m
         # number of images needed per axis: r_max / (height of the cell along that axis)
         vol = torch.det(cell_m).abs()
         cr = torch.stack([torch.linalg.cross(cell_m[1], cell_m[2]), torch.linalg.cross(cell_m[2], cell_m[0]), torch.linalg.cross(cell_m[0], cell_m[1])])
@@ -66,13 +76,13 @@ def _brute_force(pos, cell, pbc, r_max):
     ei, sh = [], []
     for s in shifts:
         off = s.to(pos.dtype) @ cell_m
-        d = pos.unsqueeze(0) + off - pos.unsqueeze(1)  # [i, j]
+        d = wrapped.unsqueeze(0) + off - wrapped.unsqueeze(1)  # [i, j]
         mask = d.norm(dim=-1) < r_max
         if not bool(s.any()):
             mask.fill_diagonal_(False)
         ij = mask.nonzero()
         ei.append(ij.T)
-        sh.append(s.expand(ij.shape[0], 3))
+        sh.append(s.expand(ij.shape[0], 3) - img0[ij[:, 1]] + img0[ij[:, 0]])
     return torch.cat(ei, dim=1), torch.cat(sh, dim=0)
 
 
@@ -156,10 +166,12 @@ def neighbor_list(
     else:
         ei, sh = _brute_force(pos, cell, pbc, float(r_max))
     n = pos.shape[0]
-    key = ei[0] * n + ei[1]
-    # ties (same pair through different images) keep a deterministic order via the shift
-    sk = ((sh[:, 0] + 8) * 17 + (sh[:, 1] + 8)) * 17 + (sh[:, 2] + 8)
-    order = torch.argsort(key * 4913 + sk)
+    # sort by (centre, neighbour); ties (same pair through different images) keep a deterministic order
+    # via the shift.  Successive stable sorts from the least significant key (any shift magnitude --
+    # raw MD positions may sit many cells away from the home cell).
+    order = torch.arange(ei.shape[1], device=ei.device)
+    for k in (sh[:, 2], sh[:, 1], sh[:, 0], ei[0] * n + ei[1]):
+        order = order[torch.argsort(k[order], stable=True)]
     return ei[:, order].contiguous(), sh[order].to(pos.dtype).contiguous()
 
 
@@ -170,13 +182,30 @@ class EdgeCSR:
     """Centre-sorted edge list. ``perm`` maps sorted position -> original edge (None if the
     input was already sorted)."""
 
-    __slots__ = ("num_atoms", "num_edges", "ctr", "nbr", "row_ptr", "perm", "max_degree")
+    __slots__ = ("num_atoms", "num_edges", "ctr", "nbr", "row_ptr", "perm", "max_degree", "_transposed")
 
     def __init__(self, num_atoms, ctr, nbr, row_ptr, perm, max_degree):
         self.num_atoms = int(num_atoms)
         self.num_edges = int(ctr.shape[0])
         self.ctr, self.nbr, self.row_ptr, self.perm = ctr, nbr, row_ptr, perm
         self.max_degree = int(max_degree)
+        self._transposed = None
+
+    def transposed(self, n_total: int):
+        """Transposed CSR for the neighbour-side force reduction (ab2_force_scatter): ``col_ptr``
+        [n_total+1] int32 and ``col_perm`` [E] int32 = edge ids grouped by neighbour atom, in
+        ascending edge order inside a group (stable sort -> a fixed summation order).  Built once
+        per neighbour list; ``n_total`` counts owned + ghost atoms."""
+        if self._transposed is None or self._transposed[0] != int(n_total):
+            nbr64 = self.nbr.long()
+            col_perm = torch.argsort(nbr64, stable=True).to(torch.int32).contiguous()
+            counts = torch.bincount(nbr64, minlength=int(n_total))
+            if counts.shape[0] != int(n_total):
+                raise ValueError("edge neighbour index out of range")
+            col_ptr = torch.zeros(int(n_total) + 1, dtype=torch.int32, device=self.nbr.device)
+            col_ptr[1:] = torch.cumsum(counts, 0).to(torch.int32)
+            self._transposed = (int(n_total), col_ptr, col_perm)
+        return self._transposed[1], self._transposed[2]
 
 
 def build_csr(edge_index: torch.Tensor, num_centres: int) -> EdgeCSR:

@@ -131,18 +131,23 @@ class FusedAllegroEnergy(torch.nn.Module):
         )
         self._core: Optional[AllegroCore] = None
         self._core_key = None
-        self._csr_cache = None
+        self._caches: Dict[str, tuple] = {}
 
     # ------------------------------------------------------------------------------------
     def _param_key(self):
-        return tuple((p.data_ptr(), p._version) for p in self.parameters())
+        # buffers too: the dense w3j tensors are state the kernels' tables are built from
+        return tuple((p.data_ptr(), p._version) for p in list(self.parameters()) + list(self.buffers()))
 
     def core(self) -> AllegroCore:
         dev = next(self.parameters()).device
+        if dev.type != "cuda":
+            raise RuntimeError("allegro_b200: the model must live on a CUDA device (no CPU path for the hot path)")
+        return self._core_for(dev)
+
+    def _core_for(self, dev) -> AllegroCore:
+        """Packed device constants, rebuilt whenever a parameter or buffer changed (load_state_dict, .to())."""
         key = (self._param_key(), str(dev))
         if self._core is None or self._core_key != key:
-            if dev.type != "cuda":
-                raise RuntimeError("allegro_b200: the model must live on a CUDA device (no CPU path for the hot path)")
             self._core = AllegroCore(self.tensor_embed, self.allegro, self.edge_readout, self.avg_num_neighbors,
                                      self.model_dtype, dev)
             import os
@@ -163,27 +168,56 @@ class FusedAllegroEnergy(torch.nn.Module):
             raise RuntimeError("allegro_b200: inputs must be CUDA tensors (no CPU fallback on the hot path)")
         return self._energy_and_forces(data, stress)
 
+    def _cached(self, slot: str, srcs, extra, build):
+        """Derived per-neighbour-list data (CSR, int32 types, shift vectors) keyed on the IDENTITY of the
+        source tensors, their in-place version counters and ``extra``.  The cache keeps references to the
+        sources, so their storage cannot be recycled for another frame's tensors while the entry lives (a
+        key made of data_ptr alone would match a new frame that the caching allocator placed at the same
+        address)."""
+        hit = self._caches.get(slot)
+        vers = tuple(t._version for t in srcs)
+        if hit is not None and len(hit[0]) == len(srcs) and all(a is b for a, b in zip(hit[0], srcs)) and hit[1] == vers and hit[2] == extra:
+            return hit[3]
+        val = build()
+        self._caches[slot] = (tuple(srcs), vers, extra, val)
+        return val
+
+    @staticmethod
+    def _single_frame(data: D.Type):
+        """The fused path evaluates ONE frame (like the reference's compiled/deployed model, _compile.py:10-74):
+        a batched dict (``batch`` with more than one frame, or several cells) is rejected instead of being
+        summed into one total energy."""
+        b = data.get(D.BATCH_KEY)
+        if b is not None and b.numel() > 0 and int(b.max()) > 0:
+            raise NotImplementedError("allegro_b200: batched frames are not supported on the fused path; evaluate frames one at a time")
+        c = data.get(D.CELL_KEY)
+        if c is not None and c.numel() != 9:
+            raise NotImplementedError("allegro_b200: more than one cell in `data` (batched frames) is not supported")
+
     def _energy_and_forces(self, data: D.Type, stress: bool) -> D.Type:
+        self._single_frame(data)
         pos = data[D.POSITIONS_KEY]
         core = self.core()
         n = pos.shape[0]
         csr = self._csr(data[D.EDGE_INDEX_KEY], n)
         shift_vec = None
         if D.EDGE_CELL_SHIFT_KEY in data and D.CELL_KEY in data:
-            sh = data[D.EDGE_CELL_SHIFT_KEY]
-            key = (sh.data_ptr(), sh._version, data[D.CELL_KEY].data_ptr(), data[D.CELL_KEY]._version, id(csr))
-            if getattr(self, "_shift_cache", None) is None or self._shift_cache[0] != key:
+            sh, cell = data[D.EDGE_CELL_SHIFT_KEY], data[D.CELL_KEY]
+
+            def _shift():
                 s = sh if csr.perm is None else sh[csr.perm]
-                self._shift_cache = (key, (s.to(pos.dtype) @ data[D.CELL_KEY].view(3, 3).to(pos.dtype)).contiguous())
-            shift_vec = self._shift_cache[1]
-        types = data[D.ATOM_TYPE_KEY].reshape(-1)
-        tkey = (types.data_ptr(), types._version)
-        if getattr(self, "_types_cache", None) is None or self._types_cache[0] != tkey:
-            self._types_cache = (tkey, types.to(torch.int32).contiguous())
+                return (s.to(pos.dtype) @ cell.view(3, 3).to(pos.dtype)).contiguous()
+
+            shift_vec = self._cached("shift", (sh, cell), (id(csr), pos.dtype), _shift)
+        types_in = data[D.ATOM_TYPE_KEY]
+        types = types_in.reshape(-1)
+        if types.shape[0] != n:
+            raise ValueError(f"atom_types has {types.shape[0]} entries for {n} atoms")
+        types_i32 = self._cached("types", (types_in,), (n,), lambda: types.to(torch.int32).contiguous())
         ss = self.per_type_energy_scale_shift
         gscale = ss.scales[types].to(core.acc)
         want_virial = bool(stress) and D.CELL_KEY in data
-        Ei, F, X, Ez, virial = energy_forces(core, self._upstream, csr, pos.detach().contiguous(), self._types_cache[1], shift_vec,
+        Ei, F, X, Ez, virial = energy_forces(core, self._upstream, csr, pos.detach().contiguous(), types_i32, shift_vec,
                                              gscale, want_virial)
         e_atom = ss(Ei.unsqueeze(-1), types)
         out = dict(data)
@@ -204,15 +238,13 @@ class FusedAllegroEnergy(torch.nn.Module):
         return out
 
     def _csr(self, edge_index: torch.Tensor, n: int):
-        key = (edge_index.data_ptr(), edge_index._version, tuple(edge_index.shape), n)
-        if self._csr_cache is None or self._csr_cache[0] != key:
-            self._csr_cache = (key, D.build_csr(edge_index, n))
-        return self._csr_cache[1]
+        return self._cached("csr", (edge_index,), (tuple(edge_index.shape), n), lambda: D.build_csr(edge_index, n))
 
     def forward(self, data: D.Type) -> D.Type:
         pos = data[D.POSITIONS_KEY]
         if not pos.is_cuda:
             raise RuntimeError("allegro_b200: inputs must be CUDA tensors (no CPU fallback on the hot path)")
+        self._single_frame(data)
         core = self.core()
         ei = data[D.EDGE_INDEX_KEY]
         n = pos.shape[0]

@@ -97,14 +97,34 @@ class Contracter(torch.nn.Module):
         self._tab_cache = {}
 
     # ---- tables for the kernels --------------------------------------------------------
+    def w3j_entries(self):
+        """Non-zeros of the REGISTERED ``w3j`` buffer as (i, j, k, path, value) -- the buffer is state
+        (_contract.py:168), so after ``load_state_dict`` of a reference / real-e3nn checkpoint the kernels
+        contract with the checkpoint's coupling tensor (its block signs and normalisation), not with the
+        table this class generated at construction.  The layouts are the reference's: [P,]i,j,k or, when
+        every path is i==j diagonal, [P,]i,k (_contract.py:135-167)."""
+        w = self.w3j.detach().to(device="cpu", dtype=torch.float64)
+        if self.num_paths == 1:
+            w = w.unsqueeze(0)
+        nz = w.nonzero()
+        vals = w[tuple(nz.T)]
+        if self.w3j_is_ij_diagonal:
+            return [(int(i), int(i), int(k), int(p), float(v)) for (p, i, k), v in zip(nz.tolist(), vals.tolist())]
+        return [(int(i), int(j), int(k), int(p), float(v)) for (p, i, j, k), v in zip(nz.tolist(), vals.tolist())]
+
     def sparse_table(self):
-        """(ijk int32 [nnz,3], path int64 [nnz], value fp64 [nnz]) on the CPU."""
+        """(ijk int32 [nnz,3], path int64 [nnz], value fp64 [nnz]) on the CPU, from the ``w3j`` buffer."""
+        key = (self.w3j._version, self.w3j.data_ptr())
+        hit = self._tab_cache.get("sparse")
+        if hit is not None and hit[0] == key:
+            return hit[1]
         # sorted by output target (i, k), then j: the fast kernels gather each M[i][k] entry from a
         # contiguous table segment (include/allegro_b200.h, ab2_tp_fwd)
-        e = sorted(self.table.entries, key=lambda a: (a[0], a[2], a[1]))
-        ijk = torch.tensor([[a[0], a[1], a[2]] for a in e], dtype=torch.int32)
+        e = sorted(self.w3j_entries(), key=lambda a: (a[0], a[2], a[1], a[3]))
+        ijk = torch.tensor([[a[0], a[1], a[2]] for a in e], dtype=torch.int32).reshape(-1, 3)
         path = torch.tensor([a[3] for a in e], dtype=torch.long)
         val = torch.tensor([a[4] for a in e], dtype=torch.float64)
+        self._tab_cache["sparse"] = (key, (ijk, path, val))
         return ijk, path, val
 
     def cgw(self, dtype: torch.dtype, device) -> torch.Tensor:
@@ -122,7 +142,7 @@ class Contracter(torch.nn.Module):
         return out.contiguous().to(device=device, dtype=dtype)
 
     def device_tables(self, dtype, device):
-        key = (dtype, str(device), self.weights._version, self.weights.data_ptr())
+        key = (dtype, str(device), self.weights._version, self.weights.data_ptr(), self.w3j._version, self.w3j.data_ptr())
         hit = self._tab_cache.get("k")
         if hit is None or hit[0] != key:
             ijk, _, _ = self.sparse_table()

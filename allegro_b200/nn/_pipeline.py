@@ -359,7 +359,7 @@ def energy_forces(core: "AllegroCore", up: UpstreamPack, csr: EdgeCSR, pos: torc
     else:
         _lib.radial_bwd(dt, up.S_rc, up.p, vec, csr.ctr, csr.nbr, types_i32, up.rmax_table, up.bessel_w, up.Wb, up.cemb, up.nemb, g_e0, gvec)
     virial = (vec.T @ gvec.to(vec.dtype)) if want_virial else None
-    F = _lib.force_scatter(gvec, csr.row_ptr, csr.nbr, pos.shape[0])
+    F = _lib.force_scatter(gvec, csr, pos.shape[0])
     return Ei, F, X, Ez, virial
 
 

@@ -92,6 +92,36 @@ def build_workload(cfg: str, dtype: str, device, scale=None):
     return model, data, d, kw, n, e
 
 
+PARITY_TOL = {"float64": 1e-9, "float32": 1e-4, "bfloat16": 1e-3}
+
+
+def parity_check(model, out, d_cpu, kw, dtype: str, n_sample: int = 16):
+    """Before anything is timed: energies and forces of the model that is about to be timed, on the frame that is about
+    to be timed, against the fp64 CPU oracle on a sub-sample of atoms (strict locality, oracle/subsample.py).  The
+    oracle is the CHECKER here; it is never part of a timed region.  Raises if the bar is missed."""
+    from allegro_b200 import data as D
+    from oracle.model_ref import AllegroOracle
+    from oracle.subsample import ball, local_reference
+
+    kwo = dict(kw)
+    kwo["model_dtype"] = "float64"
+    oracle = AllegroOracle(**kwo)
+    oracle.load_state_dict({k: v.detach().double().cpu() for k, v in model.state_dict().items()})
+    atoms = ball(d_cpu[D.POSITIONS_KEY], n_sample, seed=7)
+    t = time.perf_counter()
+    centres, e_ref, f_ref = local_reference(oracle, d_cpu, atoms)
+    e = out[D.PER_ATOM_ENERGY_KEY].double().cpu()[centres]
+    f = out[D.FORCE_KEY].double().cpu()[atoms]
+    err_e = float((e - e_ref).abs().max() / e_ref.abs().max())
+    err_f = float((f - f_ref).abs().max() / f_ref.abs().max())
+    tol = PARITY_TOL[dtype]
+    res = {"vs": "fp64 CPU oracle on a locality sub-sample", "atoms_forces": int(atoms.numel()), "centres_energies": int(centres.numel()),
+           "rel_err_E": err_e, "rel_err_F": err_f, "tol": tol, "oracle_s": round(time.perf_counter() - t, 2)}
+    if not (err_e < tol and err_f < tol):
+        raise AssertionError(f"bench.py: the model about to be timed misses the parity bar: {res}")
+    return res
+
+
 def algorithmic_bytes_per_edge(name: str, core) -> float:
     """Bytes that must cross HBM per edge for each kernel of the current (per-kernel) pipeline
     (DESIGN.md section 4); b = bytes per activation element, 4 = fp32 accumulate-type element."""
@@ -145,6 +175,7 @@ def run_ours(args, rank: int, world: int):
     for _ in range(W):
         out = step()
     torch.cuda.synchronize()
+    parity = None if args.no_parity_check else parity_check(model, out, d_cpu, kw, dtype)
     sampler = ClockSampler(dev.index or 0)
     sampler.start()
     # ---- leg 1: inputs resident in HBM, device-timed ----
@@ -236,6 +267,7 @@ def run_ours(args, rank: int, world: int):
                 "h2d_bytes_per_step": pos_host.numel() * pos_host.element_size(),
                 "d2h_bytes_per_step": f_host.numel() * f_host.element_size() + e_host.numel() * e_host.element_size()},
         "gpu_launches": launches,
+        "parity_check": parity,
         "roofline": roofline,
         "kernels_ms_per_step": {k: round(v, 4) for k, v in sorted(per_kernel.items(), key=lambda kv: -kv[1])},
         "kernel_time_ms_per_step": round(kernel_total, 4),
@@ -455,6 +487,7 @@ def main():
     ap.add_argument("--dtype", default="float32", choices=["float64", "float32", "bfloat16"],
                     help="activation storage; default float32 (GEMMs on tcgen05 as split-bf16, fp32-accurate): bfloat16 storage, the dtype BASELINE names for c2, measured 4e-3/4e-2 (E/F) against the fp64 oracle, outside the 1e-3 parity bar")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-parity-check", action="store_true", help="skip the pre-timing E/F check against the CPU oracle sub-sample")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel from Python instead of replaying a CUDA graph")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", 0))

@@ -147,11 +147,14 @@ int ab2_edge_sum(int acc_dtype, int64_t N, const int32_t* row_ptr, const void* E
 int ab2_edge_sum_bwd(int acc_dtype, int64_t E, const int32_t* ctr, const void* gEi, double factor,
                      void* gEz, void* stream);
 
-/* Force assembly (appendix B step 9): F[ctr[z]] += g[z], F[nbr[z]] -= g[z]; centre side is a
- * segmented sum over the CSR row, neighbour side a warp-aggregated atomic add.  F pre-zeroed
- * (fp64 or fp32 = acc dtype). */
-int ab2_force_scatter(int acc_dtype, int64_t N, int64_t E, const int32_t* row_ptr,
-                      const int32_t* nbr, const void* gvec, void* F, void* stream);
+/* Force assembly (appendix B step 9): F[a] = sum_{z in CSR row a} g[z] - sum_{z: nbr[z]=a} g[z].
+ * Both sums are segmented reductions in a fixed order (deterministic, no atomics, F need not be
+ * zeroed): the neighbour side walks the TRANSPOSED CSR, col_ptr[n_total+1] / col_perm[E] = edge ids
+ * grouped by neighbour atom (built once per neighbour list).  N = number of centres (owned atoms),
+ * n_total = rows of F (owned + ghost atoms, allegro/_compile.py:41-61).  F: acc dtype. */
+int ab2_force_scatter(int acc_dtype, int64_t N, int64_t n_total, int64_t E, const int32_t* row_ptr,
+                      const int32_t* col_ptr, const int32_t* col_perm, const void* gvec, void* F,
+                      void* stream);
 
 /* ---- upstream two-body scalar track + geometry ------------------ */
 

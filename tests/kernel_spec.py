@@ -146,10 +146,10 @@ def edge_sum_bwd(gEi, ctr, factor):
     return factor * gEi[ctr.long()]
 
 
-def force_scatter(gvec, row_ptr, nbr, num_atoms_total):
+def force_scatter(gvec, csr, num_atoms_total):
     F = torch.zeros(num_atoms_total, 3, dtype=gvec.dtype)
-    F.index_add_(0, _ctr_of(row_ptr), gvec)
-    F.index_add_(0, nbr.long(), -gvec)
+    F.index_add_(0, _ctr_of(csr.row_ptr), gvec)
+    F.index_add_(0, csr.nbr.long(), -gvec)
     return F
 
 

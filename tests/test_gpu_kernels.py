@@ -316,7 +316,8 @@ def test_edge_sum_force_scatter_transpose():
         gEz = _lib.edge_sum_bwd(gEi.to(DEV, dtype), csr.ctr, 0.25)
         assert _rel(gEz, 0.25 * gEi[ctr]) < TOL[dtype]
         gv = torch.randn(E, 3, generator=g, dtype=torch.float64)
-        F = _lib.force_scatter(gv.to(DEV, dtype), csr.row_ptr, csr.nbr, N)
+        F = _lib.force_scatter(gv.to(DEV, dtype), csr, N)
+        assert torch.equal(F, _lib.force_scatter(gv.to(DEV, dtype), csr, N))  # deterministic: bitwise reproducible
         Fr = torch.zeros(N, 3, dtype=torch.float64).index_add_(0, ctr, gv).index_add_(0, csr.nbr.long().cpu(), -gv)
         assert _rel(F, Fr) < TOL[dtype] * 10
     x = torch.randn(33, 5, 7, generator=g).to(DEV)

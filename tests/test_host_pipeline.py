@@ -26,14 +26,7 @@ def spec_kernels(monkeypatch):
         monkeypatch.setattr(_lib, name, getattr(kernel_spec, name))
 
     def core(self):  # FusedAllegroEnergy.core without the "must live on a CUDA device" gate
-        if getattr(self, "_core", None) is None:
-            self._core = AllegroCore(self.tensor_embed, self.allegro, self.edge_readout, self.avg_num_neighbors, self.model_dtype, "cpu")
-            import os
-
-            fold = self._core if os.environ.get("ALLEGRO_B200_FOLD_EMBED", "0") == "1" else None
-            self._upstream = UpstreamPack(self.edge_norm, self.radial_chemical_embed, self.scalar_embed_mlp, self.model_dtype, "cpu",
-                                          fold_embed_of=fold)
-        return self._core
+        return self._core_for(torch.device("cpu"))
 
     monkeypatch.setattr(FusedAllegroEnergy, "core", core)
 
