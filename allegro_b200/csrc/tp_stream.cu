@@ -1,0 +1,639 @@
+// Streaming tensor-product kernels: the CSR rows are staged through shared memory by the TMA unit.
+//
+// Reference semantics: Contracter._contract (allegro/nn/_strided/_contract.py:213-251) after the
+// scatter/gather of :199-205, forward and both backward products (the Triton back-end's fwd / bwd1 /
+// bwd2 tables, _flashallegro.py:347-360), on centre-sorted CSR edges and the component-major layout.
+//
+// Why this shape.  With centre-sorted edges everything a centre needs is CONTIGUOUS in HBM: the rows
+// gVout[z0:z1][d_out][U], Vin[z0:z1][d_in][U] (or, layer 0, w0[z0:z1][n_ir][U] and Y[z0:z1][d]) and
+// gamma[c][d][U].  So the "neighbour-list gather" is a handful of 1-D bulk copies
+// (cp.async.bulk.shared.global, SASS UBLKCP) per stage of TE edges, issued by ONE elected producer
+// thread and completed on an mbarrier -- the memory-level parallelism (NS stages x several CTAs per
+// SM, 100+ KB in flight per SM) no longer depends on registers or on the number of resident warps,
+// which is what held the register-/shared-memory-M kernels of round 1 at 0.2-0.37 of the HBM rate.
+//
+// Work split.  Persistent-style grid: CTA b owns a contiguous range of centres holding ~E/grid edges
+// (binary search over row_ptr), i.e. one contiguous edge stream.  Per CTA:
+//   warp 2*NCH      producer : lane 0 issues the bulk copies (edge stages + gamma[c] one centre ahead),
+//                              all lanes copy the small Y rows (36 B/edge, not 16-byte aligned) with
+//                              4-byte cp.async completing on the same mbarrier (noinc arrive);
+//   warps 0..2*NCH-1 consumers: per 32-channel chunk TWO warps (lane = channel) that split the coupling
+//                              matrix M_c[i][k] = sum_nnz cgw * gamma[c][j]  by ROWS i (backward) or COLUMNS k
+//                              (forward), so M and the gradient accumulator gM stay in registers
+//                              (<= 45 + 45 values) at ~130 registers -> 4-5 CTAs per SM.
+// The backward is ONE launch: gVin / gw0 / gY per edge and gM accumulated over the centre's row, then
+// ggamma[c][j] = sum_nnz cgw * gM[i][k] once per centre -- written exactly once, no atomics, fixed order
+// (deterministic), gVout / w0 / Y read exactly once (round 1 read them twice in two launches).
+#include <type_traits>
+
+#include "common.cuh"
+#include "tp_fast.cuh"
+
+int g_ab2_opt_tp_stream = 1;    // 1: use these kernels where instantiated, 0: round-1 kernels
+int g_ab2_opt_tp_stream_te = 0;  // edges per stage (0 = default 8), 8 or 16
+int g_ab2_opt_tp_stream_cps = 0; // cap on CTAs per SM (0 = occupancy limit)
+
+namespace {
+
+constexpr int MAX_NNZ = 256;
+constexpr int NG = 3;  // gamma slots in flight
+
+// ---- PTX wrappers ---------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "TPS_WAIT:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra TPS_DONE;\n\t"
+        "bra TPS_WAIT;\n\t"
+        "TPS_DONE:\n\t"
+        "}" ::"r"(bar),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+// 1-D bulk copy global -> shared, completion counted in bytes on an mbarrier (TMA unit, no descriptor)
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
+                 "r"(bytes), "r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ void cp_async4(uint32_t dst, const void* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async8(uint32_t dst, const void* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory");
+}
+// arrive on the mbarrier once all cp.async issued so far by this thread have landed (count pre-accounted)
+__device__ __forceinline__ void cp_async_arrive_noinc(uint32_t bar) {
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void named_bar(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
+
+struct StreamParams {
+    int64_t N, E;
+    int U, D, nnz;
+    const int32_t* tab;
+    const void* cgw;
+    const int32_t* row_ptr;
+    const void* gamma;
+    const void* Vin;
+    const void* Y;
+    const void* w0;
+    void* Vout;
+    const void* gVout;
+    void* gVin;
+    void* gw0;
+    void* gY;
+    void* ggamma;
+};
+
+// Reduce N (<= 8) per-lane values across the warp: P = next power of two, P/2 + P/4 + .. + 1 shuffles for the
+// value-halving steps, then plain butterflies.  On return the lane holds the total of value `idx_of(lane)`.
+template <int N>
+struct MultiSum {
+    static constexpr int P = N <= 1 ? 1 : N <= 2 ? 2 : N <= 4 ? 4 : 8;
+    static constexpr int STEPS = P == 1 ? 0 : P == 2 ? 1 : P == 4 ? 2 : 3;
+    template <typename T>
+    static __device__ __forceinline__ T run(const T (&v)[N], int lane) {
+        T a[P];
+#pragma unroll
+        for (int t = 0; t < P; ++t) a[t] = t < N ? v[t] : T(0);
+        int off = 16;
+#pragma unroll
+        for (int cnt = P; cnt > 1; cnt >>= 1) {
+            const int half = cnt >> 1;
+            const bool up = lane & off;
+#pragma unroll
+            for (int t = 0; t < half; ++t) {
+                const T send = up ? a[t] : a[t + half];
+                const T got = __shfl_xor_sync(0xffffffffu, send, off);
+                a[t] = (up ? a[t + half] : a[t]) + got;
+            }
+            off >>= 1;
+        }
+        T r = a[0];
+#pragma unroll
+        for (; off > 0; off >>= 1) r += __shfl_xor_sync(0xffffffffu, r, off);
+        return r;
+    }
+    // value index held by `lane` (every lane of a group of 32/P lanes holds the same total)
+    static __device__ __forceinline__ int idx_of(int lane) {
+        int idx = 0;
+        if constexpr (STEPS >= 1) idx |= ((lane >> 4) & 1) << (STEPS - 1);
+        if constexpr (STEPS >= 2) idx |= ((lane >> 3) & 1) << (STEPS - 2);
+        if constexpr (STEPS >= 3) idx |= ((lane >> 2) & 1) << (STEPS - 3);
+        return idx;
+    }
+    static __device__ __forceinline__ bool is_writer(int lane) { return (lane & ((32 >> STEPS) - 1)) == 0; }
+};
+
+__device__ __forceinline__ int64_t lower_centre(const int32_t* __restrict__ row_ptr, int64_t N, int64_t target) {
+    int64_t lo = 0, hi = N;  // smallest c in [0, N] with row_ptr[c] >= target (row_ptr[N] = E >= target)
+    while (lo < hi) {
+        const int64_t mid = (lo + hi) >> 1;
+        if (row_ptr[mid] >= target) hi = mid;
+        else lo = mid + 1;
+    }
+    return lo;
+}
+
+// row split of the backward (l-aligned for the implicit layer-0 features so that a gw0 row never straddles
+// the two warps) and column split of the forward
+template <int D_IN, bool IMPLICIT>
+struct RowSplit {
+    static constexpr int IS = IMPLICIT ? (D_IN == 4 ? 1 : D_IN == 9 ? 4 : D_IN == 16 ? 9 : D_IN / 2) : D_IN / 2;
+};
+
+// shared-memory plan (byte offsets), identical on host and device
+struct Plan {
+    int bars, meta, tab, seg, jperm, jptr, gam, scratch, gyx, ring, stage_bytes, offA, offY, offB, total;
+};
+template <typename TAct, typename TAcc, int D_IN, int D_OUT, bool IMPLICIT, int MODE>
+__host__ __device__ inline Plan make_plan(int U, int D, int NCH, int TE, int NS) {
+    Plan p;
+    auto up = [](int x) { return (x + 127) & ~127; };
+    int o = 0;
+    p.bars = o;   o += up((2 * NS + 2 * NG) * 8);
+    p.meta = o;   o += up(NG * 8);
+    p.tab = o;    o += up(MAX_NNZ * 4);
+    p.seg = o;    o += up((D_IN * D_OUT + 1) * 4);
+    p.jperm = o;  o += up(MAX_NNZ * 2);
+    p.jptr = o;   o += up((D + 1) * 4);
+    p.gam = o;    o += up(NG * D * U * (int)sizeof(TAcc));
+    p.scratch = o; o += up(NCH * D_IN * D_OUT * 32 * (int)sizeof(TAcc));
+    p.gyx = o;    o += (NCH > 1 && MODE == 1 && IMPLICIT) ? up(NCH * TE * D_IN * (int)sizeof(TAcc)) : 0;
+    // one stage: [A block: Vin rows | w0 rows] [Y rows] [B block: gVout rows]
+    const int n_ir = IMPLICIT ? (D_IN == 1 ? 1 : D_IN == 4 ? 2 : D_IN == 9 ? 3 : D_IN == 16 ? 4 : 5) : 0;
+    const int rowA = IMPLICIT ? n_ir * U * (int)sizeof(TAct) : D_IN * U * (int)sizeof(TAct);
+    const int rowB = MODE == 1 ? D_OUT * U * (int)sizeof(TAct) : 0;
+    p.offA = 0;
+    p.offY = up(TE * rowA);
+    p.offB = p.offY + (IMPLICIT ? up(TE * D_IN * (int)sizeof(TAcc)) : 0);
+    p.stage_bytes = p.offB + up(TE * rowB);
+    p.ring = o;   o += NS * p.stage_bytes;
+    p.total = o;
+    return p;
+}
+
+template <typename TAct, typename TAcc, int D_IN, int D_OUT, bool IMPLICIT, int MODE, int NCH, int TE, int NS>
+__global__ void __launch_bounds__((2 * NCH + 1) * 32) tp_stream_kernel(const StreamParams p) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    constexpr int NCW = 2 * NCH;  // consumer warps
+    constexpr int T = D_IN * D_OUT;
+    constexpr int N_IR = IMPLICIT ? (D_IN == 1 ? 1 : D_IN == 4 ? 2 : D_IN == 9 ? 3 : D_IN == 16 ? 4 : 5) : 0;
+    const int U = p.U, D = p.D;
+    const Plan pl = make_plan<TAct, TAcc, D_IN, D_OUT, IMPLICIT, MODE>(U, D, NCH, TE, NS);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + pl.bars);
+    int2* s_meta = reinterpret_cast<int2*>(smem + pl.meta);
+    uchar4* s_tab = reinterpret_cast<uchar4*>(smem + pl.tab);
+    int* s_seg = reinterpret_cast<int*>(smem + pl.seg);
+    uint16_t* s_jperm = reinterpret_cast<uint16_t*>(smem + pl.jperm);
+    int* s_jptr = reinterpret_cast<int*>(smem + pl.jptr);
+    TAcc* s_gam = reinterpret_cast<TAcc*>(smem + pl.gam);
+    TAcc* s_scr = reinterpret_cast<TAcc*>(smem + pl.scratch);
+    TAcc* s_gyx = reinterpret_cast<TAcc*>(smem + pl.gyx);
+    uint8_t* ring = smem + pl.ring;
+    const uint32_t bar0 = smem_u32(bars);
+    auto full_bar = [&](int s) { return bar0 + 8u * s; };
+    auto empty_bar = [&](int s) { return bar0 + 8u * (NS + s); };
+    auto gfull_bar = [&](int g) { return bar0 + 8u * (2 * NS + g); };
+    auto gempty_bar = [&](int g) { return bar0 + 8u * (2 * NS + NG + g); };
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nnz = p.nnz;
+
+    // ---- one-time setup: barriers, tables ----
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < NS; ++s) {
+            mbar_init(full_bar(s), IMPLICIT ? 33 : 1);
+            mbar_init(empty_bar(s), NCW);
+        }
+        for (int g = 0; g < NG; ++g) {
+            mbar_init(gfull_bar(g), 1);
+            mbar_init(gempty_bar(g), NCW);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    for (int n = threadIdx.x; n < nnz; n += blockDim.x)
+        s_tab[n] = make_uchar4((unsigned char)p.tab[3 * n], (unsigned char)p.tab[3 * n + 1], (unsigned char)p.tab[3 * n + 2], 0);
+    for (int t = threadIdx.x; t <= T; t += blockDim.x) s_seg[t] = -1;
+    __syncthreads();
+    // segment start of every (i,k) target in the (i,k)-sorted table
+    for (int n = threadIdx.x; n < nnz; n += blockDim.x) {
+        const int t = s_tab[n].x * D_OUT + s_tab[n].z;
+        if (n == 0 || (s_tab[n - 1].x * D_OUT + s_tab[n - 1].z) != t) s_seg[t] = n;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        s_seg[T] = nnz;
+        for (int t = T - 1; t >= 0; --t)
+            if (s_seg[t] < 0) s_seg[t] = s_seg[t + 1];
+        // entries grouped by j (stable: ascending entry id inside a group) for the gM -> ggamma contraction
+        int pos = 0;
+        for (int j = 0; j < D; ++j) {
+            s_jptr[j] = pos;
+            for (int n = 0; n < nnz; ++n)
+                if (s_tab[n].y == j) s_jperm[pos++] = (uint16_t)n;
+        }
+        s_jptr[D] = pos;
+    }
+    __syncthreads();
+
+    // ---- this CTA's contiguous range of centres / edges ----
+    const int64_t G = gridDim.x, b = blockIdx.x;
+    const int64_t c_lo = (b == 0) ? 0 : lower_centre(p.row_ptr, p.N, b * p.E / G);
+    const int64_t c_hi = (b == G - 1) ? p.N : lower_centre(p.row_ptr, p.N, (b + 1) * p.E / G);
+    const int64_t e_lo = p.row_ptr[c_lo], e_hi = p.row_ptr[c_hi];
+    const TAct* __restrict__ gA = IMPLICIT ? (const TAct*)p.w0 : (const TAct*)p.Vin;
+    const int rowA_el = IMPLICIT ? N_IR * U : D_IN * U;  // elements per edge of the A block
+    const int rowB_el = D_OUT * U;
+    const uint32_t gam_bytes = (uint32_t)(D * U * sizeof(TAcc));
+
+    if (warp == NCW) {
+        // =============================== producer ===============================
+        int stage = 0, gslot = 0;
+        uint32_t phase = 0, gphase = 0;
+        int64_t c_iss = c_lo;  // next centre whose gamma row has not been issued
+        // gamma rows run ahead of the edge stages: every non-empty centre beginning before `look_end` is issued.
+        // Waiting for a free slot is only allowed for centres that begin inside already issued stages
+        // (< issued_end): the consumers can reach those and free a slot.  For look-ahead centres a busy ring
+        // just ends the pass (a blocking wait could deadlock when more than NG tiny centres begin in one stage).
+        auto issue_gammas = [&](int64_t issued_end, int64_t look_end) {
+            while (c_iss < c_hi) {
+                const int rb = p.row_ptr[c_iss], re = p.row_ptr[c_iss + 1];
+                if (rb >= look_end) break;
+                if (re > rb) {
+                    if (rb < issued_end) mbar_wait(gempty_bar(gslot), gphase ^ 1);
+                    else if (!mbar_test(gempty_bar(gslot), gphase ^ 1)) break;
+                    s_meta[gslot] = make_int2((int)c_iss, re);
+                    mbar_expect_tx(gfull_bar(gslot), gam_bytes);
+                    bulk_g2s(smem_u32(s_gam + (size_t)gslot * D * U), (const TAcc*)p.gamma + c_iss * D * U, gam_bytes, gfull_bar(gslot));
+                    if (++gslot == NG) { gslot = 0; gphase ^= 1; }
+                }
+                ++c_iss;
+            }
+        };
+        if (lane == 0) issue_gammas(e_lo, e_lo + TE);
+        for (int64_t za = e_lo; za < e_hi; za += TE) {
+            const int n = (int)((e_hi - za) < TE ? (e_hi - za) : TE);
+            if (lane == 0) mbar_wait(empty_bar(stage), phase ^ 1);
+            __syncwarp();
+            uint8_t* sb = ring + (size_t)stage * pl.stage_bytes;
+            if (lane == 0) {
+                const uint32_t bytesA = (uint32_t)(n * rowA_el * sizeof(TAct));
+                const uint32_t bytesB = MODE == 1 ? (uint32_t)(n * rowB_el * sizeof(TAct)) : 0u;
+                mbar_expect_tx(full_bar(stage), bytesA + bytesB);
+                bulk_g2s(smem_u32(sb + pl.offA), gA + za * rowA_el, bytesA, full_bar(stage));
+                if (MODE == 1) bulk_g2s(smem_u32(sb + pl.offB), (const TAct*)p.gVout + za * rowB_el, bytesB, full_bar(stage));
+            }
+            if (IMPLICIT) {
+                // Y rows: n * D_IN accumulate-type values, 4-byte aligned only -> element-wise cp.async
+                const TAcc* __restrict__ ysrc = (const TAcc*)p.Y + za * D_IN;
+                const uint32_t ydst = smem_u32(sb + pl.offY);
+                for (int e = lane; e < n * D_IN; e += 32) {
+                    if (sizeof(TAcc) == 4) cp_async4(ydst + 4u * e, ysrc + e);
+                    else cp_async8(ydst + 8u * e, ysrc + e);
+                }
+                cp_async_arrive_noinc(full_bar(stage));
+            }
+            if (lane == 0) issue_gammas(za + n, za + n + TE);
+            if (++stage == NS) { stage = 0; phase ^= 1; }
+        }
+        if (IMPLICIT) asm volatile("cp.async.wait_all;" ::: "memory");
+        return;
+    }
+
+    // =============================== consumers ===============================
+    const int q = warp >> 1, role = warp & 1;  // channel chunk, row/column half
+    const int u = q * 32 + lane;
+    const bool live = u < U;
+    TAcc* scr = s_scr + (size_t)q * T * 32;
+    const TAcc* __restrict__ cgw = (const TAcc*)p.cgw;
+
+    auto run = [&](auto role_tag) {
+        constexpr int ROLE = decltype(role_tag)::value;
+        constexpr int IS = RowSplit<D_IN, IMPLICIT>::IS;
+        constexpr int KS = D_OUT / 2;
+        // rows (backward) / columns (forward) owned by this warp
+        constexpr int I0 = MODE == 1 ? (ROLE ? IS : 0) : 0;
+        constexpr int NI = MODE == 1 ? (ROLE ? D_IN - IS : IS) : D_IN;
+        constexpr int K0 = MODE == 0 ? (ROLE ? KS : 0) : 0;
+        constexpr int NK = MODE == 0 ? (ROLE ? D_OUT - KS : KS) : D_OUT;
+        // Blackwell issues one 3-register FFMA per 2 cycles per SM sub-partition; the full fp32 rate needs the packed
+        // FFMA2 (fma.rn.f32x2).  M and gM are therefore held as column PAIRS (k, k+1) (+ one single column when NK is odd).
+        constexpr int KP = NK / 2, KR = NK % 2;
+        float2 M2[NI][KP > 0 ? KP : 1];
+        float Mr[NI];
+        float2 gM2[MODE == 1 ? NI : 1][KP > 0 ? KP : 1];
+        float gMr[MODE == 1 ? NI : 1];
+        int stage = 0, gslot = 0;
+        uint32_t phase = 0, gphase = 0;
+        int64_t c = -1, c_prev = c_lo - 1;
+        int64_t row_end = e_lo;
+
+        auto zero_ggamma = [&](int64_t ca, int64_t cb) {  // centres without edges in (ca, cb): ggamma = 0
+            if constexpr (MODE == 1) {
+                for (int64_t cc = ca + 1; cc < cb; ++cc)
+                    for (int j = role; j < D; j += 2)
+                        if (live) ((TAcc*)p.ggamma)[(cc * D + j) * U + u] = TAcc(0);
+            }
+        };
+        auto end_centre = [&]() {
+            if constexpr (MODE == 1) {
+                // gM -> ggamma[c][j] = sum_nnz cgw * gM[i][k]; both halves meet in the scratch buffer
+#pragma unroll
+                for (int i = 0; i < NI; ++i) {
+#pragma unroll
+                    for (int kp = 0; kp < KP; ++kp) {
+                        scr[((I0 + i) * D_OUT + 2 * kp) * 32 + lane] = gM2[i][kp].x;
+                        scr[((I0 + i) * D_OUT + 2 * kp + 1) * 32 + lane] = gM2[i][kp].y;
+                    }
+                    if (KR) scr[((I0 + i) * D_OUT + NK - 1) * 32 + lane] = gMr[i];
+                }
+                named_bar(1 + q, 64);
+                if (live) {
+                    for (int j = role; j < D; j += 2) {
+                        TAcc acc = TAcc(0);
+                        for (int n = s_jptr[j]; n < s_jptr[j + 1]; ++n) {
+                            const int e = s_jperm[n];
+                            const uchar4 t4 = s_tab[e];
+                            acc += cgw[(int64_t)e * U + u] * scr[(t4.x * D_OUT + t4.z) * 32 + lane];
+                        }
+                        ((TAcc*)p.ggamma)[(c * D + j) * U + u] = acc;
+                    }
+                }
+                named_bar(1 + q, 64);  // scratch is reused by the next centre's build
+            }
+        };
+        auto begin_centre = [&]() {
+            mbar_wait(gfull_bar(gslot), gphase);
+            const int2 mt = s_meta[gslot];
+            c = mt.x;
+            row_end = mt.y;
+            zero_ggamma(c_prev, c);
+            c_prev = c;
+            const TAcc* __restrict__ gam = s_gam + (size_t)gslot * D * U;
+            // every owned M[i][k]: register gather over its table segment, parked in the scratch buffer
+            // (table indices are run-time data), then pulled into registers with static indices
+            for (int ii = 0; ii < NI; ++ii)
+                for (int kk = 0; kk < NK; ++kk) {
+                    const int t = (I0 + ii) * D_OUT + (K0 + kk);
+                    TAcc acc = TAcc(0);
+                    if (live)
+                        for (int n = s_seg[t]; n < s_seg[t + 1]; ++n) acc += cgw[(int64_t)n * U + u] * gam[s_tab[n].y * U + u];
+                    scr[t * 32 + lane] = acc;
+                }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(gempty_bar(gslot));
+            if (++gslot == NG) { gslot = 0; gphase ^= 1; }
+#pragma unroll
+            for (int i = 0; i < NI; ++i) {
+#pragma unroll
+                for (int kp = 0; kp < KP; ++kp) {
+                    M2[i][kp] = make_float2(scr[((I0 + i) * D_OUT + K0 + 2 * kp) * 32 + lane], scr[((I0 + i) * D_OUT + K0 + 2 * kp + 1) * 32 + lane]);
+                    if (MODE == 1) gM2[i][kp] = make_float2(0.f, 0.f);
+                }
+                if (KR) Mr[i] = scr[((I0 + i) * D_OUT + K0 + NK - 1) * 32 + lane];
+                if (MODE == 1) gMr[i] = 0.f;
+            }
+        };
+
+        for (int64_t za = e_lo; za < e_hi; za += TE) {
+            const int n = (int)((e_hi - za) < TE ? (e_hi - za) : TE);
+            mbar_wait(full_bar(stage), phase);
+            const uint8_t* sb = ring + (size_t)stage * pl.stage_bytes;
+            const TAct* __restrict__ sA = reinterpret_cast<const TAct*>(sb + pl.offA);
+            [[maybe_unused]] const TAcc* __restrict__ sY = reinterpret_cast<const TAcc*>(sb + pl.offY);
+            [[maybe_unused]] const TAct* __restrict__ sB = reinterpret_cast<const TAct*>(sb + pl.offB);
+            for (int t = 0; t < n; ++t) {
+                const int64_t z = za + t;
+                if (z == row_end) {  // warp-uniform: first edge of the next non-empty centre
+                    if (c >= 0) end_centre();
+                    begin_centre();
+                }
+                if constexpr (MODE == 0) {
+                    // ---------------- forward: Vout[z][K0..][u] = sum_i v[i] M[i][k] ----------------
+                    float v[D_IN];
+                    if constexpr (IMPLICIT) {
+                        float wl[N_IR];
+#pragma unroll
+                        for (int l = 0; l < N_IR; ++l) wl[l] = live ? to_acc<float>(sA[(t * N_IR + l) * U + u]) : 0.f;
+#pragma unroll
+                        for (int i = 0; i < D_IN; ++i) v[i] = sY[t * D_IN + i] * wl[sh_l_of(i)];
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < D_IN; ++i) v[i] = live ? to_acc<float>(sA[(t * D_IN + i) * U + u]) : 0.f;
+                    }
+                    float2 o2[KP > 0 ? KP : 1];
+                    float o_r = 0.f;
+#pragma unroll
+                    for (int kp = 0; kp < KP; ++kp) o2[kp] = make_float2(0.f, 0.f);
+#pragma unroll
+                    for (int i = 0; i < D_IN; ++i) {
+                        const float2 vv = make_float2(v[i], v[i]);
+#pragma unroll
+                        for (int kp = 0; kp < KP; ++kp) o2[kp] = __ffma2_rn(vv, M2[i][kp], o2[kp]);
+                        if (KR) o_r = fmaf(v[i], Mr[i], o_r);
+                    }
+                    if (live) {
+                        TAct* __restrict__ dst = (TAct*)p.Vout + (z * D_OUT + K0) * U + u;
+#pragma unroll
+                        for (int kp = 0; kp < KP; ++kp) {
+                            dst[(2 * kp) * U] = from_acc<TAct>(o2[kp].x);
+                            dst[(2 * kp + 1) * U] = from_acc<TAct>(o2[kp].y);
+                        }
+                        if (KR) dst[(NK - 1) * U] = from_acc<TAct>(o_r);
+                    }
+                } else {
+                    // ---------------- backward ----------------
+                    float2 go2[KP > 0 ? KP : 1];
+                    float go_r = 0.f;
+#pragma unroll
+                    for (int kp = 0; kp < KP; ++kp)
+                        go2[kp] = live ? make_float2(to_acc<float>(sB[(t * D_OUT + 2 * kp) * U + u]), to_acc<float>(sB[(t * D_OUT + 2 * kp + 1) * U + u]))
+                                       : make_float2(0.f, 0.f);
+                    if (KR) go_r = live ? to_acc<float>(sB[(t * D_OUT + NK - 1) * U + u]) : 0.f;
+                    float v[NI], gin[NI];
+                    [[maybe_unused]] float wl[IMPLICIT ? N_IR : 1];
+                    [[maybe_unused]] float Yv[IMPLICIT ? NI : 1];
+                    if constexpr (IMPLICIT) {
+#pragma unroll
+                        for (int l = 0; l < N_IR; ++l)
+                            if (l * l < I0 + NI && (l + 1) * (l + 1) > I0) wl[l] = live ? to_acc<float>(sA[(t * N_IR + l) * U + u]) : 0.f;
+#pragma unroll
+                        for (int i = 0; i < NI; ++i) {
+                            Yv[i] = sY[t * D_IN + I0 + i];
+                            v[i] = Yv[i] * wl[sh_l_of(I0 + i)];
+                        }
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < NI; ++i) v[i] = live ? to_acc<float>(sA[(t * D_IN + I0 + i) * U + u]) : 0.f;
+                    }
+#pragma unroll
+                    for (int i = 0; i < NI; ++i) {
+                        float2 a2 = make_float2(0.f, 0.f);
+                        const float2 vv = make_float2(v[i], v[i]);
+#pragma unroll
+                        for (int kp = 0; kp < KP; ++kp) {
+                            a2 = __ffma2_rn(M2[i][kp], go2[kp], a2);
+                            gM2[i][kp] = __ffma2_rn(vv, go2[kp], gM2[i][kp]);
+                        }
+                        float s = a2.x + a2.y;
+                        if (KR) {
+                            s = fmaf(Mr[i], go_r, s);
+                            gMr[i] = fmaf(v[i], go_r, gMr[i]);
+                        }
+                        gin[i] = s;
+                    }
+                    if constexpr (IMPLICIT) {
+                        // Vin[i] = Y[i] w0[l(i)]:  gw0[l] = sum_{i in l} Y[i] gin[i];  gY[i] += sum_u w0[l(i)][u] gin[i]
+                        float part[NI];
+#pragma unroll
+                        for (int l = 0; l < N_IR; ++l) {
+                            if (l * l >= I0 && (l + 1) * (l + 1) <= I0 + NI) {  // l owned entirely by this warp
+                                float s = 0.f;
+#pragma unroll
+                                for (int i = l * l; i < (l + 1) * (l + 1); ++i) s = fmaf(Yv[i - I0], gin[i - I0], s);
+                                if (live) ((TAct*)p.gw0)[z * (int64_t)(N_IR * U) + l * U + u] = from_acc<TAct>(s);
+                            }
+                        }
+#pragma unroll
+                        for (int i = 0; i < NI; ++i) part[i] = wl[sh_l_of(I0 + i)] * gin[i];
+                        const float tot = MultiSum<NI>::run(part, lane);
+                        const int idx = MultiSum<NI>::idx_of(lane);
+                        if (MultiSum<NI>::is_writer(lane) && idx < NI) {
+                            if (NCH == 1) atomicAdd((float*)p.gY + z * D_IN + I0 + idx, tot);  // RED, single writer per address
+                            else s_gyx[(q * TE + t) * D_IN + I0 + idx] = tot;
+                        }
+                    } else {
+                        if (live) {
+                            TAct* __restrict__ dst = (TAct*)p.gVin + (z * D_IN + I0) * U + u;
+#pragma unroll
+                            for (int i = 0; i < NI; ++i) dst[i * U] = from_acc<TAct>(gin[i]);
+                        }
+                    }
+                }
+            }
+            if constexpr (NCH > 1 && MODE == 1 && IMPLICIT) {
+                // channel chunks of one role meet here: fixed summation order over chunks (deterministic)
+                named_bar(3 + role, 32 * NCH);
+                if (q == 0) {
+                    for (int e = lane; e < n * NI; e += 32) {
+                        const int t = e / NI, i = I0 + e % NI;
+                        float s = 0.f;
+#pragma unroll
+                        for (int qq = 0; qq < NCH; ++qq) s += s_gyx[(qq * TE + t) * D_IN + i];
+                        atomicAdd((float*)p.gY + (za + t) * D_IN + i, s);
+                    }
+                }
+                named_bar(3 + role, 32 * NCH);
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(empty_bar(stage));
+            if (++stage == NS) { stage = 0; phase ^= 1; }
+        }
+        if (c >= 0) end_centre();
+        zero_ggamma(c_prev, c_hi);
+    };
+    if (role == 0) run(std::integral_constant<int, 0>{});
+    else run(std::integral_constant<int, 1>{});
+}
+
+template <typename TAct, typename TAcc, int D_IN, int D_OUT, bool IMPLICIT, int MODE, int NCH, int TE, int NS>
+int launch_cfg(const StreamParams& p, cudaStream_t st) {
+    auto kern = tp_stream_kernel<TAct, TAcc, D_IN, D_OUT, IMPLICIT, MODE, NCH, TE, NS>;
+    const Plan pl = make_plan<TAct, TAcc, D_IN, D_OUT, IMPLICIT, MODE>(p.U, p.D, NCH, TE, NS);
+    static int num_sms = 0, max_smem = 0;
+    if (num_sms == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+        cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    }
+    if (pl.total > max_smem) return -1;
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, pl.total) != cudaSuccess) {
+        cudaGetLastError();
+        return -1;
+    }
+    const int threads = (2 * NCH + 1) * 32;
+    int cps = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&cps, kern, threads, pl.total) != cudaSuccess || cps < 1) {
+        cudaGetLastError();
+        return -1;
+    }
+    if (g_ab2_opt_tp_stream_cps > 0 && cps > g_ab2_opt_tp_stream_cps) cps = g_ab2_opt_tp_stream_cps;
+    int64_t grid = (int64_t)num_sms * cps;
+    if (grid > p.N) grid = p.N;
+    if (grid < 1) grid = 1;
+    kern<<<(unsigned)grid, threads, pl.total, st>>>(p);
+    return 0;
+}
+
+template <typename TAct, typename TAcc, int D_IN, int D_OUT, bool IMPLICIT, int MODE>
+int launch_shape(const StreamParams& p, cudaStream_t st) {
+    const int te = g_ab2_opt_tp_stream_te == 16 ? 16 : 8;
+    if (p.U <= 32) {
+        if (te == 16) return launch_cfg<TAct, TAcc, D_IN, D_OUT, IMPLICIT, MODE, 1, 16, 2>(p, st);
+        return launch_cfg<TAct, TAcc, D_IN, D_OUT, IMPLICIT, MODE, 1, 8, 3>(p, st);
+    }
+    if (p.U <= 64) return launch_cfg<TAct, TAcc, D_IN, D_OUT, IMPLICIT, MODE, 2, 8, 2>(p, st);
+    return -1;
+}
+
+}  // namespace
+
+// returns 0 if launched, -1 if (dtype, shape, alignment) has no streaming instantiation
+int ab2_tp_stream(int mode, int dtype, int64_t N, int64_t E, int U, int D, int d_in, int d_out, int nnz, const int32_t* tab,
+                  const void* cgw, const int32_t* row_ptr, const void* gamma, const void* Vin, int implicit_v0, const void* Y,
+                  const void* w0, int64_t w0_ld, void* Vout, const void* gVout, void* gVin, void* gw0, int64_t gw0_ld, void* gY,
+                  void* ggamma, cudaStream_t st) {
+    if (!g_ab2_opt_tp_stream || dtype == AB2_F64 || nnz > MAX_NNZ || nnz <= 0 || E <= 0 || N <= 0) return -1;
+    if (d_in != d_out || !(d_in == 4 || d_in == 9) || (implicit_v0 && D != d_in)) return -1;
+    const int esz = dtype == AB2_F32 ? 4 : 2;
+    // bulk copies move whole rows: 16-byte multiples, 16-byte aligned bases, dense rows
+    if ((U * esz) % 16 != 0 || (U * 4) % 16 != 0) return -1;
+    const int n_ir = d_in == 4 ? 2 : 3;
+    if (implicit_v0 && (w0_ld != (int64_t)n_ir * U || (mode == 1 && gw0_ld != (int64_t)n_ir * U))) return -1;
+    auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+    if (!al16(gamma) || (implicit_v0 ? !al16(w0) : !al16(Vin)) || (mode == 1 && !al16(gVout))) return -1;
+    StreamParams p;
+    p.N = N; p.E = E; p.U = U; p.D = D; p.nnz = nnz; p.tab = tab; p.cgw = cgw; p.row_ptr = row_ptr; p.gamma = gamma;
+    p.Vin = Vin; p.Y = Y; p.w0 = w0; p.Vout = Vout; p.gVout = gVout; p.gVin = gVin; p.gw0 = gw0; p.gY = gY; p.ggamma = ggamma;
+#define AB2_STREAM_CASE(TA, DI)                                                                                        \
+    if (d_in == DI) {                                                                                                   \
+        if (mode == 0) return implicit_v0 ? launch_shape<TA, float, DI, DI, true, 0>(p, st) : launch_shape<TA, float, DI, DI, false, 0>(p, st); \
+        return implicit_v0 ? launch_shape<TA, float, DI, DI, true, 1>(p, st) : launch_shape<TA, float, DI, DI, false, 1>(p, st);               \
+    }
+    if (dtype == AB2_F32) {
+        AB2_STREAM_CASE(float, 9)
+        AB2_STREAM_CASE(float, 4)
+    } else {
+        AB2_STREAM_CASE(bf16, 9)
+        AB2_STREAM_CASE(bf16, 4)
+    }
+#undef AB2_STREAM_CASE
+    return -1;
+}

@@ -91,7 +91,11 @@ class PackedMLP:
     """
 
     def __init__(self, mlp: ScalarMLPFunction, dtype: torch.dtype, device, out_perm=None, in_perm=None, extra_first=None, post=None):
-        ws = mlp.folded_weights()
+        ws = [w.cpu() for w in mlp.folded_weights()]  # packing is done on the host in fp64
+        if extra_first is not None:
+            extra_first = [w.detach().double().cpu() for w in extra_first]
+        if post is not None:
+            post = post.detach().double().cpu()
         if extra_first is not None:  # horizontally fused sibling linears sharing the input
             assert len(ws) == 1
             ws = [torch.cat([ws[0]] + list(extra_first), dim=1)]

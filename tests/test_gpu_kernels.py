@@ -222,11 +222,18 @@ def _tp_case(lmax, layer, L, U, coupling, dtype, seed=0):
     return c, b
 
 
-@pytest.fixture(params=[1, 2, 0], ids=["fast", "regM", "generic"])
+@pytest.fixture(params=[(1, 1, 8), (1, 1, 16), (1, 0, 8), (2, 0, 8), (0, 0, 8)], ids=["stream", "stream_te16", "fast", "regM", "generic"])
 def tp_fast(request):
-    _lib.set_option("tp_fast", request.param)
+    """Kernel families of the tensor product: TMA-staged streaming kernels (round 2, default where instantiated), the
+    round-1 shared-memory-M / split kernels, the register-M kernels, the shape-generic kernels."""
+    fast, stream, te = request.param
+    _lib.set_option("tp_fast", fast)
+    _lib.set_option("tp_stream", stream)
+    _lib.set_option("tp_stream_te", te)
     yield request.param
     _lib.set_option("tp_fast", 1)
+    _lib.set_option("tp_stream", 1)
+    _lib.set_option("tp_stream_te", 0)
 
 
 @pytest.mark.parametrize("case", [(1, 0, 1), (2, 0, 2), (2, 1, 2), (3, 0, 3), (3, 1, 3), (3, 2, 3), (1, 0, 2), (1, 1, 3)])
