@@ -104,7 +104,7 @@ extern "C" int ab2_tp_fwd(int dtype, int lmax, int64_t N, int64_t E, int U, int 
     AB2_CHECK_ARG(implicit_v0 ? (Y && w0 && d_in == D) : (Vin != nullptr), "input features");
     cudaStream_t st = (cudaStream_t)stream;
     if (g_ab2_opt_tp_fast && row_ptr &&
-        ab2_tp_stream(0, dtype, N, E, U, D, d_in, d_out, nnz, tab_ijk, cgw, row_ptr, gamma, Vin, implicit_v0, Y, w0, w0_ld, Vout, nullptr,
+        ab2_tp_stream(0, dtype, N, E, U, D, d_in, d_out, nnz, tab_ijk, cgw, row_ptr, ctr, gamma, Vin, implicit_v0, Y, w0, w0_ld, Vout, nullptr,
                       nullptr, nullptr, 0, nullptr, nullptr, st) == 0) {
         AB2_CUDA_LAUNCH_CHECK();
         return 0;
@@ -134,7 +134,7 @@ extern "C" int ab2_tp_bwd(int dtype, int lmax, int64_t N, int64_t E, int U, int 
     AB2_CHECK_ARG(implicit_v0 ? (Y && w0 && gw0 && gY && d_in == D) : (Vin && gVin), "input features / grads");
     cudaStream_t st = (cudaStream_t)stream;
     if (g_ab2_opt_tp_fast && row_ptr &&
-        ab2_tp_stream(1, dtype, N, E, U, D, d_in, d_out, nnz, tab_ijk, cgw, row_ptr, gamma, Vin, implicit_v0, Y, w0, w0_ld, nullptr, gVout,
+        ab2_tp_stream(1, dtype, N, E, U, D, d_in, d_out, nnz, tab_ijk, cgw, row_ptr, ctr, gamma, Vin, implicit_v0, Y, w0, w0_ld, nullptr, gVout,
                       gVin, gw0, gw0_ld, gY, ggamma, st) == 0) {
         AB2_CUDA_LAUNCH_CHECK();
         return 0;

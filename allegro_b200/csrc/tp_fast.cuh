@@ -23,7 +23,7 @@ extern int g_ab2_opt_tp_fast;  // 0 generic, 1 fast (smem-M fwd, split bwd), 2 r
 
 // TMA-staged streaming kernels (tp_stream.cu): mode 0 forward, mode 1 the whole backward in one launch
 int ab2_tp_stream(int mode, int dtype, int64_t N, int64_t E, int U, int D, int d_in, int d_out, int nnz, const int32_t* tab,
-                  const void* cgw, const int32_t* row_ptr, const void* gamma, const void* Vin, int implicit_v0, const void* Y,
+                  const void* cgw, const int32_t* row_ptr, const int32_t* ctr, const void* gamma, const void* Vin, int implicit_v0, const void* Y,
                   const void* w0, int64_t w0_ld, void* Vout, const void* gVout, void* gVin, void* gw0, int64_t gw0_ld, void* gY,
                   void* ggamma, cudaStream_t st);
 extern int g_ab2_opt_tp_stream, g_ab2_opt_tp_stream_te, g_ab2_opt_tp_stream_cps;

@@ -99,6 +99,7 @@ struct StreamParams {
     const int32_t* tab;
     const void* cgw;
     const int32_t* row_ptr;
+    const int32_t* ctr;
     const void* gamma;
     const void* Vin;
     const void* Y;
@@ -151,14 +152,16 @@ struct MultiSum {
     static __device__ __forceinline__ bool is_writer(int lane) { return (lane & ((32 >> STEPS) - 1)) == 0; }
 };
 
-__device__ __forceinline__ int64_t lower_centre(const int32_t* __restrict__ row_ptr, int64_t N, int64_t target) {
-    int64_t lo = 0, hi = N;  // smallest c in [0, N] with row_ptr[c] >= target (row_ptr[N] = E >= target)
-    while (lo < hi) {
-        const int64_t mid = (lo + hi) >> 1;
-        if (row_ptr[mid] >= target) hi = mid;
-        else lo = mid + 1;
-    }
-    return lo;
+// First centre of CTA b's range: the edge stream is cut every E/G edges, snapped forward to the next centre
+// boundary.  Two dependent loads (ctr[t], row_ptr[c]) instead of a binary search over row_ptr.
+__device__ __forceinline__ int64_t cut_centre(const int32_t* __restrict__ row_ptr, const int32_t* __restrict__ ctr, int64_t N, int64_t E,
+                                              int64_t b, int64_t G) {
+    if (b <= 0) return 0;
+    if (b >= G) return N;
+    const int64_t t = b * E / G;
+    if (t >= E) return N;
+    const int64_t c = ctr[t];
+    return row_ptr[c] == t ? c : c + 1;
 }
 
 // row split of the backward (l-aligned for the implicit layer-0 features so that a gw0 row never straddles
@@ -251,21 +254,30 @@ __global__ void __launch_bounds__((2 * NCH + 1) * 32) tp_stream_kernel(const Str
         s_seg[T] = nnz;
         for (int t = T - 1; t >= 0; --t)
             if (s_seg[t] < 0) s_seg[t] = s_seg[t + 1];
-        // entries grouped by j (stable: ascending entry id inside a group) for the gM -> ggamma contraction
-        int pos = 0;
-        for (int j = 0; j < D; ++j) {
-            s_jptr[j] = pos;
-            for (int n = 0; n < nnz; ++n)
-                if (s_tab[n].y == j) s_jperm[pos++] = (uint16_t)n;
-        }
-        s_jptr[D] = pos;
+    }
+    // entries grouped by j (stable: ascending entry id inside a group) for the gM -> ggamma contraction
+    if (threadIdx.x < D) {
+        int cnt = 0;
+        for (int n = 0; n < nnz; ++n) cnt += (s_tab[n].y == threadIdx.x) ? 1 : 0;
+        s_jptr[threadIdx.x + 1] = cnt;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        s_jptr[0] = 0;
+        for (int j = 0; j < D; ++j) s_jptr[j + 1] += s_jptr[j];
+    }
+    __syncthreads();
+    if (threadIdx.x < D) {
+        int pos = s_jptr[threadIdx.x];
+        for (int n = 0; n < nnz; ++n)
+            if (s_tab[n].y == threadIdx.x) s_jperm[pos++] = (uint16_t)n;
     }
     __syncthreads();
 
     // ---- this CTA's contiguous range of centres / edges ----
     const int64_t G = gridDim.x, b = blockIdx.x;
-    const int64_t c_lo = (b == 0) ? 0 : lower_centre(p.row_ptr, p.N, b * p.E / G);
-    const int64_t c_hi = (b == G - 1) ? p.N : lower_centre(p.row_ptr, p.N, (b + 1) * p.E / G);
+    const int64_t c_lo = cut_centre(p.row_ptr, p.ctr, p.N, p.E, b, G);
+    const int64_t c_hi = cut_centre(p.row_ptr, p.ctr, p.N, p.E, b + 1, G);
     const int64_t e_lo = p.row_ptr[c_lo], e_hi = p.row_ptr[c_hi];
     const TAct* __restrict__ gA = IMPLICIT ? (const TAct*)p.w0 : (const TAct*)p.Vin;
     const int rowA_el = IMPLICIT ? N_IR * U : D_IN * U;  // elements per edge of the A block
@@ -607,10 +619,10 @@ int launch_shape(const StreamParams& p, cudaStream_t st) {
 
 // returns 0 if launched, -1 if (dtype, shape, alignment) has no streaming instantiation
 int ab2_tp_stream(int mode, int dtype, int64_t N, int64_t E, int U, int D, int d_in, int d_out, int nnz, const int32_t* tab,
-                  const void* cgw, const int32_t* row_ptr, const void* gamma, const void* Vin, int implicit_v0, const void* Y,
+                  const void* cgw, const int32_t* row_ptr, const int32_t* ctr, const void* gamma, const void* Vin, int implicit_v0, const void* Y,
                   const void* w0, int64_t w0_ld, void* Vout, const void* gVout, void* gVin, void* gw0, int64_t gw0_ld, void* gY,
                   void* ggamma, cudaStream_t st) {
-    if (!g_ab2_opt_tp_stream || dtype == AB2_F64 || nnz > MAX_NNZ || nnz <= 0 || E <= 0 || N <= 0) return -1;
+    if (!g_ab2_opt_tp_stream || !ctr || dtype == AB2_F64 || nnz > MAX_NNZ || nnz <= 0 || E <= 0 || N <= 0) return -1;
     if (d_in != d_out || !(d_in == 4 || d_in == 9) || (implicit_v0 && D != d_in)) return -1;
     const int esz = dtype == AB2_F32 ? 4 : 2;
     // bulk copies move whole rows: 16-byte multiples, 16-byte aligned bases, dense rows
@@ -620,7 +632,7 @@ int ab2_tp_stream(int mode, int dtype, int64_t N, int64_t E, int U, int D, int d
     auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
     if (!al16(gamma) || (implicit_v0 ? !al16(w0) : !al16(Vin)) || (mode == 1 && !al16(gVout))) return -1;
     StreamParams p;
-    p.N = N; p.E = E; p.U = U; p.D = D; p.nnz = nnz; p.tab = tab; p.cgw = cgw; p.row_ptr = row_ptr; p.gamma = gamma;
+    p.N = N; p.E = E; p.U = U; p.D = D; p.nnz = nnz; p.tab = tab; p.cgw = cgw; p.row_ptr = row_ptr; p.ctr = ctr; p.gamma = gamma;
     p.Vin = Vin; p.Y = Y; p.w0 = w0; p.Vout = Vout; p.gVout = gVout; p.gVin = gVin; p.gw0 = gw0; p.gY = gY; p.ggamma = ggamma;
 #define AB2_STREAM_CASE(TA, DI)                                                                                        \
     if (d_in == DI) {                                                                                                   \
