@@ -16,6 +16,7 @@ void ab2_set_error(const char* fmt, ...) {
 
 int g_ab2_opt_tp_fast = 1;
 int g_ab2_opt_linear_tc = 1;
+int g_ab2_opt_linear_tma = 1;  // TMA-producer variant of the tensor-core linear where eligible
 int g_ab2_opt_tc_debug = 0;
 int g_ab2_opt_env_split = 0;  // 0: auto (env.cu)
 extern int g_ab2_opt_tp_variant;
@@ -26,6 +27,7 @@ extern "C" int ab2_set_option(const char* key, int value) {
     if (!key) return 1;
     if (!strcmp(key, "tp_fast")) { g_ab2_opt_tp_fast = value; return 0; }
     if (!strcmp(key, "linear_tc")) { g_ab2_opt_linear_tc = value; return 0; }
+    if (!strcmp(key, "linear_tma")) { g_ab2_opt_linear_tma = value; return 0; }
     if (!strcmp(key, "tc_debug")) { g_ab2_opt_tc_debug = value; return 0; }
     if (!strcmp(key, "env_split")) { g_ab2_opt_env_split = value; return 0; }
     if (!strcmp(key, "tp_variant")) { g_ab2_opt_tp_variant = value; return 0; }

@@ -167,10 +167,16 @@ extern "C" int ab2_linear(int dtype, int64_t M, int K, int N, int n_a, const voi
     AB2_CHECK_ARG(ks == K, "A segment widths must sum to K");
     AB2_CHECK_ARG(ns == N, "output segment widths must sum to N");
     cudaStream_t st = (cudaStream_t)stream;
-    if (Wpacked && ab2_linear_tc_try(dtype, M, K, N, n_a, a_ptr, a_ld, a_width, a_aux, a_aux_ld, act, Wpacked, n_o, o_ptr, o_ld, o_width, o_accum, epi,
-                                     aux, aux_ld, st) == 0) {
+    const int tc = Wpacked ? ab2_linear_tc_try(dtype, M, K, N, n_a, a_ptr, a_ld, a_width, a_aux, a_aux_ld, act, Wpacked, n_o, o_ptr, o_ld, o_width,
+                                               o_accum, epi, aux, aux_ld, st)
+                           : -1;
+    if (tc == 0) {
         AB2_CUDA_LAUNCH_CHECK();
         return 0;
+    }
+    if (tc > 0) {  // some column slices were launched, a later one could not be: the output is incomplete
+        ab2_set_error("%s:%d: tensor-core linear: a column slice failed to launch (K=%d, N=%d)", __FILE__, __LINE__, K, N);
+        return 2;
     }
     dim3 grid(ab2_blocks(M, 64), (unsigned)((N + 63) / 64));
     AB2_DISPATCH_DTYPE(dtype, linear_kernel<TAct, TAcc><<<grid, 256, 0, st>>>(p));

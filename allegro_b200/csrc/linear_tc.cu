@@ -21,9 +21,12 @@
 //
 // W (all of it: <= 128 KB as bf16 hi+lo) is staged once per CTA from a pre-packed image
 // (ab2_linear_pack) and stays resident in shared memory.
+#include <cuda.h>
+
 #include "common.cuh"
 
 extern int g_ab2_opt_linear_tc;
+extern int g_ab2_opt_linear_tma;
 extern int g_ab2_opt_tc_debug;  // bit0: no epilogue global stores, bit1: no producer global loads, bit2: no MMA issue
 
 namespace {
@@ -61,7 +64,8 @@ struct TcParams {
     int n_a;
     TcSeg a[AB2_MAX_SEG];
     int act;
-    const void* Wpacked;  // [hi image | lo image], each Npad*K bf16 in canonical layout
+    const void* Wpacked;  // hi image of this column slice: Npad*K bf16 in canonical layout
+    const void* Wlo;      // lo image of the same slice (fp32 storage only)
     int n_o;
     TcSeg o[AB2_MAX_SEG];
     int epi;
@@ -267,9 +271,289 @@ __device__ __forceinline__ void load8(const TcParams& p, int64_t m, int k, float
     for (int t = 0; t < 8; ++t) v[t] = 0.f;
 }
 
+
+// output chunk table entry for columns [c0, c0 + 32)
+template <typename TSrc>
+__device__ __forceinline__ ChunkInfo tc_chunk_info(const TcParams& p, int c0) {
+    ChunkInfo info{nullptr, nullptr, 0, 0, 0};
+    if (sizeof(TSrc) == 4 && c0 + 32 <= p.N && !(p.debug & 64)) {
+        int lo = 0, seg = -1, seg_lo = 0;
+#pragma unroll
+        for (int s2 = 0; s2 < AB2_MAX_SEG; ++s2) {
+            if (s2 < p.n_o) {
+                if (c0 >= lo && c0 + 32 <= lo + p.o[s2].width) { seg = s2; seg_lo = lo; }
+                lo += p.o[s2].width;
+            }
+        }
+        if (seg >= 0) {
+            float* base = (float*)p.o[seg].ptr + (c0 - seg_lo);
+            bool ok = !(reinterpret_cast<uintptr_t>(base) & 15) && !((p.o[seg].ld * 4) & 15);
+            if (p.epi == AB2_EPI_MUL_DSILU &&
+                ((reinterpret_cast<uintptr_t>((const float*)p.aux + c0) & 15) || ((p.aux_ld * 4) & 15))) ok = false;
+            info.optr = base;
+            info.aptr = (const float*)p.aux + c0;
+            info.ld = p.o[seg].ld;
+            info.accum = p.o[seg].accum;
+            info.ok = ok ? 1 : 0;
+        }
+    }
+    return info;
+}
+
+// Shared-memory / barrier context of one CTA, common to the cp.async-producer kernel and the TMA-producer kernel.
+struct TcCtx {
+    uint8_t* sW;
+    uint8_t* sA;
+    float* sEpi;
+    float* sPf;
+    ChunkInfo* sChunk;
+    uint32_t bar0;       // full[NSTAGE], empty[NSTAGE], tmem_full[2], tmem_empty[2]
+    uint32_t tmem_base;
+    int nkb, stage_bytes, w_half;
+    uint32_t idesc;
+    __device__ __forceinline__ uint32_t full_bar(int s) const { return bar0 + 8u * s; }
+    __device__ __forceinline__ uint32_t empty_bar(int s) const { return bar0 + 8u * (NSTAGE + s); }
+    __device__ __forceinline__ uint32_t tfull_bar(int a) const { return bar0 + 8u * (2 * NSTAGE + a); }
+    __device__ __forceinline__ uint32_t tempty_bar(int a) const { return bar0 + 8u * (2 * NSTAGE + 2 + a); }
+};
+
+// =============================== MMA issuer (one warp, one elected lane) ===============================
+template <bool SPLIT>
+__device__ __forceinline__ void tc_mma_role(const TcParams& p, const TcCtx& c, int lane) {
+    const int nkb = c.nkb, stage_bytes = c.stage_bytes, w_half = c.w_half;
+    const uint32_t tmem_base = c.tmem_base, idesc = c.idesc;
+    uint8_t* sW = c.sW;
+    uint8_t* sA = c.sA;
+    auto full_bar = [&](int s) { return c.full_bar(s); };
+    auto empty_bar = [&](int s) { return c.empty_bar(s); };
+    auto tfull_bar = [&](int a) { return c.tfull_bar(a); };
+    auto tempty_bar = [&](int a) { return c.tempty_bar(a); };
+    int stage = 0;
+    uint32_t phase = 0;
+    int64_t it = 0;
+    const uint32_t sW_u = smem_u32(sW);
+    const uint32_t w_sbo = (uint32_t)(p.K / 8) * 128;  // bytes between 8-column (n) groups of W
+    for (int64_t tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+        const int a = (int)(it & 1);
+        const uint32_t aphase = (uint32_t)((it >> 1) & 1);
+        mbar_wait(tempty_bar(a), aphase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(a * 256);
+        for (int kb = 0; kb < nkb; ++kb) {
+            mbar_wait(full_bar(stage), phase);
+            tc_fence_after();
+            if (lane == 0) {
+                const uint32_t a_hi = smem_u32(sA + stage * stage_bytes);
+                const int ksteps = min(2, (p.K - kb * KC) / 16);
+                for (int ks = 0; ks < ((p.debug & 4) ? 0 : ksteps); ++ks) {
+                    const uint64_t da_hi = make_desc(a_hi + ks * 256, 128, (KC / 8) * 128);
+                    const uint32_t wk = sW_u + (uint32_t)(kb * (KC / 8) + ks * 2) * 128;
+                    const uint64_t db_hi = make_desc(wk, 128, w_sbo);
+                    umma_bf16(d_tmem, da_hi, db_hi, idesc, (kb | ks) ? 1u : 0u);
+                    if constexpr (SPLIT) {
+                        const uint64_t da_lo = make_desc(a_hi + STAGE_HALF + ks * 256, 128, (KC / 8) * 128);
+                        const uint64_t db_lo = make_desc(wk + w_half, 128, w_sbo);
+                        umma_bf16(d_tmem, da_lo, db_hi, idesc, 1u);
+                        umma_bf16(d_tmem, da_hi, db_lo, idesc, 1u);
+                    }
+                }
+                umma_commit(empty_bar(stage));                  // ring slot free once these MMAs retire
+                if (kb == nkb - 1) umma_commit(tfull_bar(a));   // accumulator complete
+            }
+            __syncwarp();
+            if (++stage == p.nstage) { stage = 0; phase ^= 1; }
+        }
+    }
+}
+
+// =============================== epilogue (4 warps, one TMEM lane quadrant each) ===============================
+template <typename TSrc, int PF>
+__device__ __forceinline__ void tc_epilogue_role(const TcParams& p, const TcCtx& c, int warp, int lane) {
+    const uint32_t tmem_base = c.tmem_base;
+    float* sEpi = c.sEpi;
+    float* sPf = c.sPf;
+    ChunkInfo* sChunk = c.sChunk;
+    auto tfull_bar = [&](int a) { return c.tfull_bar(a); };
+    auto tempty_bar = [&](int a) { return c.tempty_bar(a); };
+    const int q = warp & 3;  // TMEM lane quadrant this warp may access
+    int64_t it = 0;
+    for (int64_t tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+        const int a = (int)(it & 1);
+        const uint32_t aphase = (uint32_t)((it >> 1) & 1);
+        // ---- epilogue-side global reads (silu' aux or old values to accumulate) are prefetched with
+        //      cp.async into per-warp buffers, two 32-column chunks ahead, starting BEFORE the
+        //      accumulator is ready ----
+        const int64_t m_base = tile * BM + q * 32;
+        const int64_t left64 = p.M - m_base;  // <= 0: this warp's 32 rows lie beyond M
+        const int rows_left = left64 >= 32 ? 32 : (left64 > 0 ? (int)left64 : 0);
+        const bool full = rows_left == 32;
+        const int rsub = lane >> 3, c4 = lane & 7;
+        // row handled in slot itr: itr*4 + rsub; loads of a partial tile read a clamped (valid) row
+        auto row_of = [&](int itr) { const int r = itr * 4 + rsub; return full ? r : (r < rows_left ? r : rows_left - 1); };
+        float* pfw = sPf + q * 2 * 32 * EPI_LD;
+        auto prefetch = [&](int c0) {
+            if constexpr (PF == 0) return;
+            if (c0 < p.Npad && rows_left > 0) {
+                const ChunkInfo ci = sChunk[c0 >> 5];
+                if (ci.ok && (PF == 1 || ci.accum)) {
+                    const int64_t gld = (PF == 1) ? p.aux_ld : ci.ld;
+                    const float* tb = ((PF == 1) ? ci.aptr : (const float*)ci.optr) + m_base * gld + c4 * 4;
+                    const uint32_t gl = (uint32_t)gld;
+                    float* dstb = pfw + ((c0 >> 5) & 1) * 32 * EPI_LD + c4 * 4;
+#pragma unroll
+                    for (int itr = 0; itr < 8; ++itr)
+                        cp_async16(smem_u32(dstb + (itr * 4 + rsub) * EPI_LD), tb + (uint32_t)row_of(itr) * gl, 16u);
+                }
+            }
+            cp_async_commit();
+        };
+        prefetch(0);
+        prefetch(32);
+        mbar_wait(tfull_bar(a), aphase);
+        tc_fence_after();
+        const int64_t m = tile * BM + q * 32 + lane;
+        const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * 256);
+        // two 16-column TMEM loads in flight, then the epilogue of both
+        auto process = [&](int c0, const uint32_t (&r)[16]) {
+            if (m >= p.M) return;
+            float v[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
+            if (p.epi == AB2_EPI_MUL_DSILU) {
+                const TSrc* ax = (const TSrc*)p.aux + m * p.aux_ld + c0;
+                if (sizeof(TSrc) == 4 && c0 + 16 <= p.N && ((reinterpret_cast<uintptr_t>(ax) & 15) == 0)) {
+                    const float4* a4 = reinterpret_cast<const float4*>(ax);
+#pragma unroll
+                    for (int t = 0; t < 4; ++t) {
+                        const float4 x = __ldg(a4 + t);
+                        v[4 * t] *= dsilu_f(x.x); v[4 * t + 1] *= dsilu_f(x.y); v[4 * t + 2] *= dsilu_f(x.z); v[4 * t + 3] *= dsilu_f(x.w);
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j)
+                        if (c0 + j < p.N) v[j] *= dsilu_f(to_acc<float>(ax[j]));
+                }
+            }
+            // scatter the 16 columns into the output segments
+            int seg_lo = 0;
+#pragma unroll
+            for (int s = 0; s < AB2_MAX_SEG; ++s) {
+                if (s < p.n_o) {
+                    const int seg_hi = seg_lo + p.o[s].width;
+                    const int lo = max(seg_lo, c0), hi = min(seg_hi, min(c0 + 16, p.N));
+                    if (lo < hi) {
+                        TSrc* dst = (TSrc*)p.o[s].ptr + m * p.o[s].ld + (lo - seg_lo);
+                        const bool vec = (sizeof(TSrc) == 4) && (hi - lo == 16) && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0);
+                        if (vec) {
+                            float4* d4 = reinterpret_cast<float4*>(dst);
+#pragma unroll
+                            for (int t = 0; t < 4; ++t) {
+                                float4 o4 = make_float4(v[4 * t], v[4 * t + 1], v[4 * t + 2], v[4 * t + 3]);
+                                if (p.o[s].accum) {
+                                    const float4 old = d4[t];
+                                    o4.x += old.x; o4.y += old.y; o4.z += old.z; o4.w += old.w;
+                                }
+                                d4[t] = o4;
+                            }
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) {
+                                const int n = c0 + j;
+                                if (n >= lo && n < hi) {
+                                    float x = v[j];
+                                    if (p.o[s].accum) x += to_acc<float>(dst[n - lo]);
+                                    dst[n - lo] = from_acc<TSrc>(x);
+                                }
+                            }
+                        }
+                    }
+                    seg_lo = seg_hi;
+                }
+            }
+        };
+        float* stg = sEpi + q * 32 * EPI_LD;
+        for (int c0 = 0; c0 < p.Npad; c0 += 32) {
+            uint32_t r0[16], r1[16];
+            const bool two = c0 + 16 < p.Npad;
+            tmem_ld16_nowait(t_row + c0, r0);
+            if (two) tmem_ld16_nowait(t_row + c0 + 16, r1);
+            tmem_ld_wait();
+            const ChunkInfo ci = sChunk[c0 >> 5];
+            if constexpr (PF != 0) cp_async_wait<1>();  // this chunk's prefetch group (if any) has landed
+            if ((p.debug & 1) || rows_left == 0) {
+            } else if (ci.ok) {
+                // coalesced path (ok implies two): stage my row (lane): 32 floats -> shared, then every
+                // global access covers 4 rows x 128 B
+                float4* srow = reinterpret_cast<float4*>(stg + lane * EPI_LD);
+#pragma unroll
+                for (int t = 0; t < 4; ++t) {
+                    srow[t] = make_float4(__uint_as_float(r0[4 * t]), __uint_as_float(r0[4 * t + 1]), __uint_as_float(r0[4 * t + 2]), __uint_as_float(r0[4 * t + 3]));
+                    srow[4 + t] = make_float4(__uint_as_float(r1[4 * t]), __uint_as_float(r1[4 * t + 1]), __uint_as_float(r1[4 * t + 2]), __uint_as_float(r1[4 * t + 3]));
+                }
+                __syncwarp();
+                // 1) all shared-memory reads, 2) (uniform) epilogue variants with all global loads
+                //    issued before use, 3) stores: tile base pointer + 32-bit row offsets.
+                float4 x[8];
+#pragma unroll
+                for (int itr = 0; itr < 8; ++itr) x[itr] = *reinterpret_cast<const float4*>(stg + (itr * 4 + rsub) * EPI_LD + c4 * 4);
+                float* tb = ci.optr + m_base * ci.ld + c4 * 4;
+                const uint32_t ol = (uint32_t)ci.ld;
+                uint32_t off[8];
+#pragma unroll
+                for (int itr = 0; itr < 8; ++itr) off[itr] = (uint32_t)row_of(itr) * ol;
+                const float* pfb = pfw + ((c0 >> 5) & 1) * 32 * EPI_LD;
+                if (p.epi == AB2_EPI_MUL_DSILU) {
+                    float4 ax[8];
+                    const float* ab = ci.aptr + m_base * p.aux_ld + c4 * 4;
+                    const uint32_t al = (uint32_t)p.aux_ld;
+#pragma unroll
+                    for (int itr = 0; itr < 8; ++itr)
+                        ax[itr] = (PF == 1) ? *reinterpret_cast<const float4*>(pfb + (itr * 4 + rsub) * EPI_LD + c4 * 4)
+                                                   : ldg128_nc(ab + (uint32_t)row_of(itr) * al);
+#pragma unroll
+                    for (int itr = 0; itr < 8; ++itr) {
+                        x[itr].x *= dsilu_fast(ax[itr].x); x[itr].y *= dsilu_fast(ax[itr].y);
+                        x[itr].z *= dsilu_fast(ax[itr].z); x[itr].w *= dsilu_fast(ax[itr].w);
+                    }
+                }
+                if (ci.accum) {
+                    float4 old[8];
+#pragma unroll
+                    for (int itr = 0; itr < 8; ++itr)
+                        old[itr] = (PF == 2) ? *reinterpret_cast<const float4*>(pfb + (itr * 4 + rsub) * EPI_LD + c4 * 4)
+                                                    : ldg128(tb + off[itr]);
+#pragma unroll
+                    for (int itr = 0; itr < 8; ++itr) {
+                        x[itr].x += old[itr].x; x[itr].y += old[itr].y; x[itr].z += old[itr].z; x[itr].w += old[itr].w;
+                    }
+                }
+                if (full) {
+#pragma unroll
+                    for (int itr = 0; itr < 8; ++itr) stg128(tb + off[itr], x[itr]);
+                } else {
+#pragma unroll
+                    for (int itr = 0; itr < 8; ++itr)
+                        if (itr * 4 + rsub < rows_left) stg128(tb + off[itr], x[itr]);
+                }
+                __syncwarp();
+            } else {
+                process(c0, r0);
+                if (two) process(c0 + 16, r1);
+            }
+            if constexpr (PF != 0) {
+                __syncwarp();
+                prefetch(c0 + 64);  // refill the buffer just consumed (always commits a group)
+            }
+        }
+        tc_fence_before();
+        if (p.debug & 8) mbar_arrive(tempty_bar(a));
+        else mbar_arrive_relaxed(tempty_bar(a));
+    }
+}
+
 template <typename TSrc, bool SPLIT, int PF>
 __global__ void __launch_bounds__(NTHREADS, 1) linear_tc_kernel(const TcParams p) {
-    extern __shared__ __align__(128) uint8_t smem[];
+    extern __shared__ __align__(1024) uint8_t smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int w_half = p.Npad * p.K * 2;                     // bytes of one W image
     const int w_bytes = SPLIT ? 2 * w_half : w_half;
@@ -330,37 +614,18 @@ __global__ void __launch_bounds__(NTHREADS, 1) linear_tc_kernel(const TcParams p
         sKmap[e] = ent;
         sKaux[e] = aent;
     } else if (threadIdx.x < MAX_K / 8 + MAX_CHUNK) {
-        // output chunk table
-        const int c0 = (threadIdx.x - MAX_K / 8) * 32;
-        ChunkInfo info{nullptr, nullptr, 0, 0, 0};
-        if (sizeof(TSrc) == 4 && c0 + 32 <= p.N && !(p.debug & 64)) {
-            int lo = 0, seg = -1, seg_lo = 0;
-#pragma unroll
-            for (int s2 = 0; s2 < AB2_MAX_SEG; ++s2) {
-                if (s2 < p.n_o) {
-                    if (c0 >= lo && c0 + 32 <= lo + p.o[s2].width) { seg = s2; seg_lo = lo; }
-                    lo += p.o[s2].width;
-                }
-            }
-            if (seg >= 0) {
-                float* base = (float*)p.o[seg].ptr + (c0 - seg_lo);
-                bool ok = !(reinterpret_cast<uintptr_t>(base) & 15) && !((p.o[seg].ld * 4) & 15);
-                if (p.epi == AB2_EPI_MUL_DSILU &&
-                    ((reinterpret_cast<uintptr_t>((const float*)p.aux + c0) & 15) || ((p.aux_ld * 4) & 15))) ok = false;
-                info.optr = base;
-                info.aptr = (const float*)p.aux + c0;
-                info.ld = p.o[seg].ld;
-                info.accum = p.o[seg].accum;
-                info.ok = ok ? 1 : 0;
-            }
-        }
-        sChunk[threadIdx.x - MAX_K / 8] = info;
+        sChunk[threadIdx.x - MAX_K / 8] = tc_chunk_info<TSrc>(p, (threadIdx.x - MAX_K / 8) * 32);
     }
-    // stage W (pre-packed canonical image) with plain 16-byte copies
+    // stage W (pre-packed canonical images of this column slice) with plain 16-byte copies
     {
         const uint4* src = reinterpret_cast<const uint4*>(p.Wpacked);
         uint4* dst = reinterpret_cast<uint4*>(sW);
-        for (int e = threadIdx.x; e < w_bytes / 16; e += NTHREADS) dst[e] = __ldg(src + e);
+        for (int e = threadIdx.x; e < w_half / 16; e += NTHREADS) dst[e] = __ldg(src + e);
+        if constexpr (SPLIT) {
+            const uint4* srcl = reinterpret_cast<const uint4*>(p.Wlo);
+            uint4* dstl = reinterpret_cast<uint4*>(sW + w_half);
+            for (int e = threadIdx.x; e < w_half / 16; e += NTHREADS) dstl[e] = __ldg(srcl + e);
+        }
     }
     fence_proxy_async();  // W was written through the generic proxy, tcgen05.mma reads via the async proxy
     tc_fence_before();
@@ -370,6 +635,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) linear_tc_kernel(const TcParams p
 
     const int nkb = (p.K + KC - 1) / KC;
     const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.Npad >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+    TcCtx ctx;
+    ctx.sW = sW; ctx.sA = sA; ctx.sEpi = sEpi; ctx.sPf = sPf; ctx.sChunk = sChunk; ctx.bar0 = bar0; ctx.tmem_base = tmem_base;
+    ctx.nkb = nkb; ctx.stage_bytes = stage_bytes; ctx.w_half = w_half; ctx.idesc = idesc;
 
     if (warp < NPROD) {
         // =============================== producers ===============================
@@ -506,224 +774,225 @@ __global__ void __launch_bounds__(NTHREADS, 1) linear_tc_kernel(const TcParams p
         }
         cp_async_wait<0>();
     } else if (warp == NPROD) {
-        // =============================== MMA issuer ===============================
-        int stage = 0;
-        uint32_t phase = 0;
-        int64_t it = 0;
-        const uint32_t sW_u = smem_u32(sW);
-        const uint32_t w_sbo = (uint32_t)(p.K / 8) * 128;  // bytes between 8-column (n) groups of W
-        for (int64_t tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
-            const int a = (int)(it & 1);
-            const uint32_t aphase = (uint32_t)((it >> 1) & 1);
-            mbar_wait(tempty_bar(a), aphase ^ 1);
-            tc_fence_after();
-            const uint32_t d_tmem = tmem_base + (uint32_t)(a * 256);
-            for (int kb = 0; kb < nkb; ++kb) {
-                mbar_wait(full_bar(stage), phase);
-                tc_fence_after();
-                if (lane == 0) {
-                    const uint32_t a_hi = smem_u32(sA + stage * stage_bytes);
-                    const int ksteps = min(2, (p.K - kb * KC) / 16);
-                    for (int ks = 0; ks < ((p.debug & 4) ? 0 : ksteps); ++ks) {
-                        const uint64_t da_hi = make_desc(a_hi + ks * 256, 128, (KC / 8) * 128);
-                        const uint32_t wk = sW_u + (uint32_t)(kb * (KC / 8) + ks * 2) * 128;
-                        const uint64_t db_hi = make_desc(wk, 128, w_sbo);
-                        umma_bf16(d_tmem, da_hi, db_hi, idesc, (kb | ks) ? 1u : 0u);
-                        if constexpr (SPLIT) {
-                            const uint64_t da_lo = make_desc(a_hi + STAGE_HALF + ks * 256, 128, (KC / 8) * 128);
-                            const uint64_t db_lo = make_desc(wk + w_half, 128, w_sbo);
-                            umma_bf16(d_tmem, da_lo, db_hi, idesc, 1u);
-                            umma_bf16(d_tmem, da_hi, db_lo, idesc, 1u);
-                        }
-                    }
-                    umma_commit(empty_bar(stage));                  // ring slot free once these MMAs retire
-                    if (kb == nkb - 1) umma_commit(tfull_bar(a));   // accumulator complete
-                }
-                __syncwarp();
-                if (++stage == p.nstage) { stage = 0; phase ^= 1; }
-            }
-        }
+        tc_mma_role<SPLIT>(p, ctx, lane);
     } else {
-        // =============================== epilogue ===============================
-        const int q = warp & 3;  // TMEM lane quadrant this warp may access
-        int64_t it = 0;
-        for (int64_t tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
-            const int a = (int)(it & 1);
-            const uint32_t aphase = (uint32_t)((it >> 1) & 1);
-            // ---- epilogue-side global reads (silu' aux or old values to accumulate) are prefetched with
-            //      cp.async into per-warp buffers, two 32-column chunks ahead, starting BEFORE the
-            //      accumulator is ready ----
-            const int64_t m_base = tile * BM + q * 32;
-            const int64_t left64 = p.M - m_base;  // <= 0: this warp's 32 rows lie beyond M
-            const int rows_left = left64 >= 32 ? 32 : (left64 > 0 ? (int)left64 : 0);
-            const bool full = rows_left == 32;
-            const int rsub = lane >> 3, c4 = lane & 7;
-            // row handled in slot itr: itr*4 + rsub; loads of a partial tile read a clamped (valid) row
-            auto row_of = [&](int itr) { const int r = itr * 4 + rsub; return full ? r : (r < rows_left ? r : rows_left - 1); };
-            float* pfw = sPf + q * 2 * 32 * EPI_LD;
-            auto prefetch = [&](int c0) {
-                if constexpr (PF == 0) return;
-                if (c0 < p.Npad && rows_left > 0) {
-                    const ChunkInfo ci = sChunk[c0 >> 5];
-                    if (ci.ok && (PF == 1 || ci.accum)) {
-                        const int64_t gld = (PF == 1) ? p.aux_ld : ci.ld;
-                        const float* tb = ((PF == 1) ? ci.aptr : (const float*)ci.optr) + m_base * gld + c4 * 4;
-                        const uint32_t gl = (uint32_t)gld;
-                        float* dstb = pfw + ((c0 >> 5) & 1) * 32 * EPI_LD + c4 * 4;
-#pragma unroll
-                        for (int itr = 0; itr < 8; ++itr)
-                            cp_async16(smem_u32(dstb + (itr * 4 + rsub) * EPI_LD), tb + (uint32_t)row_of(itr) * gl, 16u);
-                    }
-                }
-                cp_async_commit();
-            };
-            prefetch(0);
-            prefetch(32);
-            mbar_wait(tfull_bar(a), aphase);
-            tc_fence_after();
-            const int64_t m = tile * BM + q * 32 + lane;
-            const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * 256);
-            // two 16-column TMEM loads in flight, then the epilogue of both
-            auto process = [&](int c0, const uint32_t (&r)[16]) {
-                if (m >= p.M) return;
-                float v[16];
-#pragma unroll
-                for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
-                if (p.epi == AB2_EPI_MUL_DSILU) {
-                    const TSrc* ax = (const TSrc*)p.aux + m * p.aux_ld + c0;
-                    if (sizeof(TSrc) == 4 && c0 + 16 <= p.N && ((reinterpret_cast<uintptr_t>(ax) & 15) == 0)) {
-                        const float4* a4 = reinterpret_cast<const float4*>(ax);
-#pragma unroll
-                        for (int t = 0; t < 4; ++t) {
-                            const float4 x = __ldg(a4 + t);
-                            v[4 * t] *= dsilu_f(x.x); v[4 * t + 1] *= dsilu_f(x.y); v[4 * t + 2] *= dsilu_f(x.z); v[4 * t + 3] *= dsilu_f(x.w);
-                        }
-                    } else {
-#pragma unroll
-                        for (int j = 0; j < 16; ++j)
-                            if (c0 + j < p.N) v[j] *= dsilu_f(to_acc<float>(ax[j]));
-                    }
-                }
-                // scatter the 16 columns into the output segments
-                int seg_lo = 0;
-#pragma unroll
-                for (int s = 0; s < AB2_MAX_SEG; ++s) {
-                    if (s < p.n_o) {
-                        const int seg_hi = seg_lo + p.o[s].width;
-                        const int lo = max(seg_lo, c0), hi = min(seg_hi, min(c0 + 16, p.N));
-                        if (lo < hi) {
-                            TSrc* dst = (TSrc*)p.o[s].ptr + m * p.o[s].ld + (lo - seg_lo);
-                            const bool vec = (sizeof(TSrc) == 4) && (hi - lo == 16) && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0);
-                            if (vec) {
-                                float4* d4 = reinterpret_cast<float4*>(dst);
-#pragma unroll
-                                for (int t = 0; t < 4; ++t) {
-                                    float4 o4 = make_float4(v[4 * t], v[4 * t + 1], v[4 * t + 2], v[4 * t + 3]);
-                                    if (p.o[s].accum) {
-                                        const float4 old = d4[t];
-                                        o4.x += old.x; o4.y += old.y; o4.z += old.z; o4.w += old.w;
-                                    }
-                                    d4[t] = o4;
-                                }
-                            } else {
-#pragma unroll
-                                for (int j = 0; j < 16; ++j) {
-                                    const int n = c0 + j;
-                                    if (n >= lo && n < hi) {
-                                        float x = v[j];
-                                        if (p.o[s].accum) x += to_acc<float>(dst[n - lo]);
-                                        dst[n - lo] = from_acc<TSrc>(x);
-                                    }
-                                }
-                            }
-                        }
-                        seg_lo = seg_hi;
-                    }
-                }
-            };
-            float* stg = sEpi + q * 32 * EPI_LD;
-            for (int c0 = 0; c0 < p.Npad; c0 += 32) {
-                uint32_t r0[16], r1[16];
-                const bool two = c0 + 16 < p.Npad;
-                tmem_ld16_nowait(t_row + c0, r0);
-                if (two) tmem_ld16_nowait(t_row + c0 + 16, r1);
-                tmem_ld_wait();
-                const ChunkInfo ci = sChunk[c0 >> 5];
-                if constexpr (PF != 0) cp_async_wait<1>();  // this chunk's prefetch group (if any) has landed
-                if ((p.debug & 1) || rows_left == 0) {
-                } else if (ci.ok) {
-                    // coalesced path (ok implies two): stage my row (lane): 32 floats -> shared, then every
-                    // global access covers 4 rows x 128 B
-                    float4* srow = reinterpret_cast<float4*>(stg + lane * EPI_LD);
-#pragma unroll
-                    for (int t = 0; t < 4; ++t) {
-                        srow[t] = make_float4(__uint_as_float(r0[4 * t]), __uint_as_float(r0[4 * t + 1]), __uint_as_float(r0[4 * t + 2]), __uint_as_float(r0[4 * t + 3]));
-                        srow[4 + t] = make_float4(__uint_as_float(r1[4 * t]), __uint_as_float(r1[4 * t + 1]), __uint_as_float(r1[4 * t + 2]), __uint_as_float(r1[4 * t + 3]));
-                    }
-                    __syncwarp();
-                    // 1) all shared-memory reads, 2) (uniform) epilogue variants with all global loads
-                    //    issued before use, 3) stores: tile base pointer + 32-bit row offsets.
-                    float4 x[8];
-#pragma unroll
-                    for (int itr = 0; itr < 8; ++itr) x[itr] = *reinterpret_cast<const float4*>(stg + (itr * 4 + rsub) * EPI_LD + c4 * 4);
-                    float* tb = ci.optr + m_base * ci.ld + c4 * 4;
-                    const uint32_t ol = (uint32_t)ci.ld;
-                    uint32_t off[8];
-#pragma unroll
-                    for (int itr = 0; itr < 8; ++itr) off[itr] = (uint32_t)row_of(itr) * ol;
-                    const float* pfb = pfw + ((c0 >> 5) & 1) * 32 * EPI_LD;
-                    if (p.epi == AB2_EPI_MUL_DSILU) {
-                        float4 ax[8];
-                        const float* ab = ci.aptr + m_base * p.aux_ld + c4 * 4;
-                        const uint32_t al = (uint32_t)p.aux_ld;
-#pragma unroll
-                        for (int itr = 0; itr < 8; ++itr)
-                            ax[itr] = (PF == 1) ? *reinterpret_cast<const float4*>(pfb + (itr * 4 + rsub) * EPI_LD + c4 * 4)
-                                                       : ldg128_nc(ab + (uint32_t)row_of(itr) * al);
-#pragma unroll
-                        for (int itr = 0; itr < 8; ++itr) {
-                            x[itr].x *= dsilu_fast(ax[itr].x); x[itr].y *= dsilu_fast(ax[itr].y);
-                            x[itr].z *= dsilu_fast(ax[itr].z); x[itr].w *= dsilu_fast(ax[itr].w);
-                        }
-                    }
-                    if (ci.accum) {
-                        float4 old[8];
-#pragma unroll
-                        for (int itr = 0; itr < 8; ++itr)
-                            old[itr] = (PF == 2) ? *reinterpret_cast<const float4*>(pfb + (itr * 4 + rsub) * EPI_LD + c4 * 4)
-                                                        : ldg128(tb + off[itr]);
-#pragma unroll
-                        for (int itr = 0; itr < 8; ++itr) {
-                            x[itr].x += old[itr].x; x[itr].y += old[itr].y; x[itr].z += old[itr].z; x[itr].w += old[itr].w;
-                        }
-                    }
-                    if (full) {
-#pragma unroll
-                        for (int itr = 0; itr < 8; ++itr) stg128(tb + off[itr], x[itr]);
-                    } else {
-#pragma unroll
-                        for (int itr = 0; itr < 8; ++itr)
-                            if (itr * 4 + rsub < rows_left) stg128(tb + off[itr], x[itr]);
-                    }
-                    __syncwarp();
-                } else {
-                    process(c0, r0);
-                    if (two) process(c0 + 16, r1);
-                }
-                if constexpr (PF != 0) {
-                    __syncwarp();
-                    prefetch(c0 + 64);  // refill the buffer just consumed (always commits a group)
-                }
-            }
-            tc_fence_before();
-            if (p.debug & 8) mbar_arrive(tempty_bar(a));
-            else mbar_arrive_relaxed(tempty_bar(a));
-        }
+        tc_epilogue_role<TSrc, PF>(p, ctx, warp, lane);
     }
     // ---- teardown ----
     tc_fence_before();
     __syncthreads();
     if (warp == NPROD) tmem_dealloc(tmem_base, 512);
+}
+
+// =========================================================================================
+// TMA-producer variant (fp32 storage, every A segment a multiple of 32 columns wide).
+//
+//   warp 13      : one elected lane issues cp.async.bulk.tensor.2d loads (SASS UTMALDG) of 128-row x 32-column fp32
+//                  boxes (16 KB, SWIZZLE_128B) into a ring of NR raw slots, one box per k-chunk (+ one for the silu'
+//                  multiplier of that chunk), completing on an mbarrier; rows beyond M are zero-filled by the TMA unit.
+//   warps 0-7    : four converter GROUPS of two warps.  Group g owns the stages q = g (mod 4): it waits for the raw
+//                  slot, reads it conflict-free (the 128-byte swizzle puts the 8 rows of a core matrix in 8 different
+//                  bank groups), applies SiLU / silu'(aux), splits into bf16 hi + lo and writes the canonical K-major
+//                  stage.  Four stages are in conversion at once, so the fixed latency of one stage (mbarrier wait, LDS,
+//                  convert, STS, fence.proxy.async, arrive) no longer bounds the load rate: round 1's eight producer
+//                  warps all worked on the SAME stage and topped out at 2.3-3.2 TB/s on the load side.
+//   warp 8 / 9-12: MMA issuer and epilogue, unchanged (tc_mma_role / tc_epilogue_role).
+// =========================================================================================
+constexpr int TMA_NGRP = 4;
+constexpr int TMA_THREADS = NTHREADS + 32;
+constexpr int TMA_BOX_BYTES = BM * KC * 4;  // 16 KB
+
+struct alignas(64) TmaMaps {
+    CUtensorMap a[AB2_MAX_SEG];
+    CUtensorMap x[AB2_MAX_SEG];
+};
+
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int x, int y, uint32_t bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+                 "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(x), "r"(y)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+
+template <int PF>
+__global__ void __launch_bounds__(TMA_THREADS, 1) linear_tma_kernel(const TcParams p, const __grid_constant__ TmaMaps maps, int NR) {
+    using TSrc = float;
+    constexpr bool SPLIT = true;
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int w_half = p.Npad * p.K * 2;
+    const int w_bytes = 2 * w_half;
+    const int stage_bytes = 2 * STAGE_HALF;
+    const int raw_slot = TMA_BOX_BYTES * (p.has_aux ? 2 : 1);
+    // plan: raw ring (1024-byte aligned, swizzle atom) | W | canonical ring | epilogue staging | prefetch | tail
+    uint8_t* sRaw = smem + ((1024u - (smem_u32(smem) & 1023u)) & 1023u);
+    uint8_t* sW = sRaw + (size_t)NR * raw_slot;
+    uint8_t* sA = sW + ((w_bytes + 127) & ~127);
+    float* sEpi = reinterpret_cast<float*>(sA + p.nstage * stage_bytes);
+    float* sPf = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(sEpi) + EPI_BYTES);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(sEpi) + EPI_BYTES + (PF ? PF_BYTES : 0));
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NSTAGE + 4);
+    ChunkInfo* sChunk = reinterpret_cast<ChunkInfo*>(reinterpret_cast<uint8_t*>(bars) + TAIL_BARS + TAIL_SLOT);
+    // k-chunk table (one entry per 32 columns): segment index, column offset inside the segment, has-aux flag
+    int4* sKseg = reinterpret_cast<int4*>(reinterpret_cast<uint8_t*>(sChunk) + TAIL_CHUNK);
+    uint64_t* rbars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(sKseg) + (MAX_K / 32) * 16);  // raw_full[8], raw_empty[8]
+    const uint32_t bar0 = smem_u32(bars), rbar0 = smem_u32(rbars);
+    auto rfull_bar = [&](int s) { return rbar0 + 8u * s; };
+    auto rempty_bar = [&](int s) { return rbar0 + 8u * (8 + s); };
+    const int nkb = p.K / KC;
+
+    // ---- one-time setup ----
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < NSTAGE; ++s) {
+            mbar_init(bar0 + 8u * s, 64);                // canonical stage full: the two warps of a converter group
+            mbar_init(bar0 + 8u * (NSTAGE + s), 1);      // empty: tcgen05.commit
+        }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(bar0 + 8u * (2 * NSTAGE + a), 1);
+            mbar_init(bar0 + 8u * (2 * NSTAGE + 2 + a), 128);
+        }
+        for (int s = 0; s < 8; ++s) {
+            mbar_init(rfull_bar(s), 1);                  // expect_tx arrive of the TMA lane
+            mbar_init(rempty_bar(s), 64);
+        }
+        fence_barrier_init();
+    }
+    if (warp == NPROD) tmem_alloc(smem_u32(tmem_slot), 512);
+    if (threadIdx.x < MAX_K / 32) {
+        int kk = threadIdx.x * KC;
+        int4 ent = make_int4(-1, 0, 0, 0);
+#pragma unroll
+        for (int sgi = 0; sgi < AB2_MAX_SEG; ++sgi) {
+            if (sgi < p.n_a && ent.x < 0 && kk < p.K) {
+                if (kk < p.a[sgi].width) ent = make_int4(sgi, kk, p.a[sgi].aux ? 1 : 0, 0);
+                kk -= p.a[sgi].width;
+            }
+        }
+        sKseg[threadIdx.x] = ent;
+    } else if (threadIdx.x >= 64 && threadIdx.x < 64 + MAX_CHUNK) {
+        sChunk[threadIdx.x - 64] = tc_chunk_info<TSrc>(p, (threadIdx.x - 64) * 32);
+    }
+    {
+        const uint4* src = reinterpret_cast<const uint4*>(p.Wpacked);
+        uint4* dst = reinterpret_cast<uint4*>(sW);
+        for (int e = threadIdx.x; e < w_half / 16; e += TMA_THREADS) dst[e] = __ldg(src + e);
+        const uint4* srcl = reinterpret_cast<const uint4*>(p.Wlo);
+        uint4* dstl = reinterpret_cast<uint4*>(sW + w_half);
+        for (int e = threadIdx.x; e < w_half / 16; e += TMA_THREADS) dstl[e] = __ldg(srcl + e);
+    }
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    TcCtx ctx;
+    ctx.sW = sW; ctx.sA = sA; ctx.sEpi = sEpi; ctx.sPf = sPf; ctx.sChunk = sChunk; ctx.bar0 = bar0; ctx.tmem_base = *tmem_slot;
+    ctx.nkb = nkb; ctx.stage_bytes = stage_bytes; ctx.w_half = w_half;
+    ctx.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.Npad >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+    const int64_t my_tiles = (p.num_tiles > blockIdx.x) ? (p.num_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    const int64_t total = my_tiles * nkb;
+
+    if (warp == NPROD + 5) {
+        // =============================== TMA producer ===============================
+        if (lane == 0) {
+            for (int sgi = 0; sgi < p.n_a; ++sgi) {
+                asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&maps.a[sgi])) : "memory");
+                if (p.a[sgi].aux) asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&maps.x[sgi])) : "memory");
+            }
+            int rs = 0, kb = 0;
+            uint32_t rph = 0;
+            int64_t tile = blockIdx.x;
+            for (int64_t qs = 0; qs < total; ++qs) {
+                mbar_wait(rempty_bar(rs), rph ^ 1);
+                const int4 ent = sKseg[kb];
+                const uint32_t dst = smem_u32(sRaw + (size_t)rs * raw_slot);
+                const bool ax = p.has_aux && ent.z;
+                mbar_expect_tx(rfull_bar(rs), TMA_BOX_BYTES * (ax ? 2u : 1u));
+                if (!(p.debug & 2)) {
+                    tma_load_2d(dst, &maps.a[ent.x], ent.y, (int)(tile * BM), rfull_bar(rs));
+                    if (ax) tma_load_2d(dst + TMA_BOX_BYTES, &maps.x[ent.x], ent.y, (int)(tile * BM), rfull_bar(rs));
+                } else {
+                    asm volatile("mbarrier.complete_tx.shared::cta.b64 [%0], %1;" ::"r"(rfull_bar(rs)), "r"(TMA_BOX_BYTES * (ax ? 2u : 1u)) : "memory");
+                }
+                if (++rs == NR) { rs = 0; rph ^= 1; }
+                if (++kb == nkb) { kb = 0; tile += gridDim.x; }
+            }
+        }
+    } else if (warp < NPROD) {
+        // =============================== converters ===============================
+        const int grp = warp >> 1, sub = warp & 1;
+        const int r8 = lane & 7, kc = lane >> 3;
+        // raw slot / canonical stage of sequence number qs: plain counters (advance by TMA_NGRP per iteration)
+        int rs = grp % NR, cs = grp % p.nstage, kb = grp % nkb;
+        uint32_t rph = (uint32_t)((grp / NR) & 1), cph = (uint32_t)((grp / p.nstage) & 1);
+        for (int64_t qs = grp; qs < total; qs += TMA_NGRP) {
+            mbar_wait(rfull_bar(rs), rph);
+            const uint8_t* raw = sRaw + (size_t)rs * raw_slot;
+            const bool ax = p.has_aux && sKseg[kb].z;
+            float v[8][8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int row = (sub * 8 + i) * 8 + r8;
+                const uint8_t* rp = raw + row * 128;
+                const float4 x = *reinterpret_cast<const float4*>(rp + (((2 * kc) ^ r8) << 4));
+                const float4 y = *reinterpret_cast<const float4*>(rp + (((2 * kc + 1) ^ r8) << 4));
+                v[i][0] = x.x; v[i][1] = x.y; v[i][2] = x.z; v[i][3] = x.w; v[i][4] = y.x; v[i][5] = y.y; v[i][6] = y.z; v[i][7] = y.w;
+            }
+            if (ax) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int row = (sub * 8 + i) * 8 + r8;
+                    const uint8_t* rp = raw + TMA_BOX_BYTES + row * 128;
+                    const float4 x = *reinterpret_cast<const float4*>(rp + (((2 * kc) ^ r8) << 4));
+                    const float4 y = *reinterpret_cast<const float4*>(rp + (((2 * kc + 1) ^ r8) << 4));
+                    v[i][0] *= dsilu_fast(x.x); v[i][1] *= dsilu_fast(x.y); v[i][2] *= dsilu_fast(x.z); v[i][3] *= dsilu_fast(x.w);
+                    v[i][4] *= dsilu_fast(y.x); v[i][5] *= dsilu_fast(y.y); v[i][6] *= dsilu_fast(y.z); v[i][7] *= dsilu_fast(y.w);
+                }
+            }
+            __syncwarp();
+            mbar_arrive(rempty_bar(rs));  // raw slot drained (values are in registers)
+            mbar_wait(ctx.empty_bar(cs), cph ^ 1);
+            uint8_t* st_hi = sA + cs * stage_bytes;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                if (p.act == AB2_ACT_SILU) {
+#pragma unroll
+                    for (int t = 0; t < 8; ++t) v[i][t] = silu_fast(v[i][t]);
+                }
+                const int g = sub * 8 + i;
+                const uint32_t off = g * (KC / 8) * 128 + kc * 128 + r8 * 16;
+                uint32_t hi[4];
+                float lo[8];
+#pragma unroll
+                for (int t = 0; t < 4; ++t) {
+                    const __nv_bfloat16 h0 = __float2bfloat16_rn(v[i][2 * t]), h1 = __float2bfloat16_rn(v[i][2 * t + 1]);
+                    lo[2 * t] = v[i][2 * t] - __bfloat162float(h0);
+                    lo[2 * t + 1] = v[i][2 * t + 1] - __bfloat162float(h1);
+                    __nv_bfloat162 hh;
+                    hh.x = h0; hh.y = h1;
+                    hi[t] = *reinterpret_cast<uint32_t*>(&hh);
+                }
+                *reinterpret_cast<uint4*>(st_hi + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                *reinterpret_cast<uint4*>(st_hi + STAGE_HALF + off) =
+                    make_uint4(pack_bf16x2(lo[0], lo[1]), pack_bf16x2(lo[2], lo[3]), pack_bf16x2(lo[4], lo[5]), pack_bf16x2(lo[6], lo[7]));
+            }
+            fence_proxy_async();
+            mbar_arrive(ctx.full_bar(cs));
+            // advance the counters by TMA_NGRP stages
+            rs += TMA_NGRP; while (rs >= NR) { rs -= NR; rph ^= 1; }
+            cs += TMA_NGRP; while (cs >= p.nstage) { cs -= p.nstage; cph ^= 1; }
+            kb += TMA_NGRP; while (kb >= nkb) kb -= nkb;
+        }
+    } else if (warp == NPROD) {
+        tc_mma_role<SPLIT>(p, ctx, lane);
+    } else {
+        tc_epilogue_role<TSrc, PF>(p, ctx, warp, lane);
+    }
+    // ---- teardown ----
+    tc_fence_before();
+    __syncthreads();
+    if (warp == NPROD) tmem_dealloc(ctx.tmem_base, 512);
 }
 
 // W[K][N] (row-major TSrc) -> canonical K-major no-swizzle bf16 images (hi, lo), Npad rows:
@@ -746,13 +1015,17 @@ __global__ void pack_w_kernel(int K, int N, int Npad, const TSrc* __restrict__ W
 static int tc_npad(int N) { return (N + 15) / 16 * 16; }
 
 extern "C" int64_t ab2_linear_packed_bytes(int dtype, int K, int N) {
-    if (dtype == AB2_F64 || K % 16 != 0 || K <= 0 || N <= 0) return 0;
+    if (dtype == AB2_F64 || K % 16 != 0 || K <= 0 || K > MAX_K || N <= 0) return 0;
     const int Npad = tc_npad(N);
-    if (Npad > 256) return 0;
-    const int64_t bytes = (int64_t)Npad * K * 2 * 2;  // hi + lo images
-    const int64_t used = (dtype == AB2_F32) ? bytes : bytes / 2;
-    if (used > MAX_W_BYTES) return 0;
-    return bytes;
+    return (int64_t)Npad * K * 2 * 2;  // hi + lo images (any N: wide outputs run as column slices, see ab2_linear_tc_try)
+}
+
+// widest column slice (multiple of 32, <= 256) whose resident W image fits MAX_W_BYTES
+static int tc_slice_cap(int dtype, int K) {
+    const int per_col = K * 2 * (dtype == AB2_F32 ? 2 : 1);
+    int cap = (MAX_W_BYTES / per_col) / 32 * 32;
+    if (cap > 256) cap = 256;
+    return cap;
 }
 
 extern "C" int ab2_linear_pack(int dtype, int K, int N, const void* W, void* packed, void* stream) {
@@ -769,19 +1042,76 @@ extern "C" int ab2_linear_pack(int dtype, int K, int N, const void* W, void* pac
     return 0;
 }
 
-// returns 0 if launched, -1 if this call is not eligible (caller falls back to linear.cu)
-int ab2_linear_tc_try(int dtype, int64_t M, int K, int N, int n_a, const void* const* a_ptr, const int64_t* a_ld,
-                      const int32_t* a_width, const void* const* a_aux, const int64_t* a_aux_ld, int act, const void* Wpacked, int n_o, void* const* o_ptr, const int64_t* o_ld,
-                      const int32_t* o_width, const int32_t* o_accum, int epi, const void* aux, int64_t aux_ld, cudaStream_t st) {
-    if (!g_ab2_opt_linear_tc || !Wpacked || dtype == AB2_F64) return -1;
-    if (ab2_linear_packed_bytes(dtype, K, N) == 0 || K > MAX_K) return -1;
-    const int esz = (dtype == AB2_F32) ? 4 : 2;
-    for (int s = 0; s < n_a; ++s) {
-        if (a_width[s] % 8 != 0) return -1;
-        if ((reinterpret_cast<uintptr_t>(a_ptr[s]) % 16) != 0 || (a_ld[s] * esz) % 16 != 0) return -1;
-        if (act == AB2_ACT_MUL_DSILU && a_aux && a_aux[s] &&
-            ((reinterpret_cast<uintptr_t>(a_aux[s]) % 16) != 0 || (a_aux_ld[s] * esz) % 16 != 0)) return -1;
+// ---- host side of the TMA variant: tensor maps (driver entry point fetched through the runtime, no libcuda link) ----
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn tc_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* ptr = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess && qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(ptr);
+        else
+            cudaGetLastError();
     }
+    return fn;
+}
+
+// 2-D map of one fp32 row segment: dims {width, M}, row pitch ld*4 bytes, box 32 columns x 128 rows, 128-byte swizzle
+static bool tc_make_map(CUtensorMap* map, const void* ptr, int64_t ld, int width, int64_t M) {
+    EncodeTiledFn fn = tc_encode_fn();
+    if (!fn) return false;
+    const cuuint64_t dims[2] = {(cuuint64_t)width, (cuuint64_t)M};
+    const cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
+    const cuuint32_t box[2] = {(cuuint32_t)KC, (cuuint32_t)BM};
+    const cuuint32_t estr[2] = {1, 1};
+    return fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+              CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+static int tc_launch_tma(TcParams& p, int pf_mode, int w_bytes, int stage_bytes, int max_smem, unsigned grid, cudaStream_t st) {
+    TmaMaps maps;
+    memset(&maps, 0, sizeof(maps));
+    for (int s = 0; s < p.n_a; ++s) {
+        if (!tc_make_map(&maps.a[s], p.a[s].ptr, p.a[s].ld, p.a[s].width, p.M)) return -1;
+        if (p.a[s].aux && !tc_make_map(&maps.x[s], p.a[s].aux, p.a[s].aux_ld, p.a[s].width, p.M)) return -1;
+    }
+    const int raw_slot = TMA_BOX_BYTES * (p.has_aux ? 2 : 1);
+    // shared-memory plan: 4 (else 2) canonical stages, as many raw slots as fit (2..6), 1 KB slack for the swizzle alignment
+    int nstage = 0, NR = 0;
+    size_t smem = 0;
+    for (int cn : {NSTAGE, 2}) {
+        const size_t fixed = 1024 + ((w_bytes + 127) & ~127) + (size_t)cn * stage_bytes + EPI_BYTES + (pf_mode ? PF_BYTES : 0) + TAIL_BYTES;
+        if ((size_t)max_smem < fixed + 2 * (size_t)raw_slot) continue;
+        int nr = (int)(((size_t)max_smem - fixed) / raw_slot);
+        if (nr > 6) nr = 6;
+        nstage = cn; NR = nr; smem = fixed + (size_t)nr * raw_slot;
+        break;
+    }
+    if (!nstage) return -1;
+    p.nstage = nstage;
+    auto go = [&](auto kern) -> int {
+        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+            cudaGetLastError();
+            return -1;
+        }
+        kern<<<grid, TMA_THREADS, smem, st>>>(p, maps, NR);
+        return 0;
+    };
+    if (pf_mode == 1) return go(linear_tma_kernel<1>);
+    if (pf_mode == 2) return go(linear_tma_kernel<2>);
+    return go(linear_tma_kernel<0>);
+}
+
+// One column slice [n0, n0 + N) of the GEMM with its W images resident in shared memory.
+static int tc_launch_slice(int dtype, int64_t M, int K, int N, int n_a, const void* const* a_ptr, const int64_t* a_ld,
+                           const int32_t* a_width, const void* const* a_aux, const int64_t* a_aux_ld, int act, const void* Whi, const void* Wlo,
+                           int n_o, void* const* o_ptr, const int64_t* o_ld, const int32_t* o_width, const int32_t* o_accum, int epi,
+                           const void* aux, int64_t aux_ld, cudaStream_t st) {
     const int has_aux = (act == AB2_ACT_MUL_DSILU && a_aux) ? 1 : 0;
     int pf_mode = 0;
     if (dtype == AB2_F32) {
@@ -798,7 +1128,7 @@ int ab2_linear_tc_try(int dtype, int64_t M, int K, int N, int n_a, const void* c
     }
     TcParams p;
     memset(&p, 0, sizeof(p));
-    p.M = M; p.K = K; p.N = N; p.Npad = tc_npad(N); p.n_a = n_a; p.act = act; p.Wpacked = Wpacked; p.n_o = n_o;
+    p.M = M; p.K = K; p.N = N; p.Npad = tc_npad(N); p.n_a = n_a; p.act = act; p.Wpacked = Whi; p.Wlo = Wlo; p.n_o = n_o;
     p.epi = epi; p.aux = aux; p.aux_ld = aux_ld; p.num_tiles = (M + BM - 1) / BM;
     for (int s = 0; s < n_a; ++s) {
         p.a[s].ptr = a_ptr[s]; p.a[s].ld = a_ld[s]; p.a[s].width = a_width[s];
@@ -825,7 +1155,13 @@ int ab2_linear_tc_try(int dtype, int64_t M, int K, int N, int n_a, const void* c
     p.pf_mode = pf_mode;
     p.debug = g_ab2_opt_tc_debug;
     const unsigned grid = (unsigned)((p.num_tiles < num_sms) ? p.num_tiles : num_sms);
-    cudaError_t e;
+    // ---- TMA-producer kernel: fp32 storage, every A segment (and K) a multiple of 32 columns ----
+    bool tma_ok = g_ab2_opt_linear_tma && split && K % KC == 0 && M < ((int64_t)1 << 31);
+    for (int s = 0; s < n_a && tma_ok; ++s) tma_ok = a_width[s] % KC == 0;
+    if (tma_ok) {
+        const int rc = tc_launch_tma(p, pf_mode, w_bytes, stage_bytes, max_smem, grid, st);
+        if (rc == 0) return 0;
+    }
     auto go = [&](auto kern) -> int {
         if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
             cudaGetLastError();
@@ -834,7 +1170,6 @@ int ab2_linear_tc_try(int dtype, int64_t M, int K, int N, int n_a, const void* c
         kern<<<grid, NTHREADS, smem, st>>>(p);
         return 0;
     };
-    (void)e;
     if (split) {
         if (pf_mode == 1) return go(linear_tc_kernel<float, true, 1>);
         if (pf_mode == 2) return go(linear_tc_kernel<float, true, 2>);
@@ -843,3 +1178,52 @@ int ab2_linear_tc_try(int dtype, int64_t M, int K, int N, int n_a, const void* c
     return go(linear_tc_kernel<bf16, false, 0>);
 }
 
+// returns 0 if launched, -1 if this call is not eligible (caller falls back to linear.cu).
+// Outputs wider than 256 columns, or whose W image exceeds the shared-memory budget, run as column slices (one launch
+// per slice, each with its W slice resident; the A rows are re-read per slice).
+int ab2_linear_tc_try(int dtype, int64_t M, int K, int N, int n_a, const void* const* a_ptr, const int64_t* a_ld,
+                      const int32_t* a_width, const void* const* a_aux, const int64_t* a_aux_ld, int act, const void* Wpacked, int n_o, void* const* o_ptr, const int64_t* o_ld,
+                      const int32_t* o_width, const int32_t* o_accum, int epi, const void* aux, int64_t aux_ld, cudaStream_t st) {
+    if (!g_ab2_opt_linear_tc || !Wpacked || dtype == AB2_F64) return -1;
+    if (ab2_linear_packed_bytes(dtype, K, N) == 0) return -1;
+    const int esz = (dtype == AB2_F32) ? 4 : 2;
+    for (int s = 0; s < n_a; ++s) {
+        if (a_width[s] % 8 != 0) return -1;
+        if ((reinterpret_cast<uintptr_t>(a_ptr[s]) % 16) != 0 || (a_ld[s] * esz) % 16 != 0) return -1;
+        if (act == AB2_ACT_MUL_DSILU && a_aux && a_aux[s] &&
+            ((reinterpret_cast<uintptr_t>(a_aux[s]) % 16) != 0 || (a_aux_ld[s] * esz) % 16 != 0)) return -1;
+    }
+    const int cap = tc_slice_cap(dtype, K);
+    if (cap < 32) return -1;
+    const int Npad_full = tc_npad(N);
+    const int nslices = (N + cap - 1) / cap;
+    int width = ((N + nslices - 1) / nslices + 31) / 32 * 32;  // equal slices, multiples of 32 columns
+    if (width > cap) width = cap;
+    const uint8_t* hi = reinterpret_cast<const uint8_t*>(Wpacked);
+    const uint8_t* lo = hi + (size_t)Npad_full * K * 2;
+    for (int n0 = 0; n0 < N; n0 += width) {
+        const int ns = (N - n0 < width) ? (N - n0) : width;
+        // output sub-segments covered by [n0, n0 + ns)
+        void* so_ptr[AB2_MAX_SEG];
+        int64_t so_ld[AB2_MAX_SEG];
+        int32_t so_w[AB2_MAX_SEG], so_acc[AB2_MAX_SEG];
+        int cnt = 0, seg_lo = 0;
+        for (int s = 0; s < n_o; ++s) {
+            const int seg_hi = seg_lo + o_width[s];
+            const int a = n0 > seg_lo ? n0 : seg_lo, b = (n0 + ns) < seg_hi ? (n0 + ns) : seg_hi;
+            if (a < b) {
+                so_ptr[cnt] = reinterpret_cast<uint8_t*>(o_ptr[s]) + (size_t)(a - seg_lo) * esz;
+                so_ld[cnt] = o_ld[s];
+                so_w[cnt] = b - a;
+                so_acc[cnt] = o_accum ? o_accum[s] : 0;
+                ++cnt;
+            }
+            seg_lo = seg_hi;
+        }
+        const void* aux_s = aux ? reinterpret_cast<const uint8_t*>(aux) + (size_t)n0 * esz : nullptr;
+        const int rc = tc_launch_slice(dtype, M, K, ns, n_a, a_ptr, a_ld, a_width, a_aux, a_aux_ld, act, hi + (size_t)n0 * K * 2,
+                                       lo + (size_t)n0 * K * 2, cnt, so_ptr, so_ld, so_w, so_acc, epi, aux_s, aux_ld, st);
+        if (rc != 0) return n0 == 0 ? -1 : 1;  // a later slice failing would leave a half-written output: report an error
+    }
+    return 0;
+}

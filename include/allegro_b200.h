@@ -100,9 +100,11 @@ int ab2_linear(int dtype, int64_t M, int K, int N, int n_a, const void* const* a
 
 /* Tensor-core (tcgen05) path of ab2_linear.  ab2_linear_packed_bytes returns the size of the
  * packed weight image (bf16 hi + lo parts in the UMMA canonical K-major core-matrix layout) or 0
- * if (dtype, K, N) is not eligible (fp64, K % 16 != 0, N > 256, image > 128 KB);
- * ab2_linear_pack builds it on the device from W[K][N].  With fp32 storage the kernel computes
- * A_hi W_hi + A_lo W_hi + A_hi W_lo in bf16 MMAs with fp32 accumulation (~2^-16 relative). */
+ * if (dtype, K, N) is not eligible (fp64, K % 16 != 0, K > 512); ab2_linear_pack builds it on the
+ * device from W[K][N].  Any N is accepted: outputs wider than 256 columns, or whose W image does not
+ * fit the shared-memory budget (128 KB), run as column slices (one launch per slice, W slice resident).
+ * With fp32 storage the kernel computes A_hi W_hi + A_lo W_hi + A_hi W_lo in bf16 MMAs with fp32
+ * accumulation (~2^-16 relative). */
 int64_t ab2_linear_packed_bytes(int dtype, int K, int N);
 int ab2_linear_pack(int dtype, int K, int N, const void* W, void* packed, void* stream);
 

@@ -90,7 +90,10 @@ def test_linear_concat_split_act_epi(dtype, shape):
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 @pytest.mark.parametrize("shape", [(1000, [64, 32], [64, 96]), (77, [64], [96, 64, 96]), (40000, [64, 64, 64], [64]),
-                                   (300, [64], [1]), (129, [64, 96], [64, 64, 32]), (5000, [32, 16], [32]), (128, [96, 64, 96], [64])])
+                                   (300, [64], [1]), (129, [64, 96], [64, 64, 32]), (5000, [32, 16], [32]), (128, [96, 64, 96], [64]),
+                                   # c3-sized layers (S=128, U=64): wide outputs / W images beyond the shared-memory budget run as column slices
+                                   (700, [128], [192, 128, 192]), (333, [128], [128, 192]), (260, [128, 128, 64], [128]),
+                                   (515, [192, 128, 192], [128]), (200, [128], [384]), (150, [384], [128]), (90, [128, 192], [100, 60])])
 @pytest.mark.parametrize("mode", ["plain", "silu_in", "dsilu_epi_accum"])
 def test_linear_tensor_core_path(dtype, shape, mode):
     """tcgen05 path (16-byte aligned segments, K % 16 == 0) against an fp64 reference and against
