@@ -195,20 +195,22 @@ __host__ __device__ inline Plan make_plan(int U, int D, int NCH, int TE, int NS)
     const int rowB = MODE == 1 ? D_OUT * U * (int)sizeof(TAct) : 0;
     p.offA = 0;
     p.offY = up(TE * rowA);
-    p.offB = p.offY + (IMPLICIT ? up(TE * D_IN * (int)sizeof(TAcc)) : 0);
+    p.offB = p.offY + (IMPLICIT ? up(TE * ((D_IN + 3) / 4 * 4) * (int)sizeof(TAcc)) : 0);  // Y rows padded to 16 bytes
     p.stage_bytes = p.offB + up(TE * rowB);
     p.ring = o;   o += NS * p.stage_bytes;
     p.total = o;
     return p;
 }
 
-template <typename TAct, typename TAcc, int D_IN, int D_OUT, bool IMPLICIT, int MODE, int NCH, int TE, int NS>
+template <typename TAct, typename TAcc, int D_IN, int D_OUT, bool IMPLICIT, int MODE, int NCH, int TE, int NS, int UT>
 __global__ void __launch_bounds__((2 * NCH + 1) * 32) tp_stream_kernel(const StreamParams p) {
     extern __shared__ __align__(128) uint8_t smem[];
     constexpr int NCW = 2 * NCH;  // consumer warps
     constexpr int T = D_IN * D_OUT;
     constexpr int N_IR = IMPLICIT ? (D_IN == 1 ? 1 : D_IN == 4 ? 2 : D_IN == 9 ? 3 : D_IN == 16 ? 4 : 5) : 0;
-    const int U = p.U, D = p.D;
+    // UT != 0: the channel count is a compile-time constant -> every shared / global offset of the edge loop is an
+    // immediate (the first version spent ~2/3 of its instructions on 64-bit index arithmetic with a run-time U)
+    const int U = UT ? UT : p.U, D = p.D;
     const Plan pl = make_plan<TAct, TAcc, D_IN, D_OUT, IMPLICIT, MODE>(U, D, NCH, TE, NS);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + pl.bars);
     int2* s_meta = reinterpret_cast<int2*>(smem + pl.meta);
@@ -325,9 +327,11 @@ __global__ void __launch_bounds__((2 * NCH + 1) * 32) tp_stream_kernel(const Str
                 // Y rows: n * D_IN accumulate-type values, 4-byte aligned only -> element-wise cp.async
                 const TAcc* __restrict__ ysrc = (const TAcc*)p.Y + za * D_IN;
                 const uint32_t ydst = smem_u32(sb + pl.offY);
+                constexpr int YP = (D_IN + 3) / 4 * 4;  // padded row length in shared memory
                 for (int e = lane; e < n * D_IN; e += 32) {
-                    if (sizeof(TAcc) == 4) cp_async4(ydst + 4u * e, ysrc + e);
-                    else cp_async8(ydst + 8u * e, ysrc + e);
+                    const int r = e / D_IN, i = e - r * D_IN;
+                    if (sizeof(TAcc) == 4) cp_async4(ydst + 4u * (r * YP + i), ysrc + e);
+                    else cp_async8(ydst + 8u * (r * YP + i), ysrc + e);
                 }
                 cp_async_arrive_noinc(full_bar(stage));
             }
@@ -341,7 +345,7 @@ __global__ void __launch_bounds__((2 * NCH + 1) * 32) tp_stream_kernel(const Str
     // =============================== consumers ===============================
     const int q = warp >> 1, role = warp & 1;  // channel chunk, row/column half
     const int u = q * 32 + lane;
-    const bool live = u < U;
+    const bool live = UT ? true : (u < U);
     TAcc* scr = s_scr + (size_t)q * T * 32;
     const TAcc* __restrict__ cgw = (const TAcc*)p.cgw;
 
@@ -357,6 +361,7 @@ __global__ void __launch_bounds__((2 * NCH + 1) * 32) tp_stream_kernel(const Str
         // Blackwell issues one 3-register FFMA per 2 cycles per SM sub-partition; the full fp32 rate needs the packed
         // FFMA2 (fma.rn.f32x2).  M and gM are therefore held as column PAIRS (k, k+1) (+ one single column when NK is odd).
         constexpr int KP = NK / 2, KR = NK % 2;
+        [[maybe_unused]] constexpr int YP = (D_IN + 3) / 4 * 4;  // padded Y row in shared memory
         float2 M2[NI][KP > 0 ? KP : 1];
         float Mr[NI];
         float2 gM2[MODE == 1 ? NI : 1][KP > 0 ? KP : 1];
@@ -433,31 +438,50 @@ __global__ void __launch_bounds__((2 * NCH + 1) * 32) tp_stream_kernel(const Str
             }
         };
 
-        for (int64_t za = e_lo; za < e_hi; za += TE) {
-            const int n = (int)((e_hi - za) < TE ? (e_hi - za) : TE);
+        // running per-lane output pointers (advanced by one edge row per iteration: no 64-bit multiplies in the loop)
+        [[maybe_unused]] TAct* __restrict__ vout_p = MODE == 0 ? (TAct*)p.Vout + ((int64_t)e_lo * D_OUT + K0) * U + u : nullptr;
+        [[maybe_unused]] TAct* __restrict__ gvin_p = (MODE == 1 && !IMPLICIT) ? (TAct*)p.gVin + ((int64_t)e_lo * D_IN + I0) * U + u : nullptr;
+        [[maybe_unused]] TAct* __restrict__ gw0_p = (MODE == 1 && IMPLICIT) ? (TAct*)p.gw0 + (int64_t)e_lo * (N_IR * U) + u : nullptr;
+        [[maybe_unused]] float* __restrict__ gy_p = (MODE == 1 && IMPLICIT) ? (float*)p.gY + (int64_t)e_lo * D_IN + I0 : nullptr;
+        const int e_lo32 = (int)e_lo, e_hi32 = (int)e_hi;
+        int row_end32 = e_lo32;
+        for (int za = e_lo32; za < e_hi32; za += TE) {
+            const int n = (e_hi32 - za) < TE ? (e_hi32 - za) : TE;
             mbar_wait(full_bar(stage), phase);
             const uint8_t* sb = ring + (size_t)stage * pl.stage_bytes;
-            const TAct* __restrict__ sA = reinterpret_cast<const TAct*>(sb + pl.offA);
+            // per-lane bases: element (t, r) of a staged row block is base[(t * ROWS + r) * U]
+            const TAct* __restrict__ sA = reinterpret_cast<const TAct*>(sb + pl.offA) + u;
             [[maybe_unused]] const TAcc* __restrict__ sY = reinterpret_cast<const TAcc*>(sb + pl.offY);
-            [[maybe_unused]] const TAct* __restrict__ sB = reinterpret_cast<const TAct*>(sb + pl.offB);
-            for (int t = 0; t < n; ++t) {
-                const int64_t z = za + t;
-                if (z == row_end) {  // warp-uniform: first edge of the next non-empty centre
+            [[maybe_unused]] const TAct* __restrict__ sB = reinterpret_cast<const TAct*>(sb + pl.offB) + u;
+            int t = 0;
+            while (t < n) {
+                if (za + t == row_end32) {  // warp-uniform: first edge of the next non-empty centre
                     if (c >= 0) end_centre();
                     begin_centre();
+                    row_end32 = (int)row_end;
                 }
+                // edges of the current centre inside this stage: a branch-free run (unrolled for ILP)
+                const int t_end = (row_end32 - za) < n ? (row_end32 - za) : n;
+#pragma unroll 2
+                for (; t < t_end; ++t) {
                 if constexpr (MODE == 0) {
                     // ---------------- forward: Vout[z][K0..][u] = sum_i v[i] M[i][k] ----------------
                     float v[D_IN];
                     if constexpr (IMPLICIT) {
                         float wl[N_IR];
 #pragma unroll
-                        for (int l = 0; l < N_IR; ++l) wl[l] = live ? to_acc<float>(sA[(t * N_IR + l) * U + u]) : 0.f;
+                        for (int l = 0; l < N_IR; ++l) wl[l] = live ? to_acc<float>(sA[(t * N_IR + l) * U]) : 0.f;
+                        float Yr[YP];
 #pragma unroll
-                        for (int i = 0; i < D_IN; ++i) v[i] = sY[t * D_IN + i] * wl[sh_l_of(i)];
+                        for (int i4 = 0; i4 < YP / 4; ++i4) {
+                            const float4 y4 = *reinterpret_cast<const float4*>(sY + t * YP + 4 * i4);
+                            Yr[4 * i4] = y4.x; Yr[4 * i4 + 1] = y4.y; Yr[4 * i4 + 2] = y4.z; Yr[4 * i4 + 3] = y4.w;
+                        }
+#pragma unroll
+                        for (int i = 0; i < D_IN; ++i) v[i] = Yr[i] * wl[sh_l_of(i)];
                     } else {
 #pragma unroll
-                        for (int i = 0; i < D_IN; ++i) v[i] = live ? to_acc<float>(sA[(t * D_IN + i) * U + u]) : 0.f;
+                        for (int i = 0; i < D_IN; ++i) v[i] = live ? to_acc<float>(sA[(t * D_IN + i) * U]) : 0.f;
                     }
                     float2 o2[KP > 0 ? KP : 1];
                     float o_r = 0.f;
@@ -471,38 +495,46 @@ __global__ void __launch_bounds__((2 * NCH + 1) * 32) tp_stream_kernel(const Str
                         if (KR) o_r = fmaf(v[i], Mr[i], o_r);
                     }
                     if (live) {
-                        TAct* __restrict__ dst = (TAct*)p.Vout + (z * D_OUT + K0) * U + u;
 #pragma unroll
                         for (int kp = 0; kp < KP; ++kp) {
-                            dst[(2 * kp) * U] = from_acc<TAct>(o2[kp].x);
-                            dst[(2 * kp + 1) * U] = from_acc<TAct>(o2[kp].y);
+                            vout_p[(2 * kp) * U] = from_acc<TAct>(o2[kp].x);
+                            vout_p[(2 * kp + 1) * U] = from_acc<TAct>(o2[kp].y);
                         }
-                        if (KR) dst[(NK - 1) * U] = from_acc<TAct>(o_r);
+                        if (KR) vout_p[(NK - 1) * U] = from_acc<TAct>(o_r);
                     }
+                    vout_p += D_OUT * U;
                 } else {
                     // ---------------- backward ----------------
                     float2 go2[KP > 0 ? KP : 1];
                     float go_r = 0.f;
 #pragma unroll
                     for (int kp = 0; kp < KP; ++kp)
-                        go2[kp] = live ? make_float2(to_acc<float>(sB[(t * D_OUT + 2 * kp) * U + u]), to_acc<float>(sB[(t * D_OUT + 2 * kp + 1) * U + u]))
+                        go2[kp] = live ? make_float2(to_acc<float>(sB[(t * D_OUT + 2 * kp) * U]), to_acc<float>(sB[(t * D_OUT + 2 * kp + 1) * U]))
                                        : make_float2(0.f, 0.f);
-                    if (KR) go_r = live ? to_acc<float>(sB[(t * D_OUT + NK - 1) * U + u]) : 0.f;
+                    if (KR) go_r = live ? to_acc<float>(sB[(t * D_OUT + NK - 1) * U]) : 0.f;
                     float v[NI], gin[NI];
                     [[maybe_unused]] float wl[IMPLICIT ? N_IR : 1];
                     [[maybe_unused]] float Yv[IMPLICIT ? NI : 1];
                     if constexpr (IMPLICIT) {
 #pragma unroll
                         for (int l = 0; l < N_IR; ++l)
-                            if (l * l < I0 + NI && (l + 1) * (l + 1) > I0) wl[l] = live ? to_acc<float>(sA[(t * N_IR + l) * U + u]) : 0.f;
+                            if (l * l < I0 + NI && (l + 1) * (l + 1) > I0) wl[l] = live ? to_acc<float>(sA[(t * N_IR + l) * U]) : 0.f;
+                        // this warp's rows [I0, I0 + NI) of the padded Y row: aligned 16-byte broadcasts
+                        constexpr int A0 = I0 / 4 * 4, A1 = (I0 + NI + 3) / 4 * 4;
+                        float Yr[A1 - A0];
+#pragma unroll
+                        for (int i4 = 0; i4 < (A1 - A0) / 4; ++i4) {
+                            const float4 y4 = *reinterpret_cast<const float4*>(sY + t * YP + A0 + 4 * i4);
+                            Yr[4 * i4] = y4.x; Yr[4 * i4 + 1] = y4.y; Yr[4 * i4 + 2] = y4.z; Yr[4 * i4 + 3] = y4.w;
+                        }
 #pragma unroll
                         for (int i = 0; i < NI; ++i) {
-                            Yv[i] = sY[t * D_IN + I0 + i];
+                            Yv[i] = Yr[I0 - A0 + i];
                             v[i] = Yv[i] * wl[sh_l_of(I0 + i)];
                         }
                     } else {
 #pragma unroll
-                        for (int i = 0; i < NI; ++i) v[i] = live ? to_acc<float>(sA[(t * D_IN + I0 + i) * U + u]) : 0.f;
+                        for (int i = 0; i < NI; ++i) v[i] = live ? to_acc<float>(sA[(t * D_IN + I0 + i) * U]) : 0.f;
                     }
 #pragma unroll
                     for (int i = 0; i < NI; ++i) {
@@ -529,7 +561,7 @@ __global__ void __launch_bounds__((2 * NCH + 1) * 32) tp_stream_kernel(const Str
                                 float s = 0.f;
 #pragma unroll
                                 for (int i = l * l; i < (l + 1) * (l + 1); ++i) s = fmaf(Yv[i - I0], gin[i - I0], s);
-                                if (live) ((TAct*)p.gw0)[z * (int64_t)(N_IR * U) + l * U + u] = from_acc<TAct>(s);
+                                if (live) gw0_p[l * U] = from_acc<TAct>(s);
                             }
                         }
 #pragma unroll
@@ -537,17 +569,20 @@ __global__ void __launch_bounds__((2 * NCH + 1) * 32) tp_stream_kernel(const Str
                         const float tot = MultiSum<NI>::run(part, lane);
                         const int idx = MultiSum<NI>::idx_of(lane);
                         if (MultiSum<NI>::is_writer(lane) && idx < NI) {
-                            if (NCH == 1) atomicAdd((float*)p.gY + z * D_IN + I0 + idx, tot);  // RED, single writer per address
+                            if (NCH == 1) atomicAdd(gy_p + idx, tot);  // RED (fire and forget), single writer per address
                             else s_gyx[(q * TE + t) * D_IN + I0 + idx] = tot;
                         }
+                        gw0_p += N_IR * U;
+                        gy_p += D_IN;
                     } else {
                         if (live) {
-                            TAct* __restrict__ dst = (TAct*)p.gVin + (z * D_IN + I0) * U + u;
 #pragma unroll
-                            for (int i = 0; i < NI; ++i) dst[i * U] = from_acc<TAct>(gin[i]);
+                            for (int i = 0; i < NI; ++i) gvin_p[i * U] = from_acc<TAct>(gin[i]);
                         }
+                        gvin_p += D_IN * U;
                     }
                 }
+                }  // run
             }
             if constexpr (NCH > 1 && MODE == 1 && IMPLICIT) {
                 // channel chunks of one role meet here: fixed summation order over chunks (deterministic)
@@ -574,9 +609,9 @@ __global__ void __launch_bounds__((2 * NCH + 1) * 32) tp_stream_kernel(const Str
     else run(std::integral_constant<int, 1>{});
 }
 
-template <typename TAct, typename TAcc, int D_IN, int D_OUT, bool IMPLICIT, int MODE, int NCH, int TE, int NS>
+template <typename TAct, typename TAcc, int D_IN, int D_OUT, bool IMPLICIT, int MODE, int NCH, int TE, int NS, int UT>
 int launch_cfg(const StreamParams& p, cudaStream_t st) {
-    auto kern = tp_stream_kernel<TAct, TAcc, D_IN, D_OUT, IMPLICIT, MODE, NCH, TE, NS>;
+    auto kern = tp_stream_kernel<TAct, TAcc, D_IN, D_OUT, IMPLICIT, MODE, NCH, TE, NS, UT>;
     const Plan pl = make_plan<TAct, TAcc, D_IN, D_OUT, IMPLICIT, MODE>(p.U, p.D, NCH, TE, NS);
     static int num_sms = 0, max_smem = 0;
     if (num_sms == 0) {
@@ -606,12 +641,10 @@ int launch_cfg(const StreamParams& p, cudaStream_t st) {
 
 template <typename TAct, typename TAcc, int D_IN, int D_OUT, bool IMPLICIT, int MODE>
 int launch_shape(const StreamParams& p, cudaStream_t st) {
-    const int te = g_ab2_opt_tp_stream_te == 16 ? 16 : 8;
-    if (p.U <= 32) {
-        if (te == 16) return launch_cfg<TAct, TAcc, D_IN, D_OUT, IMPLICIT, MODE, 1, 16, 2>(p, st);
-        return launch_cfg<TAct, TAcc, D_IN, D_OUT, IMPLICIT, MODE, 1, 8, 3>(p, st);
-    }
-    if (p.U <= 64) return launch_cfg<TAct, TAcc, D_IN, D_OUT, IMPLICIT, MODE, 2, 8, 2>(p, st);
+    if (p.U == 32) return launch_cfg<TAct, TAcc, D_IN, D_OUT, IMPLICIT, MODE, 1, 8, 3, 32>(p, st);
+    if (p.U < 32) return launch_cfg<TAct, TAcc, D_IN, D_OUT, IMPLICIT, MODE, 1, 8, 3, 0>(p, st);
+    if (p.U == 64) return launch_cfg<TAct, TAcc, D_IN, D_OUT, IMPLICIT, MODE, 2, 8, 2, 64>(p, st);
+    if (p.U < 64) return launch_cfg<TAct, TAcc, D_IN, D_OUT, IMPLICIT, MODE, 2, 8, 2, 0>(p, st);
     return -1;
 }
 

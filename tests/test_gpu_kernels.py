@@ -95,11 +95,15 @@ def test_linear_concat_split_act_epi(dtype, shape):
                                    (700, [128], [192, 128, 192]), (333, [128], [128, 192]), (260, [128, 128, 64], [128]),
                                    (515, [192, 128, 192], [128]), (200, [128], [384]), (150, [384], [128]), (90, [128, 192], [100, 60])])
 @pytest.mark.parametrize("mode", ["plain", "silu_in", "dsilu_epi_accum"])
-def test_linear_tensor_core_path(dtype, shape, mode):
+@pytest.mark.parametrize("tma", [1, 0], ids=["tma", "cpasync"])
+def test_linear_tensor_core_path(dtype, shape, mode, tma):
     """tcgen05 path (16-byte aligned segments, K % 16 == 0) against an fp64 reference and against
     the CUDA-core kernel.  fp32 storage uses the 3-term bf16 split: held to 1e-4 (measured ~1e-5)."""
     M, awid, owid = shape
     K, N = sum(awid), sum(owid)
+    if tma and (dtype != torch.float32 or any(w % 32 for w in awid)):
+        pytest.skip("TMA producers need fp32 storage and 32-column segments (same kernel as the cp.async case otherwise)")
+    _lib.set_option("linear_tma", tma)
     g = torch.Generator().manual_seed(M + K + N)
     abufs = [torch.randn(M, w + 8, generator=g, dtype=torch.float64) for w in awid]
     W = torch.randn(K, N, generator=g, dtype=torch.float64) / math.sqrt(K)
@@ -135,6 +139,7 @@ def test_linear_tensor_core_path(dtype, shape, mode):
             exp[:, o : o + w] += 0.25
         o += w
     scale = exp.abs().max().item()
+    _lib.set_option("linear_tma", 1)
     tol = 1e-4 if dtype == torch.float32 else 2e-2
     assert (res["tc"] - exp).abs().max().item() / scale < tol
     assert (res["simt"] - exp).abs().max().item() / scale < (1e-5 if dtype == torch.float32 else 2e-2)

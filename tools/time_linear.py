@@ -34,10 +34,15 @@ def run(awid, owid, dtype, debug=0, tc=True, epi=0, accum=False, reps=10):
     return ms, byts / ms / 1e6
 
 
-for awid, owid in shapes:
-    K, N = sum(awid), sum(owid)
-    line = f"K={K:3d} N={N:3d}:"
-    for name, kw in [("full", {}), ("dsilu", dict(epi=1)), ("accum", dict(accum=True)), ("dsilu+acc", dict(epi=1, accum=True))]:
-        ms, gbs = run(awid, owid, torch.float32, **kw)
-        line += f"  {name} {ms*1e3:6.0f}us ({gbs:5.0f}GB/s)"
-    print(line, flush=True)
+shapes += [([128], [192, 128, 192]), ([128, 64], [128]), ([128], [128, 192]), ([192, 128, 192], [128])]  # c3-sized layers
+for tma in (1, 0):
+    _lib.set_option("linear_tma", tma)
+    print(f"--- linear_tma={tma} ({'TMA producer + converter groups' if tma else 'round-1 cp.async producers'}) ---", flush=True)
+    for awid, owid in shapes:
+        K, N = sum(awid), sum(owid)
+        line = f"K={K:3d} N={N:3d}:"
+        for name, kw in [("full", {}), ("dsilu", dict(epi=1)), ("accum", dict(accum=True)), ("dsilu+acc", dict(epi=1, accum=True))]:
+            ms, gbs = run(awid, owid, torch.float32, **kw)
+            line += f"  {name} {ms*1e3:6.0f}us ({gbs:5.0f}GB/s)"
+        print(line, flush=True)
+_lib.set_option("linear_tma", 1)
