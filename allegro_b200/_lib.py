@@ -48,6 +48,9 @@ _SIGNATURES = {
     "ab2_transpose_ui": ([_i32, _i64, _i32, _i32, _vp, _vp, _i32, _vp], C.c_int),
     "ab2_edge_vec": ([_i32, _i32, _i64, _vp, _vp, _vp, _vp, _vp, _vp], C.c_int),
     "ab2_radial_fwd": ([_i32, _i64, _i32, _i32, _dbl, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp], C.c_int),
+    "ab2_nl_bin": ([_i32, _i64, _vp, _vp, _vp, _vp, _vp, _dbl, _vp, _vp], C.c_int),
+    "ab2_nl_count": ([_i32, _i64, _vp, _vp, _vp, _vp, _vp, _dbl, _vp, _vp, _vp, _vp], C.c_int),
+    "ab2_nl_fill": ([_i32, _i64, _vp, _vp, _vp, _vp, _vp, _dbl, _vp, _vp, _vp, _vp, _vp, _vp], C.c_int),
     "ab2_radial_bwd": ([_i32, _i64, _i32, _i32, _dbl, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp], C.c_int),
 }
 
@@ -413,3 +416,37 @@ def radial_bwd(dtype, S_rc: int, p_cut: float, vec, ctr, nbr, types, rmax_table,
         _check(load().ab2_radial_bwd(DTYPE_ENUM[dtype], E, S_rc, bessel_w.numel(), float(p_cut), _ptr(vec), _ptr(ctr), _ptr(nbr), _ptr(types),
                                      _ptr(rmax_table), rmax_table.shape[0], _ptr(bessel_w), _ptr(Wb), _ptr(cemb), _ptr(nemb),
                                      _ptr(_contig(g_e0, "g_e0")), _ptr(gvec), _stream()))
+
+
+def neighbor_csr(pos: torch.Tensor, r_max: float, box, pbc=(True, True, True), origin=None, n_centres: Optional[int] = None):
+    """Cell-list neighbour search on the device -> (row_ptr [n_centres+1] int32, nbr [E] int32, shift_vec [E,3] pos dtype).
+    Orthorhombic ``box`` (3 lengths); centres are atoms [0, n_centres) (owned atoms first)."""
+    n = pos.shape[0]
+    n_centres = n if n_centres is None else int(n_centres)
+    box = [float(b) for b in box]
+    origin = [0.0, 0.0, 0.0] if origin is None else [float(o) for o in origin]
+    ncell = [max(1, int(b // float(r_max))) for b in box]
+    g_box, g_org = (C.c_double * 3)(*box), (C.c_double * 3)(*origin)
+    g_pbc, g_nc = (C.c_int32 * 3)(*[int(bool(p)) for p in pbc]), (C.c_int32 * 3)(*ncell)
+    dt = DTYPE_ENUM[pos.dtype]
+    pos = _contig(pos, "pos")
+    cell_id = torch.empty(n, dtype=torch.int32, device=pos.device)
+    with _timed("nl_bin"):
+        _check(load().ab2_nl_bin(dt, n, _ptr(pos), g_box, g_org, g_pbc, g_nc, float(r_max), _ptr(cell_id), _stream()))
+    order = torch.argsort(cell_id, stable=True).to(torch.int32)
+    ncells = ncell[0] * ncell[1] * ncell[2]
+    cell_start = torch.zeros(ncells + 1, dtype=torch.int32, device=pos.device)
+    cell_start[1:] = torch.cumsum(torch.bincount(cell_id.long(), minlength=ncells), 0).to(torch.int32)
+    counts = torch.empty(n_centres, dtype=torch.int32, device=pos.device)
+    with _timed("nl_count"):
+        _check(load().ab2_nl_count(dt, n_centres, _ptr(pos), g_box, g_org, g_pbc, g_nc, float(r_max), _ptr(cell_start), _ptr(order), _ptr(counts), _stream()))
+    row_ptr = torch.zeros(n_centres + 1, dtype=torch.int32, device=pos.device)
+    row_ptr[1:] = torch.cumsum(counts, 0).to(torch.int32)
+    E = int(row_ptr[-1])
+    nbr = torch.empty(E, dtype=torch.int32, device=pos.device)
+    shift = torch.empty(E, 3, dtype=pos.dtype, device=pos.device)
+    if E:
+        with _timed("nl_fill"):
+            _check(load().ab2_nl_fill(dt, n_centres, _ptr(pos), g_box, g_org, g_pbc, g_nc, float(r_max), _ptr(cell_start), _ptr(order), _ptr(row_ptr),
+                                      _ptr(nbr), _ptr(shift), _stream()))
+    return row_ptr, nbr, shift

@@ -62,11 +62,21 @@ class AllegroCalculator:
             if self._data is None:
                 raise ValueError("atom_types are needed for the first evaluation")
             atom_types = self._data[D.ATOM_TYPE_KEY]
-        ei, shift = D.neighbor_list(pos, self.r_max + self.skin, cell, self.pbc)
-        data = {D.POSITIONS_KEY: pos.clone(), D.ATOM_TYPE_KEY: atom_types.reshape(-1).clone(), D.EDGE_INDEX_KEY: ei}
-        if cell is not None:
+        data = {D.POSITIONS_KEY: pos.clone(), D.ATOM_TYPE_KEY: atom_types.reshape(-1).clone()}
+        inner = getattr(self.model, "model", self.model)
+        if hasattr(inner, "energy_and_forces") and D.csr_supported(pos, self.r_max + self.skin, cell, self.pbc):
+            # CUDA cell list straight into the kernels' CSR (no int64 COO list, no sort by centre)
+            csr, shift_vec = D.neighbor_csr(pos, self.r_max + self.skin, cell, self.pbc)
+            data[D.CSR_KEY], data[D.EDGE_SHIFT_VEC_KEY] = csr, shift_vec
             data[D.CELL_KEY] = cell.view(3, 3).clone()
-            data[D.EDGE_CELL_SHIFT_KEY] = shift
+            self._n_edges = csr.num_edges
+        else:
+            ei, shift = D.neighbor_list(pos, self.r_max + self.skin, cell, self.pbc)
+            data[D.EDGE_INDEX_KEY] = ei
+            self._n_edges = int(ei.shape[1])
+            if cell is not None:
+                data[D.CELL_KEY] = cell.view(3, 3).clone()
+                data[D.EDGE_CELL_SHIFT_KEY] = shift
         self._data, self._pos_ref = data, pos.clone()
         self._graphed = None
         self._since_check = 0
@@ -100,4 +110,4 @@ class AllegroCalculator:
 
     @property
     def num_edges(self) -> int:
-        return 0 if self._data is None else int(self._data[D.EDGE_INDEX_KEY].shape[1])
+        return 0 if self._data is None else int(self._n_edges)

@@ -37,6 +37,11 @@ TOTAL_ENERGY_KEY = "total_energy"
 FORCE_KEY = "forces"
 STRESS_KEY = "stress"
 VIRIAL_KEY = "virial"
+# prepared-frame keys (this package only): a prebuilt centre-sorted CSR (EdgeCSR) and the per-edge shift vectors
+# [E,3] = edge_cell_shift @ cell in CSR order.  When present they are used instead of edge_index / edge_cell_shift,
+# so the int64 COO list never has to exist (neighbor_csr below; 5x10^7 edges at the 1M-atom scale).
+CSR_KEY = "edge_csr"
+EDGE_SHIFT_VEC_KEY = "edge_shift_vec"
 
 Type = Dict[str, torch.Tensor]
 
@@ -254,3 +259,38 @@ def to_ghost_format(data: Type) -> Type:
     data.pop(PBC_KEY, None)
     data["num_local_atoms"] = torch.tensor(pos.shape[0])
     return data
+
+
+def csr_supported(pos: torch.Tensor, r_max: float, cell: Optional[torch.Tensor], pbc=(True, True, True)) -> bool:
+    """Can ``neighbor_csr`` (CUDA cell list) take this frame?  CUDA positions, orthorhombic box, >= 3 cells of
+    edge r_max on every periodic axis."""
+    if not pos.is_cuda or cell is None:
+        return False
+    c = cell.view(3, 3)
+    if bool((c - torch.diag(torch.diagonal(c))).abs().max() != 0):
+        return False
+    return all((not p) or float(c[a, a]) >= 3 * r_max for a, p in enumerate(pbc))
+
+
+def neighbor_csr(pos: torch.Tensor, r_max: float, cell: torch.Tensor, pbc=(True, True, True), n_centres: Optional[int] = None):
+    """Neighbour search on the device straight into the kernels' format (ab2_nl_bin / count / fill).
+    -> (EdgeCSR, shift_vec [E,3] in the positions' dtype).  Centres are atoms [0, n_centres) (owned atoms first)."""
+    from . import _lib
+
+    pbc = tuple(bool(p) for p in (pbc if not isinstance(pbc, bool) else (pbc,) * 3))
+    if not csr_supported(pos, r_max, cell, pbc):
+        raise ValueError("neighbor_csr needs CUDA positions and an orthorhombic box with >= 3 r_max per periodic axis")
+    box = [float(v) for v in torch.diagonal(cell.view(3, 3))]
+    origin = [0.0, 0.0, 0.0]
+    for a, p in enumerate(pbc):
+        if not p:  # open axis: grid over the occupied extent
+            lo, hi = float(pos[:, a].min()), float(pos[:, a].max())
+            origin[a] = lo
+            box[a] = (hi - lo) * (1 + 1e-9) + 1e-6
+    n = pos.shape[0]
+    nc = n if n_centres is None else int(n_centres)
+    row_ptr, nbr, shift = _lib.neighbor_csr(pos, r_max, box, pbc, origin, nc)
+    counts = (row_ptr[1:] - row_ptr[:-1])
+    ctr = torch.repeat_interleave(torch.arange(nc, device=pos.device, dtype=torch.int32), counts.long())
+    maxdeg = int(counts.max()) if nc > 0 else 0
+    return EdgeCSR(nc, ctr.contiguous(), nbr, row_ptr, None, maxdeg), shift

@@ -199,9 +199,14 @@ class FusedAllegroEnergy(torch.nn.Module):
         pos = data[D.POSITIONS_KEY]
         core = self.core()
         n = pos.shape[0]
-        csr = self._csr(data[D.EDGE_INDEX_KEY], n)
+        prepared = D.CSR_KEY in data  # prebuilt CSR (+ shift vectors in CSR order): data.neighbor_csr
+        csr = data[D.CSR_KEY] if prepared else self._csr(data[D.EDGE_INDEX_KEY], n)
         shift_vec = None
-        if D.EDGE_CELL_SHIFT_KEY in data and D.CELL_KEY in data:
+        if prepared:
+            shift_vec = data.get(D.EDGE_SHIFT_VEC_KEY)
+            if shift_vec is not None:
+                shift_vec = shift_vec.to(pos.dtype).contiguous()
+        elif D.EDGE_CELL_SHIFT_KEY in data and D.CELL_KEY in data:
             sh, cell = data[D.EDGE_CELL_SHIFT_KEY], data[D.CELL_KEY]
 
             def _shift():

@@ -182,6 +182,27 @@ int ab2_radial_bwd(int dtype, int64_t E, int S_rc, int num_bessels, double p_cut
                    const void* center_embed, const void* neighbor_embed, const void* g_e0,
                    void* gvec, void* stream);
 
+/* ---- neighbour list on the device, directly in CSR --------------- */
+
+/* Cell-list search on an orthorhombic box with per-axis periodicity.  The reference receives edge_index [2,E] int64
+ * from nequip's data pipeline / LAMMPS (allegro/nn/_allegro.py:238, allegro/_compile.py:41-61); these three kernels
+ * produce the centre-sorted CSR (row_ptr / nbr int32) and the per-edge shift VECTORS the path consumes, without the
+ * int64 COO list.  Host-side geometry: box[3], origin[3] (doubles), pbc[3], ncell[3] with box/ncell >= r_max and
+ * >= 3 cells on every periodic axis.  pos: [n][3] fp64 or fp32, raw (unwrapped) coordinates;
+ *   r = pos[nbr] + shift - pos[centre]  holds for the raw positions.
+ * Call order: ab2_nl_bin -> (host: order = stable argsort(cell_id), cell_start = prefix sum of the cell histogram)
+ *             -> ab2_nl_count -> (host: row_ptr = prefix sum) -> ab2_nl_fill.
+ * Centres are atoms [0, n_centres) (owned atoms first, ghosts after: only owned atoms get rows). */
+int ab2_nl_bin(int pos_dtype, int64_t n, const void* pos, const double* box_host, const double* origin_host,
+               const int32_t* pbc_host, const int32_t* ncell_host, double r_max, int32_t* cell_id, void* stream);
+int ab2_nl_count(int pos_dtype, int64_t n_centres, const void* pos, const double* box_host,
+                 const double* origin_host, const int32_t* pbc_host, const int32_t* ncell_host, double r_max,
+                 const int32_t* cell_start, const int32_t* order, int32_t* counts, void* stream);
+int ab2_nl_fill(int pos_dtype, int64_t n_centres, const void* pos, const double* box_host,
+                const double* origin_host, const int32_t* pbc_host, const int32_t* ncell_host, double r_max,
+                const int32_t* cell_start, const int32_t* order, const int32_t* row_ptr, int32_t* nbr,
+                void* shift, void* stream);
+
 /* layout helpers between the reference strided layout [z][u][i] and the internal [z][i][u] */
 int ab2_transpose_ui(int dtype, int64_t E, int U, int d, const void* src, void* dst, int to_internal,
                      void* stream);
