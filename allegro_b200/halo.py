@@ -31,7 +31,7 @@ from . import data as D
 class SlabDecomposition:
     """Static exchange plan of one rank (valid as long as the neighbour list is)."""
 
-    def __init__(self, pos: torch.Tensor, cell: torch.Tensor, types: torch.Tensor, r_max: float, rank: int, world: int):
+    def __init__(self, pos: torch.Tensor, cell: torch.Tensor, types: torch.Tensor, r_max: float, rank: int, world: int, device=None):
         assert world >= 2, "use the plain periodic path on one rank"
         cell = cell.view(3, 3)
         assert bool((cell - torch.diag(torch.diagonal(cell))).abs().max() == 0), "slab decomposition needs an orthorhombic box"
@@ -76,10 +76,20 @@ class SlabDecomposition:
         self.pbc = (False, True, True)
         # unwrapped x so that slab + ghosts form one contiguous block along x
         pos_local = self.local_positions_from_global(pos)
-        ei, sh = D.neighbor_list(pos_local, r_max, self.cell, self.pbc)
-        keep = ei[0] < self.n_owned  # edges of owned centres only
-        self.edge_index = ei[:, keep].contiguous()
-        self.edge_cell_shift = sh[keep].contiguous()
+        self.csr, self.shift_vec = None, None
+        self.edge_index = self.edge_cell_shift = None
+        dev = torch.device(device) if device is not None else None
+        if dev is not None and dev.type == "cuda" and D.csr_supported(pos_local.to(dev), r_max, self.cell, self.pbc):
+            # CUDA cell list over owned + ghost atoms, rows for the owned centres only, straight into the kernels' CSR:
+            # the int64 COO list of the local frame (6.5M edges per rank for the 1M-atom box) is never built
+            self.csr, self.shift_vec = D.neighbor_csr(pos_local.to(dev), r_max, self.cell.to(dev), self.pbc, n_centres=self.n_owned)
+            self.n_edges = self.csr.num_edges
+        else:
+            ei, sh = D.neighbor_list(pos_local, r_max, self.cell, self.pbc)
+            keep = ei[0] < self.n_owned  # edges of owned centres only
+            self.edge_index = ei[:, keep].contiguous()
+            self.edge_cell_shift = sh[keep].contiguous()
+            self.n_edges = int(self.edge_index.shape[1])
 
     # positions of owned + ghost atoms taken from a global frame (set-up / tests)
     def local_positions_from_global(self, pos: torch.Tensor) -> torch.Tensor:
@@ -95,7 +105,8 @@ class SlabDecomposition:
     def to(self, device) -> "SlabDecomposition":
         for k in ("owned", "send_right_idx", "send_left_idx", "ghost_global", "types_local", "global_ids_local", "cell",
                   "edge_index", "edge_cell_shift"):
-            setattr(self, k, getattr(self, k).to(device))
+            if getattr(self, k) is not None:
+                setattr(self, k, getattr(self, k).to(device))
         return self
 
     # ---- communication --------------------------------------------------------------------
@@ -168,13 +179,11 @@ class DistributedAllegro:
         dec = self.dec
         ghosts = dec.exchange_forward(pos_owned.detach())
         pos_local = torch.cat([pos_owned.detach(), ghosts], 0).requires_grad_(True)
-        data = {
-            D.POSITIONS_KEY: pos_local,
-            D.ATOM_TYPE_KEY: dec.types_local,
-            D.EDGE_INDEX_KEY: dec.edge_index,
-            D.EDGE_CELL_SHIFT_KEY: dec.edge_cell_shift,
-            D.CELL_KEY: dec.cell,
-        }
+        data = {D.POSITIONS_KEY: pos_local, D.ATOM_TYPE_KEY: dec.types_local, D.CELL_KEY: dec.cell}
+        if dec.csr is not None:
+            data[D.CSR_KEY], data[D.EDGE_SHIFT_VEC_KEY] = dec.csr, dec.shift_vec
+        else:
+            data[D.EDGE_INDEX_KEY], data[D.EDGE_CELL_SHIFT_KEY] = dec.edge_index, dec.edge_cell_shift
         if hasattr(self.model, "energy_and_forces"):
             # autograd-free CUDA path: forces on owned AND ghost atoms come out of one pass
             data[D.POSITIONS_KEY] = pos_local.detach()
