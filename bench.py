@@ -480,12 +480,73 @@ def run_reference(args, rank: int, world: int):
     print(json.dumps(res))
 
 
+def run_reference_gpu(args, rank: int, world: int, triton: bool = False):
+    """GPU baseline (SURVEY 8d "GPU reference baseline"): the oracle -- a plain-PyTorch restatement of the reference's
+    default path, autograd forces -- evaluated on one B200 at the full benchmark size, fp32, eager.  With ``triton``
+    every eligible Contracter is replaced by the reference's own TritonContracter (oracle/_ref, staged verbatim from
+    /root/reference by oracle/build_ref.py), i.e. the reference's accelerated inference path."""
+    if rank != 0:
+        return
+    from allegro_b200 import data as D
+    from allegro_b200 import systems
+    from oracle.model_ref import AllegroOracle
+
+    dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", 0)))
+    torch.cuda.set_device(dev)
+    cfg = args.config
+    d = systems.make_system(cfg)
+    n, e = d[D.POSITIONS_KEY].shape[0], d[D.EDGE_INDEX_KEY].shape[1]
+    kw = systems.model_kwargs(cfg, e / n, "float32")
+    oracle = AllegroOracle(**kw)
+    swapped = 0
+    if triton:
+        from oracle import build_ref
+
+        ref = build_ref.load()
+        inner = oracle.model if hasattr(oracle, "model") else oracle
+        tps = inner.allegro.tps
+        for i, tp in enumerate(tps):
+            if tp.w3j.dim() != 4:
+                continue  # the reference's Triton path only takes [P,I,J,K] tables (_flashallegro.py:315)
+            new = ref.TritonContracter(irreps_in1=repr(tp.irreps_in1).replace(" ", ""), irreps_in2=repr(tp.irreps_in2).replace(" ", ""), irreps_out=repr(tp.irreps_out).replace(" ", ""), mul=tp.mul,
+                                       instructions=tp.instructions, path_channel_coupling=tp.path_channel_coupling,
+                                       scatter_factor=tp.scatter_factor, irrep_normalization=tp.irrep_normalization)
+            new.load_state_dict(tp.state_dict())
+            tps[i] = new
+            swapped += 1
+    oracle = oracle.to(dev).eval()
+    dd = {k: v.to(dev) for k, v in d.items()}
+    dd[D.POSITIONS_KEY] = dd[D.POSITIONS_KEY].float()
+    dd[D.CELL_KEY] = dd[D.CELL_KEY].float()
+    dd[D.EDGE_CELL_SHIFT_KEY] = dd[D.EDGE_CELL_SHIFT_KEY].float()
+    K, W = args.steps, args.warmup
+    for _ in range(max(W, 1)):
+        out = oracle(dd)
+    torch.cuda.synchronize()
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0.record()
+    for _ in range(K):
+        out = oracle(dd)
+    t1.record()
+    torch.cuda.synchronize()
+    ms = t0.elapsed_time(t1) / K
+    res = {"impl": args.impl, "metric": METRIC, "value": n * 1e3 / ms, "unit": UNIT, "n_gpus": 1, "steps": K, "warmup": W, "ms_per_step": ms,
+           "higher_is_better": True, "dtype": "f32", "data": "synthetic",
+           "config": {"workload": f"{cfg}: {n} atoms, {e} edges (full size)", "what": "oracle/ (plain PyTorch restatement of the reference, autograd forces) on 1 B200, eager"
+                      + (f", {swapped} Contracter(s) replaced by the reference's TritonContracter" if triton else ""),
+                      "peak_mem_gb": round(torch.cuda.max_memory_allocated() / 2**30, 1)}}
+    print(json.dumps(res))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=10)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference", "reference-gpu", "reference-gpu-triton"],
+                    help="reference = CPU oracle (the driver's reference arm); reference-gpu(-triton) = the same oracle on the B200 "
+                         "(eager PyTorch; -triton swaps in the reference's own Triton tensor-product kernel staged under oracle/_ref): "
+                         "the GPU baseline of the >=10x target, NOT the driver's anchor")
     ap.add_argument("--config", default="c2")
     ap.add_argument("--dtype", default="float32", choices=["float64", "float32", "bfloat16"],
                     help="activation storage; default float32 (GEMMs on tcgen05 as split-bf16, fp32-accurate): bfloat16 storage, the dtype BASELINE names for c2, measured 4e-3/4e-2 (E/F) against the fp64 oracle, outside the 1e-3 parity bar")
@@ -497,6 +558,8 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", 1))
     if args.impl == "reference":
         return run_reference(args, rank, world)
+    if args.impl.startswith("reference-gpu"):
+        return run_reference_gpu(args, rank, world, triton=args.impl.endswith("triton"))
     return run_ours(args, rank, world)
 
 
