@@ -798,7 +798,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) linear_tc_kernel(const TcParams p
 //                  warps all worked on the SAME stage and topped out at 2.3-3.2 TB/s on the load side.
 //   warp 8 / 9-12: MMA issuer and epilogue, unchanged (tc_mma_role / tc_epilogue_role).
 // =========================================================================================
-constexpr int TMA_NGRP = 4;
 constexpr int TMA_THREADS = NTHREADS + 32;
 constexpr int TMA_BOX_BYTES = BM * KC * 4;  // 16 KB
 
@@ -816,8 +815,14 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
 
-template <int PF>
+// G converter groups of 8/G warps.  A raw slot and a canonical stage must always be consumed / produced by the SAME group
+// (NR % G == 0 and nstage % G == 0, checked on the host): a group then never waits more than one mbarrier phase ahead
+// of its own slot.  (With slots shared between groups a group's first wait can be for the SECOND fill of a slot whose
+// first fill has not completed yet -- the parity wait returns immediately and the pipeline falls apart.)
+template <int PF, int G>
 __global__ void __launch_bounds__(TMA_THREADS, 1) linear_tma_kernel(const TcParams p, const __grid_constant__ TmaMaps maps, int NR) {
+    constexpr int WPG = NPROD / G;      // warps per converter group
+    constexpr int RGW = 16 / WPG;       // 8-row groups of a stage handled by one warp
     using TSrc = float;
     constexpr bool SPLIT = true;
     extern __shared__ __align__(1024) uint8_t smem[];
@@ -846,7 +851,7 @@ __global__ void __launch_bounds__(TMA_THREADS, 1) linear_tma_kernel(const TcPara
     // ---- one-time setup ----
     if (threadIdx.x == 0) {
         for (int s = 0; s < NSTAGE; ++s) {
-            mbar_init(bar0 + 8u * s, 64);                // canonical stage full: the two warps of a converter group
+            mbar_init(bar0 + 8u * s, WPG * 32);          // canonical stage full: the warps of one converter group
             mbar_init(bar0 + 8u * (NSTAGE + s), 1);      // empty: tcgen05.commit
         }
         for (int a = 0; a < 2; ++a) {
@@ -855,7 +860,7 @@ __global__ void __launch_bounds__(TMA_THREADS, 1) linear_tma_kernel(const TcPara
         }
         for (int s = 0; s < 8; ++s) {
             mbar_init(rfull_bar(s), 1);                  // expect_tx arrive of the TMA lane
-            mbar_init(rempty_bar(s), 64);
+            mbar_init(rempty_bar(s), WPG * 32);
         }
         fence_barrier_init();
     }
@@ -921,19 +926,19 @@ __global__ void __launch_bounds__(TMA_THREADS, 1) linear_tma_kernel(const TcPara
         }
     } else if (warp < NPROD) {
         // =============================== converters ===============================
-        const int grp = warp >> 1, sub = warp & 1;
+        const int grp = warp / WPG, sub = warp % WPG;
         const int r8 = lane & 7, kc = lane >> 3;
-        // raw slot / canonical stage of sequence number qs: plain counters (advance by TMA_NGRP per iteration)
+        // raw slot / canonical stage of sequence number qs: plain counters (advance by G per iteration)
         int rs = grp % NR, cs = grp % p.nstage, kb = grp % nkb;
         uint32_t rph = (uint32_t)((grp / NR) & 1), cph = (uint32_t)((grp / p.nstage) & 1);
-        for (int64_t qs = grp; qs < total; qs += TMA_NGRP) {
+        for (int64_t qs = grp; qs < total; qs += G) {
             mbar_wait(rfull_bar(rs), rph);
             const uint8_t* raw = sRaw + (size_t)rs * raw_slot;
             const bool ax = p.has_aux && sKseg[kb].z;
-            float v[8][8];
+            float v[RGW][8];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const int row = (sub * 8 + i) * 8 + r8;
+            for (int i = 0; i < RGW; ++i) {
+                const int row = (sub * RGW + i) * 8 + r8;
                 const uint8_t* rp = raw + row * 128;
                 const float4 x = *reinterpret_cast<const float4*>(rp + (((2 * kc) ^ r8) << 4));
                 const float4 y = *reinterpret_cast<const float4*>(rp + (((2 * kc + 1) ^ r8) << 4));
@@ -941,8 +946,8 @@ __global__ void __launch_bounds__(TMA_THREADS, 1) linear_tma_kernel(const TcPara
             }
             if (ax) {
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const int row = (sub * 8 + i) * 8 + r8;
+                for (int i = 0; i < RGW; ++i) {
+                    const int row = (sub * RGW + i) * 8 + r8;
                     const uint8_t* rp = raw + TMA_BOX_BYTES + row * 128;
                     const float4 x = *reinterpret_cast<const float4*>(rp + (((2 * kc) ^ r8) << 4));
                     const float4 y = *reinterpret_cast<const float4*>(rp + (((2 * kc + 1) ^ r8) << 4));
@@ -955,12 +960,12 @@ __global__ void __launch_bounds__(TMA_THREADS, 1) linear_tma_kernel(const TcPara
             mbar_wait(ctx.empty_bar(cs), cph ^ 1);
             uint8_t* st_hi = sA + cs * stage_bytes;
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
+            for (int i = 0; i < RGW; ++i) {
                 if (p.act == AB2_ACT_SILU) {
 #pragma unroll
                     for (int t = 0; t < 8; ++t) v[i][t] = silu_fast(v[i][t]);
                 }
-                const int g = sub * 8 + i;
+                const int g = sub * RGW + i;
                 const uint32_t off = g * (KC / 8) * 128 + kc * 128 + r8 * 16;
                 uint32_t hi[4];
                 float lo[8];
@@ -979,10 +984,10 @@ __global__ void __launch_bounds__(TMA_THREADS, 1) linear_tma_kernel(const TcPara
             }
             fence_proxy_async();
             mbar_arrive(ctx.full_bar(cs));
-            // advance the counters by TMA_NGRP stages
-            rs += TMA_NGRP; while (rs >= NR) { rs -= NR; rph ^= 1; }
-            cs += TMA_NGRP; while (cs >= p.nstage) { cs -= p.nstage; cph ^= 1; }
-            kb += TMA_NGRP; while (kb >= nkb) kb -= nkb;
+            // advance the counters by G stages (NR and nstage are multiples of G: at most one wrap each)
+            rs += G; if (rs >= NR) { rs -= NR; rph ^= 1; }
+            cs += G; if (cs >= p.nstage) { cs -= p.nstage; cph ^= 1; }
+            kb += G; while (kb >= nkb) kb -= nkb;
         }
     } else if (warp == NPROD) {
         tc_mma_role<SPLIT>(p, ctx, lane);
@@ -1081,18 +1086,17 @@ static int tc_launch_tma(TcParams& p, int pf_mode, int w_bytes, int stage_bytes,
         if (p.a[s].aux && !tc_make_map(&maps.x[s], p.a[s].aux, p.a[s].aux_ld, p.a[s].width, p.M)) return -1;
     }
     const int raw_slot = TMA_BOX_BYTES * (p.has_aux ? 2 : 1);
-    // shared-memory plan: 4 (else 2) canonical stages, as many raw slots as fit (2..6), 1 KB slack for the swizzle alignment
-    int nstage = 0, NR = 0;
+    // shared-memory plan (1 KB slack for the swizzle alignment): G converter groups, NR raw slots, cn canonical stages with
+    // NR % G == 0 and cn % G == 0 (see the kernel); deepest pipeline that fits
+    const int plans[6][3] = {{4, 8, 4}, {4, 4, 4}, {2, 4, 4}, {2, 2, 4}, {2, 4, 2}, {2, 2, 2}};  // {G, NR, cn}
+    int G = 0, NR = 0, nstage = 0;
     size_t smem = 0;
-    for (int cn : {NSTAGE, 2}) {
-        const size_t fixed = 1024 + ((w_bytes + 127) & ~127) + (size_t)cn * stage_bytes + EPI_BYTES + (pf_mode ? PF_BYTES : 0) + TAIL_BYTES;
-        if ((size_t)max_smem < fixed + 2 * (size_t)raw_slot) continue;
-        int nr = (int)(((size_t)max_smem - fixed) / raw_slot);
-        if (nr > 6) nr = 6;
-        nstage = cn; NR = nr; smem = fixed + (size_t)nr * raw_slot;
-        break;
+    for (int q = 0; q < 6 && !G; ++q) {
+        const size_t need = 1024 + ((w_bytes + 127) & ~127) + (size_t)plans[q][2] * stage_bytes + EPI_BYTES + (pf_mode ? PF_BYTES : 0) + TAIL_BYTES +
+                            (size_t)plans[q][1] * raw_slot;
+        if (need <= (size_t)max_smem) { G = plans[q][0]; NR = plans[q][1]; nstage = plans[q][2]; smem = need; }
     }
-    if (!nstage) return -1;
+    if (!G) return -1;
     p.nstage = nstage;
     auto go = [&](auto kern) -> int {
         if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
@@ -1102,9 +1106,14 @@ static int tc_launch_tma(TcParams& p, int pf_mode, int w_bytes, int stage_bytes,
         kern<<<grid, TMA_THREADS, smem, st>>>(p, maps, NR);
         return 0;
     };
-    if (pf_mode == 1) return go(linear_tma_kernel<1>);
-    if (pf_mode == 2) return go(linear_tma_kernel<2>);
-    return go(linear_tma_kernel<0>);
+    if (G == 4) {
+        if (pf_mode == 1) return go(linear_tma_kernel<1, 4>);
+        if (pf_mode == 2) return go(linear_tma_kernel<2, 4>);
+        return go(linear_tma_kernel<0, 4>);
+    }
+    if (pf_mode == 1) return go(linear_tma_kernel<1, 2>);
+    if (pf_mode == 2) return go(linear_tma_kernel<2, 2>);
+    return go(linear_tma_kernel<0, 2>);
 }
 
 // One column slice [n0, n0 + N) of the GEMM with its W images resident in shared memory.

@@ -28,6 +28,7 @@
 
 #include "common.cuh"
 #include "tp_fast.cuh"
+#include "tp_tables_generated.cuh"
 
 int g_ab2_opt_tp_stream = 1;    // 1: use these kernels where instantiated, 0: round-1 kernels
 int g_ab2_opt_tp_stream_te = 0;  // edges per stage (0 = default 8), 8 or 16
@@ -164,6 +165,20 @@ __device__ __forceinline__ int64_t cut_centre(const int32_t* __restrict__ row_pt
     return row_ptr[c] == t ? c : c + 1;
 }
 
+// baked coupling-table structure for a shape (TabNone: none)
+template <int D_IN, int D_OUT>
+struct BakedTab {
+    using type = TabNone;
+};
+template <>
+struct BakedTab<9, 9> {
+    using type = Tab9x9x9;
+};
+template <>
+struct BakedTab<4, 4> {
+    using type = Tab4x4x4;
+};
+
 // row split of the backward (l-aligned for the implicit layer-0 features so that a gw0 row never straddles
 // the two warps) and column split of the forward
 template <int D_IN, bool IMPLICIT>
@@ -275,6 +290,18 @@ __global__ void __launch_bounds__((2 * NCH + 1) * 32) tp_stream_kernel(const Str
             if (s_tab[n].y == threadIdx.x) s_jperm[pos++] = (uint16_t)n;
     }
     __syncthreads();
+
+    // ---- does the run-time table have the baked structure?  (then the per-centre contractions are straight-line code) ----
+    using TAB = typename BakedTab<D_IN, D_OUT>::type;
+    bool baked = false;
+    if constexpr (TAB::NNZ > 0) {
+        int ok = (nnz == TAB::NNZ && D == TAB::D_ENV) ? 1 : 0;
+        for (int n = threadIdx.x; n < TAB::NNZ && ok; n += blockDim.x) {
+            const uchar4 t4 = s_tab[n < nnz ? n : 0];
+            if (t4.x != TAB::I(n) || t4.y != TAB::J(n) || t4.z != TAB::K(n)) ok = 0;
+        }
+        baked = __syncthreads_and(ok) != 0 ;
+    }
 
     // ---- this CTA's contiguous range of centres / edges ----
     const int64_t G = gridDim.x, b = blockIdx.x;
@@ -438,6 +465,81 @@ __global__ void __launch_bounds__((2 * NCH + 1) * 32) tp_stream_kernel(const Str
             }
         };
 
+        // ---- baked-structure versions: every index below is a compile-time constant after unrolling ----
+        auto addM = [&](int ii, int kk, float v) {  // M[ii][kk] += v  (ii, kk local to this warp's rows / columns)
+            if (kk < 2 * KP) {
+                if (kk & 1) M2[ii][kk >> 1].y += v;
+                else M2[ii][kk >> 1].x += v;
+            } else {
+                Mr[ii] += v;
+            }
+        };
+        auto getGM = [&](int ii, int kk) -> float {
+            if constexpr (MODE == 1) {
+                if (kk < 2 * KP) return (kk & 1) ? gM2[ii][kk >> 1].y : gM2[ii][kk >> 1].x;
+                return gMr[ii];
+            } else {
+                return 0.f;
+            }
+        };
+        int parity_c = 0;  // alternates per centre: two scratch halves -> one barrier per centre
+        auto end_centre_baked = [&]() {
+            if constexpr (MODE == 1 && TAB::NNZ > 0) {
+                // partial ggamma[j] over the table entries whose row i belongs to this warp; the two halves meet in scratch
+                float gg[TAB::D_ENV];
+#pragma unroll
+                for (int j = 0; j < TAB::D_ENV; ++j) gg[j] = 0.f;
+#pragma unroll
+                for (int n = 0; n < TAB::NNZ; ++n) {
+                    const int ti = TAB::I(n), tj = TAB::J(n), tk = TAB::K(n);
+                    if (ti >= I0 && ti < I0 + NI) gg[tj] = fmaf(live ? __ldg(cgw + n * U + u) : 0.f, getGM(ti - I0, tk), gg[tj]);
+                }
+                float* sc = scr + parity_c * (TAB::D_ENV * 32);
+                if (ROLE == 1) {
+#pragma unroll
+                    for (int j = 0; j < TAB::D_ENV; ++j) sc[j * 32 + lane] = gg[j];
+                }
+                named_bar(1 + q, 64);
+                if (ROLE == 0 && live) {
+#pragma unroll
+                    for (int j = 0; j < TAB::D_ENV; ++j) ((TAcc*)p.ggamma)[(c * D + j) * U + u] = gg[j] + sc[j * 32 + lane];
+                }
+                parity_c ^= 1;
+            }
+        };
+        auto begin_centre_baked = [&]() {
+            if constexpr (TAB::NNZ > 0) {
+                mbar_wait(gfull_bar(gslot), gphase);
+                const int2 mt = s_meta[gslot];
+                c = mt.x;
+                row_end = mt.y;
+                zero_ggamma(c_prev, c);
+                c_prev = c;
+                const TAcc* __restrict__ gam = s_gam + (size_t)gslot * D * U + u;
+                float g[TAB::D_ENV];
+#pragma unroll
+                for (int j = 0; j < TAB::D_ENV; ++j) g[j] = live ? gam[j * U] : 0.f;
+                __syncwarp();
+                if (lane == 0) mbar_arrive(gempty_bar(gslot));
+                if (++gslot == NG) { gslot = 0; gphase ^= 1; }
+#pragma unroll
+                for (int i = 0; i < NI; ++i) {
+#pragma unroll
+                    for (int kp = 0; kp < KP; ++kp) {
+                        M2[i][kp] = make_float2(0.f, 0.f);
+                        if (MODE == 1) gM2[i][kp] = make_float2(0.f, 0.f);
+                    }
+                    if (KR) Mr[i] = 0.f;
+                    if (MODE == 1) gMr[i] = 0.f;
+                }
+#pragma unroll
+                for (int n = 0; n < TAB::NNZ; ++n) {
+                    const int ti = TAB::I(n), tj = TAB::J(n), tk = TAB::K(n);
+                    if (ti >= I0 && ti < I0 + NI && tk >= K0 && tk < K0 + NK) addM(ti - I0, tk - K0, (live ? __ldg(cgw + n * U + u) : 0.f) * g[tj]);
+                }
+            }
+        };
+
         // running per-lane output pointers (advanced by one edge row per iteration: no 64-bit multiplies in the loop)
         [[maybe_unused]] TAct* __restrict__ vout_p = MODE == 0 ? (TAct*)p.Vout + ((int64_t)e_lo * D_OUT + K0) * U + u : nullptr;
         [[maybe_unused]] TAct* __restrict__ gvin_p = (MODE == 1 && !IMPLICIT) ? (TAct*)p.gVin + ((int64_t)e_lo * D_IN + I0) * U + u : nullptr;
@@ -456,8 +558,13 @@ __global__ void __launch_bounds__((2 * NCH + 1) * 32) tp_stream_kernel(const Str
             int t = 0;
             while (t < n) {
                 if (za + t == row_end32) {  // warp-uniform: first edge of the next non-empty centre
-                    if (c >= 0) end_centre();
-                    begin_centre();
+                    if (baked) {
+                        if (c >= 0) end_centre_baked();
+                        begin_centre_baked();
+                    } else {
+                        if (c >= 0) end_centre();
+                        begin_centre();
+                    }
                     row_end32 = (int)row_end;
                 }
                 // edges of the current centre inside this stage: a branch-free run (unrolled for ILP)
@@ -602,7 +709,10 @@ __global__ void __launch_bounds__((2 * NCH + 1) * 32) tp_stream_kernel(const Str
             if (lane == 0) mbar_arrive(empty_bar(stage));
             if (++stage == NS) { stage = 0; phase ^= 1; }
         }
-        if (c >= 0) end_centre();
+        if (c >= 0) {
+            if (baked) end_centre_baked();
+            else end_centre();
+        }
         zero_ggamma(c_prev, c_hi);
     };
     if (role == 0) run(std::integral_constant<int, 0>{});

@@ -152,7 +152,7 @@ class FusedAllegroEnergy(torch.nn.Module):
                                      self.model_dtype, dev)
             import os
 
-            fold = self._core if os.environ.get("ALLEGRO_B200_FOLD_EMBED", "0") == "1" else None
+            fold = self._core if os.environ.get("ALLEGRO_B200_FOLD_EMBED", "1") == "1" else None  # default on (measured: -0.12 ms/step on c2)
             self._upstream = UpstreamPack(self.edge_norm, self.radial_chemical_embed, self.scalar_embed_mlp, self.model_dtype, dev,
                                           fold_embed_of=fold)
             self._core_key = key

@@ -285,7 +285,7 @@ class UpstreamPack:
         # fold_embed_of: x_emb only feeds two LINEAR maps (tensorembed.py:88-89 env_embed_linear, _allegro.py:251
         # first_layer_env_embed_projection), and the scalar-embed MLP ends in a linear layer, so their product is
         # one matrix: [w0 | x_0 | omega_0] = silu(h) @ (W_last @ W_embed).  One GEMM and the x_emb round trip less
-        # in each direction.  Opt-in (ALLEGRO_B200_FOLD_EMBED=1) until measured on the GPU.
+        # in each direction.  Default since round 2 (c2: 4.00 -> 3.88 ms/step); ALLEGRO_B200_FOLD_EMBED=0 switches it off.
         self.fold = fold_embed_of is not None
         self.mlp = PackedMLP(scalar_embed_mlp, dtype, device, post=fold_embed_of.embed.W64[0] if self.fold else None)
         self.dtype = dtype

@@ -49,10 +49,12 @@ def _run(name, stress=True):
     return rec, model.model._energy_and_forces(dict(rec["data"]), stress)
 
 
+@pytest.mark.parametrize("fold", ["1", "0"], ids=["fold", "nofold"])
 @pytest.mark.parametrize("name", model_case_ids())
-def test_host_pipeline_reproduces_reference(name, spec_kernels):
+def test_host_pipeline_reproduces_reference(name, fold, spec_kernels, monkeypatch):
+    monkeypatch.setenv("ALLEGRO_B200_FOLD_EMBED", fold)
     rec, out = _run(name)
-    tol = 1e-10 if rec["kwargs"]["model_dtype"] == "float64" else 2e-5
+    tol = 1e-10 if rec["kwargs"]["model_dtype"] == "float64" else 5e-5
     for key in ("atomic_energy", "forces", "edge_energy", "edge_features", "total_energy"):
         if key in rec:
             assert _rel(out[key], rec[key]) < tol, (key, _rel(out[key], rec[key]))
