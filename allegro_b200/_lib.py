@@ -48,6 +48,8 @@ _SIGNATURES = {
     "ab2_transpose_ui": ([_i32, _i64, _i32, _i32, _vp, _vp, _i32, _vp], C.c_int),
     "ab2_edge_vec": ([_i32, _i32, _i64, _vp, _vp, _vp, _vp, _vp, _vp], C.c_int),
     "ab2_radial_fwd": ([_i32, _i64, _i32, _i32, _dbl, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp], C.c_int),
+    "ab2_radial_pq_fwd": ([_i32, _i64, _i32, _i32, _dbl, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _vp], C.c_int),
+    "ab2_radial_pq_bwd": ([_i32, _i64, _i32, _i32, _dbl, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp], C.c_int),
     "ab2_nl_bin": ([_i32, _i64, _vp, _vp, _vp, _vp, _vp, _dbl, _vp, _vp], C.c_int),
     "ab2_nl_count": ([_i32, _i64, _vp, _vp, _vp, _vp, _vp, _dbl, _vp, _vp, _vp, _vp], C.c_int),
     "ab2_nl_fill": ([_i32, _i64, _vp, _vp, _vp, _vp, _vp, _dbl, _vp, _vp, _vp, _vp, _vp, _vp], C.c_int),
@@ -450,3 +452,21 @@ def neighbor_csr(pos: torch.Tensor, r_max: float, box, pbc=(True, True, True), o
             _check(load().ab2_nl_fill(dt, n_centres, _ptr(pos), g_box, g_org, g_pbc, g_nc, float(r_max), _ptr(cell_start), _ptr(order), _ptr(row_ptr),
                                       _ptr(nbr), _ptr(shift), _stream()))
     return row_ptr, nbr, shift
+
+
+def radial_pq_fwd(dtype, S: int, p_cut: float, vec, ctr, nbr, types, rmax_table, bessel_w, PQ) -> torch.Tensor:
+    """out[z][c] = sum_n B_n(x_z) PQ[t_c*T+t_n][n][c]  (ab2_radial_pq_fwd)."""
+    E = ctr.shape[0]
+    out = torch.empty(E, S, dtype=dtype, device=vec.device)
+    with _timed("radial_fwd"):
+        _check(load().ab2_radial_pq_fwd(DTYPE_ENUM[dtype], E, S, bessel_w.numel(), float(p_cut), _ptr(vec), _ptr(ctr), _ptr(nbr), _ptr(types),
+                                        _ptr(rmax_table), rmax_table.shape[0], _ptr(bessel_w), _ptr(_contig(PQ, "PQ")), _ptr(out), _stream()))
+    return out
+
+
+def radial_pq_bwd(dtype, S: int, p_cut: float, vec, ctr, nbr, types, rmax_table, bessel_w, PQ, g_out, aux, gvec):
+    E = ctr.shape[0]
+    with _timed("radial_bwd"):
+        _check(load().ab2_radial_pq_bwd(DTYPE_ENUM[dtype], E, S, bessel_w.numel(), float(p_cut), _ptr(vec), _ptr(ctr), _ptr(nbr), _ptr(types),
+                                        _ptr(rmax_table), rmax_table.shape[0], _ptr(bessel_w), _ptr(_contig(PQ, "PQ")), _ptr(_contig(g_out, "g_out")),
+                                        _ptr(_contig(aux, "aux")) if aux is not None else None, _ptr(gvec), _stream()))

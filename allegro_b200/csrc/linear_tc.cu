@@ -1078,10 +1078,11 @@ static bool tc_make_map(CUtensorMap* map, const void* ptr, int64_t ld, int width
               CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-static int tc_launch_tma(TcParams& p, int pf_mode, int w_bytes, int stage_bytes, int max_smem, unsigned grid, cudaStream_t st) {
+static int tc_launch_tma(TcParams& p, int pf_mode, int w_bytes, int stage_bytes, int max_smem, unsigned grid, cudaStream_t st, bool dry) {
     TmaMaps maps;
     memset(&maps, 0, sizeof(maps));
-    for (int s = 0; s < p.n_a; ++s) {
+    if (!tc_encode_fn()) return -1;
+    for (int s = 0; s < p.n_a && !dry; ++s) {
         if (!tc_make_map(&maps.a[s], p.a[s].ptr, p.a[s].ld, p.a[s].width, p.M)) return -1;
         if (p.a[s].aux && !tc_make_map(&maps.x[s], p.a[s].aux, p.a[s].aux_ld, p.a[s].width, p.M)) return -1;
     }
@@ -1097,6 +1098,7 @@ static int tc_launch_tma(TcParams& p, int pf_mode, int w_bytes, int stage_bytes,
         if (need <= (size_t)max_smem) { G = plans[q][0]; NR = plans[q][1]; nstage = plans[q][2]; smem = need; }
     }
     if (!G) return -1;
+    if (dry) return 0;
     p.nstage = nstage;
     auto go = [&](auto kern) -> int {
         if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
@@ -1120,7 +1122,7 @@ static int tc_launch_tma(TcParams& p, int pf_mode, int w_bytes, int stage_bytes,
 static int tc_launch_slice(int dtype, int64_t M, int K, int N, int n_a, const void* const* a_ptr, const int64_t* a_ld,
                            const int32_t* a_width, const void* const* a_aux, const int64_t* a_aux_ld, int act, const void* Whi, const void* Wlo,
                            int n_o, void* const* o_ptr, const int64_t* o_ld, const int32_t* o_width, const int32_t* o_accum, int epi,
-                           const void* aux, int64_t aux_ld, cudaStream_t st) {
+                           const void* aux, int64_t aux_ld, cudaStream_t st, bool dry = false) {
     const int has_aux = (act == AB2_ACT_MUL_DSILU && a_aux) ? 1 : 0;
     int pf_mode = 0;
     if (dtype == AB2_F32) {
@@ -1159,6 +1161,7 @@ static int tc_launch_slice(int dtype, int64_t M, int K, int N, int n_a, const vo
         if ((int)need <= max_smem) { raw_depth = plans[q][0]; nstage = plans[q][1]; smem = need; }
     }
     if (!nstage) return -1;
+    if (dry) return 0;
     p.nstage = nstage;
     p.raw_depth = raw_depth;
     p.pf_mode = pf_mode;
@@ -1168,7 +1171,7 @@ static int tc_launch_slice(int dtype, int64_t M, int K, int N, int n_a, const vo
     bool tma_ok = g_ab2_opt_linear_tma && split && K % KC == 0 && M < ((int64_t)1 << 31);
     for (int s = 0; s < n_a && tma_ok; ++s) tma_ok = a_width[s] % KC == 0;
     if (tma_ok) {
-        const int rc = tc_launch_tma(p, pf_mode, w_bytes, stage_bytes, max_smem, grid, st);
+        const int rc = tc_launch_tma(p, pf_mode, w_bytes, stage_bytes, max_smem, grid, st, dry);
         if (rc == 0) return 0;
     }
     auto go = [&](auto kern) -> int {
@@ -1208,6 +1211,17 @@ int ab2_linear_tc_try(int dtype, int64_t M, int K, int N, int n_a, const void* c
     const int nslices = (N + cap - 1) / cap;
     int width = ((N + nslices - 1) / nslices + 31) / 32 * 32;  // equal slices, multiples of 32 columns
     if (width > cap) width = cap;
+    // the slice must also leave room for the pipeline stages and the epilogue prefetch buffers: shrink until a plan fits
+    int32_t any_accum = 0;
+    for (int s = 0; s < n_o && o_accum; ++s) any_accum |= o_accum[s];
+    while (true) {
+        const int probe = width < N ? width : N;
+        if (tc_launch_slice(dtype, M, K, probe, n_a, a_ptr, a_ld, a_width, a_aux, a_aux_ld, act, Wpacked, Wpacked, 1, o_ptr, o_ld, &probe, &any_accum, epi,
+                            aux, aux_ld, st, /*dry=*/true) == 0)
+            break;
+        if (width <= 32) return -1;
+        width = (width / 2 + 31) / 32 * 32;
+    }
     const uint8_t* hi = reinterpret_cast<const uint8_t*>(Wpacked);
     const uint8_t* lo = hi + (size_t)Npad_full * K * 2;
     for (int n0 = 0; n0 < N; n0 += width) {

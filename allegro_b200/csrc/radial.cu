@@ -221,3 +221,183 @@ extern "C" int ab2_radial_bwd(int dtype, int64_t E, int S_rc, int num_bessels, d
     AB2_CUDA_LAUNCH_CHECK();
     return 0;
 }
+
+// ---------------------------------------------------------------------------------------
+// Radial embedding with per-type-pair matrices ("PQ" form), forward and adjoint:
+//
+//     out[z][c] = sum_n B_n(x_z) * PQ[t_c * T + t_n][n][c]
+//
+// The reference's product embedding (allegro/nn/_edgeembed.py:68-85) is the case PQ = typeemb(t_c,t_n)[c] * W_b[n][c];
+// since everything between the radial basis and the first nonlinearity is LINEAR (type-embedding product, first layer
+// of scalar_embed_mlp, allegro_models.py:153-183) the host can also fold that layer's weights in,
+//     PQ[t_c,t_n] = W_b diag(typeemb(t_c,t_n)) W_1        (nb x width),
+// and this kernel then emits the MLP's first pre-activation directly: the [E][S] embedding tensor and one GEMM per
+// direction disappear.  Structure: 256 edges per block; phase 1 one thread per edge evaluates the basis (and its
+// derivative) once into shared memory; phase 2 one warp per 32 CONSECUTIVE edges, lane = output column(s), the
+// nb x CPL matrix slice of the current type pair held in registers (reloaded only when the pair changes -- never for a
+// single-species system), so an edge costs nb*CPL FMAs + CPL coalesced stores.
+// ---------------------------------------------------------------------------------------
+template <typename TAct, typename TAcc, int NB, int CPL>
+__global__ void __launch_bounds__(256) radial_pq_fwd_kernel(int64_t E, int S, TAcc p, const TAcc* __restrict__ vec,
+                                                            const int32_t* __restrict__ ctr, const int32_t* __restrict__ nbr,
+                                                            const int32_t* __restrict__ types, const TAcc* __restrict__ rmax_table,
+                                                            int num_types, const TAcc* __restrict__ bw, const TAcc* __restrict__ PQ,
+                                                            TAct* __restrict__ out) {
+    __shared__ TAcc sB[NB][256];
+    __shared__ int s_pair[256];
+    const int t = threadIdx.x;
+    const int64_t z0 = (int64_t)blockIdx.x * 256;
+    {
+        const int64_t z = z0 + t;
+        TAcc B[NB];
+        int pair = 0;
+        if (z < E) {
+            const TAcc vx = vec[z * 3], vy = vec[z * 3 + 1], vz = vec[z * 3 + 2];
+            const TAcc r = sqrt(vx * vx + vy * vy + vz * vz);
+            const int tc = types[ctr[z]], tn = types[nbr[z]];
+            pair = tc * num_types + tn;
+            bessel_basis<TAcc, false>(r / rmax_table[pair], p, NB, bw, B, nullptr);
+        } else {
+#pragma unroll
+            for (int n = 0; n < NB; ++n) B[n] = TAcc(0);
+        }
+#pragma unroll
+        for (int n = 0; n < NB; ++n) sB[n][t] = B[n];
+        s_pair[t] = pair;
+    }
+    __syncthreads();
+    const int warp = t >> 5, lane = t & 31;
+    TAcc m[NB][CPL];
+    int cur = -1;
+    for (int e = warp * 32; e < warp * 32 + 32; ++e) {
+        const int64_t z = z0 + e;
+        if (z >= E) break;
+        const int pair = s_pair[e];
+        if (pair != cur) {  // warp-uniform
+            cur = pair;
+#pragma unroll
+            for (int n = 0; n < NB; ++n)
+#pragma unroll
+                for (int q = 0; q < CPL; ++q) m[n][q] = (lane + 32 * q < S) ? PQ[((int64_t)pair * NB + n) * S + lane + 32 * q] : TAcc(0);
+        }
+        TAcc acc[CPL];
+#pragma unroll
+        for (int q = 0; q < CPL; ++q) acc[q] = TAcc(0);
+#pragma unroll
+        for (int n = 0; n < NB; ++n) {
+            const TAcc b = sB[n][e];
+#pragma unroll
+            for (int q = 0; q < CPL; ++q) acc[q] += b * m[n][q];
+        }
+#pragma unroll
+        for (int q = 0; q < CPL; ++q)
+            if (lane + 32 * q < S) out[z * S + lane + 32 * q] = from_acc<TAct>(acc[q]);
+    }
+}
+
+// adjoint: gvec[z] += d out / d vec ^T (g_out[z] (* silu'(aux[z]) if aux))
+template <typename TAct, typename TAcc, int NB, int CPL>
+__global__ void __launch_bounds__(256) radial_pq_bwd_kernel(int64_t E, int S, TAcc p, const TAcc* __restrict__ vec,
+                                                            const int32_t* __restrict__ ctr, const int32_t* __restrict__ nbr,
+                                                            const int32_t* __restrict__ types, const TAcc* __restrict__ rmax_table,
+                                                            int num_types, const TAcc* __restrict__ bw, const TAcc* __restrict__ PQ,
+                                                            const TAct* __restrict__ g_out, const TAct* __restrict__ aux,
+                                                            TAcc* __restrict__ gvec) {
+    __shared__ TAcc sdB[NB][256];
+    __shared__ TAcc s_gx[256];
+    __shared__ int s_pair[256];
+    const int t = threadIdx.x;
+    const int64_t z0 = (int64_t)blockIdx.x * 256;
+    const int64_t zt = z0 + t;
+    TAcc vx = 0, vy = 0, vz = 0, r = 1, rmax = 1;
+    {
+        TAcc B[NB], dB[NB];
+        int pair = 0;
+        if (zt < E) {
+            vx = vec[zt * 3]; vy = vec[zt * 3 + 1]; vz = vec[zt * 3 + 2];
+            r = sqrt(vx * vx + vy * vy + vz * vz);
+            pair = types[ctr[zt]] * num_types + types[nbr[zt]];
+            rmax = rmax_table[pair];
+            bessel_basis<TAcc, true>(r / rmax, p, NB, bw, B, dB);
+        } else {
+#pragma unroll
+            for (int n = 0; n < NB; ++n) dB[n] = TAcc(0);
+        }
+#pragma unroll
+        for (int n = 0; n < NB; ++n) sdB[n][t] = dB[n];
+        s_pair[t] = pair;
+    }
+    __syncthreads();
+    const int warp = t >> 5, lane = t & 31;
+    TAcc m[NB][CPL];
+    int cur = -1;
+    for (int e = warp * 32; e < warp * 32 + 32; ++e) {
+        const int64_t z = z0 + e;
+        if (z >= E) break;
+        const int pair = s_pair[e];
+        if (pair != cur) {
+            cur = pair;
+#pragma unroll
+            for (int n = 0; n < NB; ++n)
+#pragma unroll
+                for (int q = 0; q < CPL; ++q) m[n][q] = (lane + 32 * q < S) ? PQ[((int64_t)pair * NB + n) * S + lane + 32 * q] : TAcc(0);
+        }
+        // gx = sum_n dB[n] sum_c g[c] m[n][c]: fold the n-sum per lane first, one warp reduction per edge
+        TAcc part = TAcc(0);
+#pragma unroll
+        for (int q = 0; q < CPL; ++q) {
+            const int c = lane + 32 * q;
+            if (c < S) {
+                TAcc g = to_acc<TAcc>(g_out[z * S + c]);
+                if (aux) g *= dsilu_f(to_acc<TAcc>(aux[z * S + c]));
+                TAcc s = TAcc(0);
+#pragma unroll
+                for (int n = 0; n < NB; ++n) s += sdB[n][e] * m[n][q];
+                part += g * s;
+            }
+        }
+        part = warp_sum(part);
+        if (lane == 0) s_gx[e] = part;
+    }
+    __syncthreads();
+    if (zt < E) {
+        const TAcc f = s_gx[t] / (rmax * r);  // dx/dr_vec = r_vec / (|r| r_max)
+        gvec[zt * 3] += f * vx;
+        gvec[zt * 3 + 1] += f * vy;
+        gvec[zt * 3 + 2] += f * vz;
+    }
+}
+
+#define AB2_RADIAL_PQ_DISPATCH(KERNEL, ...)                                                                       \
+    do {                                                                                                          \
+        const int cpl = (S + 31) / 32;                                                                            \
+        if (cpl == 1) { AB2_DISPATCH_DTYPE(dtype, KERNEL<TAct, TAcc, 8, 1><<<ab2_blocks(E, 256), 256, 0, st>>>(__VA_ARGS__)); } \
+        else if (cpl == 2) { AB2_DISPATCH_DTYPE(dtype, KERNEL<TAct, TAcc, 8, 2><<<ab2_blocks(E, 256), 256, 0, st>>>(__VA_ARGS__)); } \
+        else { AB2_DISPATCH_DTYPE(dtype, KERNEL<TAct, TAcc, 8, 4><<<ab2_blocks(E, 256), 256, 0, st>>>(__VA_ARGS__)); } \
+    } while (0)
+
+extern "C" int ab2_radial_pq_fwd(int dtype, int64_t E, int S, int num_bessels, double p_cut, const void* vec, const int32_t* ctr,
+                                 const int32_t* nbr, const int32_t* types, const void* rmax_table, int num_types, const void* bessel_w,
+                                 const void* PQ, void* out, void* stream) {
+    if (E == 0) return 0;
+    AB2_CHECK_ARG(vec && ctr && nbr && types && rmax_table && bessel_w && PQ && out, "null pointer");
+    AB2_CHECK_ARG(num_bessels == 8 && S > 0 && S <= 128, "radial_pq: 8 Bessel functions, at most 128 output columns");
+    cudaStream_t st = (cudaStream_t)stream;
+    AB2_RADIAL_PQ_DISPATCH(radial_pq_fwd_kernel, E, S, (TAcc)p_cut, (const TAcc*)vec, ctr, nbr, types, (const TAcc*)rmax_table, num_types,
+                           (const TAcc*)bessel_w, (const TAcc*)PQ, (TAct*)out);
+    AB2_CUDA_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int ab2_radial_pq_bwd(int dtype, int64_t E, int S, int num_bessels, double p_cut, const void* vec, const int32_t* ctr,
+                                 const int32_t* nbr, const int32_t* types, const void* rmax_table, int num_types, const void* bessel_w,
+                                 const void* PQ, const void* g_out, const void* aux, void* gvec, void* stream) {
+    if (E == 0) return 0;
+    AB2_CHECK_ARG(vec && ctr && nbr && types && rmax_table && bessel_w && PQ && g_out && gvec, "null pointer");
+    AB2_CHECK_ARG(num_bessels == 8 && S > 0 && S <= 128, "radial_pq: 8 Bessel functions, at most 128 output columns");
+    cudaStream_t st = (cudaStream_t)stream;
+    AB2_RADIAL_PQ_DISPATCH(radial_pq_bwd_kernel, E, S, (TAcc)p_cut, (const TAcc*)vec, ctr, nbr, types, (const TAcc*)rmax_table, num_types,
+                           (const TAcc*)bessel_w, (const TAcc*)PQ, (const TAct*)g_out, (const TAct*)aux, (TAcc*)gvec);
+    AB2_CUDA_LAUNCH_CHECK();
+    return 0;
+}

@@ -63,6 +63,24 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         "r"(parity)
         : "memory");
 }
+// Producer-side wait: the producer runs stages ahead, so a slow poll costs nothing -- but a tight try_wait loop on a
+// warp that is blocked most of the time steals issue slots from the consumer warps of the same sub-partition.
+__device__ __forceinline__ void mbar_wait_backoff(uint32_t bar, uint32_t parity) {
+    while (true) {
+        uint32_t ok;
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t"
+            "}"
+            : "=r"(ok)
+            : "r"(bar), "r"(parity)
+            : "memory");
+        if (ok) return;
+        __nanosleep(256);
+    }
+}
 __device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {
     uint32_t ok;
     asm volatile(
@@ -327,7 +345,7 @@ __global__ void __launch_bounds__((2 * NCH + 1) * 32) tp_stream_kernel(const Str
                 const int rb = p.row_ptr[c_iss], re = p.row_ptr[c_iss + 1];
                 if (rb >= look_end) break;
                 if (re > rb) {
-                    if (rb < issued_end) mbar_wait(gempty_bar(gslot), gphase ^ 1);
+                    if (rb < issued_end) mbar_wait_backoff(gempty_bar(gslot), gphase ^ 1);
                     else if (!mbar_test(gempty_bar(gslot), gphase ^ 1)) break;
                     s_meta[gslot] = make_int2((int)c_iss, re);
                     mbar_expect_tx(gfull_bar(gslot), gam_bytes);
@@ -340,7 +358,7 @@ __global__ void __launch_bounds__((2 * NCH + 1) * 32) tp_stream_kernel(const Str
         if (lane == 0) issue_gammas(e_lo, e_lo + TE);
         for (int64_t za = e_lo; za < e_hi; za += TE) {
             const int n = (int)((e_hi - za) < TE ? (e_hi - za) : TE);
-            if (lane == 0) mbar_wait(empty_bar(stage), phase ^ 1);
+            if (lane == 0) mbar_wait_backoff(empty_bar(stage), phase ^ 1);
             __syncwarp();
             uint8_t* sb = ring + (size_t)stage * pl.stage_bytes;
             if (lane == 0) {

@@ -309,6 +309,73 @@ class UpstreamPack:
         self.Wb = te.basis_linear.folded_weights()[0].to(device=device, dtype=acc).contiguous()
         self.cemb = te.center_embed.weight.detach().to(device=device, dtype=acc).contiguous()
         self.nemb = te.neighbor_embed.weight.detach().to(device=device, dtype=acc).contiguous()
+        # Per-type-pair matrices for ab2_radial_pq_*: PQ0[t_c,t_n][n][c] = typeemb(t_c,t_n)[c] * Wb[n][c] (the product embedding,
+        # _edgeembed.py:68-85).  Everything between the radial basis and the first SiLU is linear, so when the scalar-embed MLP
+        # has exactly one hidden layer its first weight matrix is folded in as well,  PQ = PQ0 @ W_1 : the radial kernel then
+        # emits the pre-activation h directly (no [E][S_rc] embedding tensor, one GEMM less per direction).
+        self.PQ, self.S_pq, self.fold_radial = None, 0, False
+        nb = int(self.bessel_w.numel())
+        import os as _os
+
+        if nb == 8 and _os.environ.get("ALLEGRO_B200_RADIAL_PQ", "1") == "1":
+            Wb64 = te.basis_linear.folded_weights()[0].detach().double().cpu()             # [nb, S_rc]
+            ce, ne = te.center_embed.weight.detach().double().cpu(), te.neighbor_embed.weight.detach().double().cpu()
+            T = ce.shape[0]
+            temb = torch.cat([ce.unsqueeze(1).expand(T, T, -1), ne.unsqueeze(0).expand(T, T, -1)], dim=-1)  # [tc, tn, S_rc]
+            PQ0 = temb.reshape(T * T, 1, -1) * Wb64.unsqueeze(0)                          # [T*T, nb, S_rc]
+            if self.mlp.is_two_layer_silu and self.mlp.dims[1] <= 128 and _os.environ.get("ALLEGRO_B200_FOLD_RADIAL", "1") == "1":
+                self.fold_radial = True
+                PQ0 = PQ0 @ self.mlp.W64[0]                                                # [T*T, nb, width]
+            if PQ0.shape[-1] <= 128:
+                self.PQ = PQ0.to(device=device, dtype=acc).contiguous()
+                self.S_pq = int(PQ0.shape[-1])
+            else:
+                self.fold_radial = False
+
+    # ---- forward / adjoint of the whole upstream scalar track -----------------------------------------------
+    def forward(self, vec, csr: EdgeCSR, types_i32, outs):
+        """vec [E,3] -> the scalar-embed MLP's outputs written into ``outs`` ([x_emb], or with the embed fold
+        [w0, x_0, omega_0]).  Returns what ``backward`` needs."""
+        dt = self.dtype
+        if self.kind == "spline":
+            from ._spline import spline_forward
+
+            t64 = types_i32.long()
+            e0, sp_saved = spline_forward(vec, t64[csr.ctr.long()], t64[csr.nbr.long()], self.rmax64, self.sp_lower, self.sp_upper, self.sp_const,
+                                          self.sp_w, self.num_types, dt)
+            return ("spline", sp_saved, self.mlp.forward([e0], outs))
+        if self.fold_radial:
+            h = _lib.radial_pq_fwd(dt, self.S_pq, self.p, vec, csr.ctr, csr.nbr, types_i32, self.rmax_table, self.bessel_w, self.PQ)
+            _lib.linear([h], self.mlp.W[1], outs, act=_lib.ACT_SILU, W_packed=self.mlp.Wp[1])
+            return ("pq_fold", None, [h])
+        if self.PQ is not None:
+            e0 = _lib.radial_pq_fwd(dt, self.S_pq, self.p, vec, csr.ctr, csr.nbr, types_i32, self.rmax_table, self.bessel_w, self.PQ)
+        else:
+            e0 = _lib.radial_fwd(dt, self.S_rc, self.p, vec, csr.ctr, csr.nbr, types_i32, self.rmax_table, self.bessel_w, self.Wb, self.cemb, self.nemb)
+        return ("bessel", None, self.mlp.forward([e0], outs))
+
+    def backward(self, saved, gouts, vec, csr: EdgeCSR, types_i32, gvec):
+        """gouts = gradients w.r.t. ``outs``; accumulates d/d vec into gvec."""
+        kind, sp_saved, pre = saved
+        dt = self.dtype
+        E = vec.shape[0]
+        if kind == "pq_fold":
+            g_h = self.mlp.hidden_grad(gouts)  # gradient w.r.t. silu(h); silu'(h) is applied by the radial adjoint (aux = h)
+            _lib.radial_pq_bwd(dt, self.S_pq, self.p, vec, csr.ctr, csr.nbr, types_i32, self.rmax_table, self.bessel_w, self.PQ, g_h, pre[0], gvec)
+            return
+        g_e0 = torch.empty(E, self.S_rc, dtype=dt, device=vec.device)
+        if self.mlp.is_two_layer_silu:
+            self.mlp.backward_plain(gouts, pre, [g_e0])
+        else:
+            self.mlp.backward(gouts, pre, [g_e0], [False])
+        if kind == "spline":
+            from ._spline import spline_backward
+
+            gvec += spline_backward(sp_saved, g_e0, self.sp_w, self.num_types).to(gvec.dtype)
+        elif self.PQ is not None:
+            _lib.radial_pq_bwd(dt, self.S_pq, self.p, vec, csr.ctr, csr.nbr, types_i32, self.rmax_table, self.bessel_w, self.PQ, g_e0, None, gvec)
+        else:
+            _lib.radial_bwd(dt, self.S_rc, self.p, vec, csr.ctr, csr.nbr, types_i32, self.rmax_table, self.bessel_w, self.Wb, self.cemb, self.nemb, g_e0, gvec)
 
 
 def energy_forces(core: "AllegroCore", up: UpstreamPack, csr: EdgeCSR, pos: torch.Tensor, types_i32: torch.Tensor,
@@ -328,36 +395,18 @@ def energy_forces(core: "AllegroCore", up: UpstreamPack, csr: EdgeCSR, pos: torc
                 torch.zeros(3, 3, dtype=acc, device=dev) if want_virial else None)
     _lib.set_tag("fwd.radial")
     vec = _lib.edge_vec(pos, csr.ctr, csr.nbr, shift_vec, acc)
-    sp_saved = None
-    if up.kind == "spline":
-        from ._spline import spline_backward, spline_forward
-
-        t64 = types_i32.long()
-        e0, sp_saved = spline_forward(vec, t64[csr.ctr.long()], t64[csr.nbr.long()], up.rmax64, up.sp_lower, up.sp_upper, up.sp_const,
-                                      up.sp_w, up.num_types, dt)
-    else:
-        e0 = _lib.radial_fwd(dt, up.S_rc, up.p, vec, csr.ctr, csr.nbr, types_i32, up.rmax_table, up.bessel_w, up.Wb, up.cemb, up.nemb)
     if up.fold:
-        pre_box = []
-        Ei, X, Ez, sv = core.forward(csr, vec, None, fill_embed=lambda w0, x0, om0: pre_box.append(up.mlp.forward([e0], [w0, x0, om0])))
-        pre_se = pre_box[0]
+        box = []
+        Ei, X, Ez, sv = core.forward(csr, vec, None, fill_embed=lambda w0, x0, om0: box.append(up.forward(vec, csr, types_i32, [w0, x0, om0])))
+        up_saved = box[0]
     else:
         x_emb = torch.empty(E, core.S_in, dtype=dt, device=pos.device)
-        pre_se = up.mlp.forward([e0], [x_emb])
+        up_saved = up.forward(vec, csr, types_i32, [x_emb])
         Ei, X, Ez, sv = core.forward(csr, vec, x_emb)
     gEi = gEi_scale if gEi_scale is not None else torch.ones_like(Ei)
     gvec, gx_emb = core.backward(sv, gEi)
-    gouts = gx_emb if up.fold else [gx_emb]
     _lib.set_tag("bwd.radial")
-    g_e0 = torch.empty(E, up.S_rc, dtype=dt, device=pos.device)
-    if up.mlp.is_two_layer_silu:
-        up.mlp.backward_plain(gouts, pre_se, [g_e0])
-    else:
-        up.mlp.backward(gouts, pre_se, [g_e0], [False])
-    if up.kind == "spline":
-        gvec += spline_backward(sp_saved, g_e0, up.sp_w, up.num_types).to(gvec.dtype)
-    else:
-        _lib.radial_bwd(dt, up.S_rc, up.p, vec, csr.ctr, csr.nbr, types_i32, up.rmax_table, up.bessel_w, up.Wb, up.cemb, up.nemb, g_e0, gvec)
+    up.backward(up_saved, gx_emb if up.fold else [gx_emb], vec, csr, types_i32, gvec)
     virial = (vec.T @ gvec.to(vec.dtype)) if want_virial else None
     F = _lib.force_scatter(gvec, csr, pos.shape[0])
     return Ei, F, X, Ez, virial

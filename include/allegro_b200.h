@@ -203,6 +203,20 @@ int ab2_nl_fill(int pos_dtype, int64_t n_centres, const void* pos, const double*
                 const int32_t* cell_start, const int32_t* order, const int32_t* row_ptr, int32_t* nbr,
                 void* shift, void* stream);
 
+/* Radial embedding with per-type-pair matrices: out[z][c] = sum_n B_n(x_z) PQ[t_c * T + t_n][n][c], B_n as above
+ * (num_bessels must be 8, S <= 128).  PQ: [T*T][8][S] in the accumulate dtype.  The product embedding above is
+ * PQ = typeemb(t_c,t_n)[c] * Wb[n][c]; because everything up to the first nonlinearity is linear
+ * (allegro/nn/_edgeembed.py:68-85, allegro_models.py:153-183) the host may fold the first scalar_embed_mlp layer in,
+ * PQ = Wb diag(typeemb) W_1, and receive that layer's pre-activation directly.
+ * bwd: gvec[z] += (d out / d vec)^T (g_out[z] * silu'(aux[z]))   (aux nullable = plain g_out). */
+int ab2_radial_pq_fwd(int dtype, int64_t E, int S, int num_bessels, double p_cut, const void* vec,
+                      const int32_t* ctr, const int32_t* nbr, const int32_t* types, const void* rmax_table,
+                      int num_types, const void* bessel_w, const void* PQ, void* out, void* stream);
+int ab2_radial_pq_bwd(int dtype, int64_t E, int S, int num_bessels, double p_cut, const void* vec,
+                      const int32_t* ctr, const int32_t* nbr, const int32_t* types, const void* rmax_table,
+                      int num_types, const void* bessel_w, const void* PQ, const void* g_out, const void* aux,
+                      void* gvec, void* stream);
+
 /* layout helpers between the reference strided layout [z][u][i] and the internal [z][i][u] */
 int ab2_transpose_ui(int dtype, int64_t E, int U, int d, const void* src, void* dst, int to_internal,
                      void* stream);

@@ -161,7 +161,7 @@ class AllegroOracle(torch.nn.Module):
         with torch.enable_grad():
             if has_cell:
                 cell0 = data[R.CELL_KEY].view(3, 3).to(pos.dtype)
-                disp = torch.zeros(3, 3, dtype=pos.dtype, requires_grad=True)
+                disp = torch.zeros(3, 3, dtype=pos.dtype, device=pos.device, requires_grad=True)
                 sym = 0.5 * (disp + disp.T)
                 data[R.POSITIONS_KEY] = pos + pos @ sym
                 data[R.CELL_KEY] = cell0 + cell0 @ sym

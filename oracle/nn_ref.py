@@ -49,7 +49,7 @@ _SILU_GAIN = silu_second_moment_gain()
 
 def scatter(src, index, dim_size: int):
     """nequip.nn.scatter(reduce='sum', dim=0): zero-initialised segment sum."""
-    out = torch.zeros((dim_size,) + tuple(src.shape[1:]), dtype=src.dtype)
+    out = torch.zeros((dim_size,) + tuple(src.shape[1:]), dtype=src.dtype, device=src.device)
     return out.index_add_(0, index, src)
 
 

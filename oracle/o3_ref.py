@@ -240,9 +240,9 @@ def _sh_recursive(lmax: int, x, y, z) -> List[torch.Tensor]:
     north = torch.tensor([0.0, 1.0, 0.0], dtype=torch.float64)
     ref = [torch.ones(1, dtype=torch.float64), s3 * north]
     for l in range(2, lmax + 1):
-        w = torch.from_numpy(np.array(wigner_3j(l - 1, 1, l))).to(x.dtype)
+        w = torch.from_numpy(np.array(wigner_3j(l - 1, 1, l))).to(dtype=x.dtype, device=x.device)
         raw = torch.einsum("ijk,...i,...j->...k", w, Ys[l - 1], y1)
-        rawref = torch.einsum("ijk,i,j->k", w.double(), ref[l - 1], ref[1])
+        rawref = torch.einsum("ijk,i,j->k", w.double().cpu(), ref[l - 1], ref[1])
         c = math.sqrt(2 * l + 1) / float(rawref.norm())
         Ys.append(c * raw)
         ref.append(c * rawref)
@@ -274,7 +274,7 @@ def spherical_harmonics(
         f = 1.0 / math.sqrt(2 * l + 1) if normalization == "norm" else 1.0 / math.sqrt(4 * math.pi)
         scale += [f] * (2 * l + 1)
     assert normalization in ("norm", "integral")
-    return out * torch.tensor(scale, dtype=out.dtype)
+    return out * torch.tensor(scale, dtype=out.dtype, device=out.device)
 
 
 # --------------------------------------------------------------------------- #

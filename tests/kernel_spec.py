@@ -180,5 +180,29 @@ def radial_bwd(dtype, S_rc, p_cut, vec, ctr, nbr, types, rmax_table, bessel_w, W
     gvec += g
 
 
-ALL = ("sh_fwd", "sh_bwd", "linear", "linear_pack", "env_sum", "env_bwd", "tp_fwd", "tp_bwd", "edge_sum", "edge_sum_bwd",
+def _radial_pq(p_cut, vec, ctr, nbr, types, rmax_table, bessel_w, PQ):
+    T = rmax_table.shape[0]
+    tc, tn = types.long()[ctr.long()], types.long()[nbr.long()]
+    x = (vec.norm(dim=-1) / rmax_table[tc, tn]).unsqueeze(-1)
+    bw = bessel_w.reshape(1, -1)
+    basis = torch.sinc(x * bw) * bw * R.polynomial_cutoff(x, float(p_cut))
+    return torch.einsum("zn,znc->zc", basis, PQ.reshape(T * T, bw.shape[1], -1)[tc * T + tn])
+
+
+def radial_pq_fwd(dtype, S, p_cut, vec, ctr, nbr, types, rmax_table, bessel_w, PQ):
+    return _radial_pq(p_cut, vec, ctr, nbr, types, rmax_table, bessel_w, PQ).to(dtype)
+
+
+def radial_pq_bwd(dtype, S, p_cut, vec, ctr, nbr, types, rmax_table, bessel_w, PQ, g_out, aux, gvec):
+    v = vec.detach().clone().requires_grad_(True)
+    g = g_out.to(vec.dtype)
+    if aux is not None:
+        g = g * _dsilu(aux.to(vec.dtype))
+    with torch.enable_grad():
+        out = _radial_pq(p_cut, v, ctr, nbr, types, rmax_table, bessel_w, PQ)
+        (gv,) = torch.autograd.grad(out, v, g)
+    gvec += gv
+
+
+ALL = ("radial_pq_fwd", "radial_pq_bwd", "sh_fwd", "sh_bwd", "linear", "linear_pack", "env_sum", "env_bwd", "tp_fwd", "tp_bwd", "edge_sum", "edge_sum_bwd",
        "force_scatter", "edge_vec", "radial_fwd", "radial_bwd")

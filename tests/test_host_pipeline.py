@@ -60,6 +60,18 @@ def test_host_pipeline_reproduces_reference(name, fold, spec_kernels, monkeypatc
             assert _rel(out[key], rec[key]) < tol, (key, _rel(out[key], rec[key]))
 
 
+@pytest.mark.parametrize("env", [{"ALLEGRO_B200_FOLD_RADIAL": "0"}, {"ALLEGRO_B200_RADIAL_PQ": "0"}, {"ALLEGRO_B200_FOLD_RADIAL": "0", "ALLEGRO_B200_FOLD_EMBED": "0"}],
+                         ids=["pq_nofold", "product_embed_kernel", "pq_nofold_noembedfold"])
+@pytest.mark.parametrize("name", ["c2_lmax2_L2", "c5_lmax3_L3_5species", "per_edge_type_cutoff"])
+def test_host_pipeline_radial_variants(name, env, spec_kernels, monkeypatch):
+    """The upstream scalar track with the first MLP layer folded into the radial kernel (default), with the per-type-pair
+    kernel but no fold, and with the round-1 product-embedding kernel: same energies and forces."""
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    rec, out = _run(name)
+    assert _rel(out["forces"], rec["forces"]) < 1e-10 and _rel(out["atomic_energy"], rec["atomic_energy"]) < 1e-10
+
+
 @pytest.mark.parametrize("name", ["c2_lmax2_L2", "c5_lmax3_L3_5species", "shared_irrep_weights", "spline_embed_reftest_cfg"])
 def test_host_pipeline_plain_backward_plan(name, spec_kernels, monkeypatch):
     """The alternative backward orchestration (producer-side SiLU', concat-K block gradients) gives the same forces."""

@@ -12,9 +12,9 @@ DEV = "cuda"
 
 def _edge_set(ctr, nbr, shift_vec, cell):
     """canonical sorted rows (centre, neighbour, integer image) for set comparison"""
-    inv = torch.linalg.inv(cell.double())
-    img = torch.round(shift_vec.double() @ inv).long()
-    rows = torch.cat([ctr.long().unsqueeze(1), nbr.long().unsqueeze(1), img], 1).cpu()
+    inv = torch.linalg.inv(cell.double().cpu())
+    img = torch.round(shift_vec.double().cpu() @ inv).long()
+    rows = torch.cat([ctr.long().cpu().unsqueeze(1), nbr.long().cpu().unsqueeze(1), img], 1)
     order = torch.arange(rows.shape[0])
     for c in (4, 3, 2, 1, 0):
         order = order[torch.argsort(rows[order, c], stable=True)]
@@ -53,7 +53,7 @@ def test_neighbor_csr_owned_centres_only():
     assert torch.equal(csr_own.nbr, csr_all.nbr[: csr_own.num_edges])
 
 
-@pytest.mark.parametrize("dtype,tol", [("float64", 1e-12), ("float32", 1e-5)])
+@pytest.mark.parametrize("dtype,tol", [("float64", 1e-12), ("float32", 1e-4)])  # rows come in a different order: fp32 sums differ
 def test_model_on_prepared_csr_equals_edge_index_route(dtype, tol):
     from test_gpu_model import _pair, _to_dev
 
@@ -80,8 +80,9 @@ def test_calculator_uses_the_cuda_list():
     assert D.CSR_KEY in calc._data and calc.num_edges > d[D.EDGE_INDEX_KEY].shape[1]  # skin list is larger
     ref = oracle(d)
     assert float((out["forces"].cpu() - ref[D.FORCE_KEY]).abs().max() / ref[D.FORCE_KEY].abs().max()) < 1e-9
-    p2 = dd[D.POSITIONS_KEY] + 0.05 * torch.randn_like(dd[D.POSITIONS_KEY])
-    out2 = calc.compute(p2)
+    p2 = dd[D.POSITIONS_KEY] + 0.03 * torch.randn_like(dd[D.POSITIONS_KEY]).clamp(-3, 3)
+    out2 = calc.compute(p2, dd[D.CELL_KEY])
+    assert calc.n_rebuilds == 1  # inside the skin: the captured graph was replayed on the new positions
     d2 = dict(d)
     d2[D.POSITIONS_KEY] = p2.cpu()
     ei, sh = D.neighbor_list(d2[D.POSITIONS_KEY], 5.0, d[D.CELL_KEY])

@@ -55,3 +55,37 @@ def test_radial_fwd_bwd_and_edge_vec(dtype, tol, S_rc, nb, T):
     gv = dev(gvec0.clone())
     _lib.radial_bwd(*args_dev, dev(g_e0), gv)                           # accumulates into gvec
     assert (gv.cpu().double() - gv_ref.double()).abs().max() < tol * float(gv_ref.abs().max()) * 10
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float64, 1e-11), (torch.float32, 1e-4), (torch.bfloat16, 2e-2)])
+@pytest.mark.parametrize("S,T,with_aux", [(64, 1, True), (128, 3, False), (16, 5, True), (100, 2, False)])
+def test_radial_pq_fwd_bwd(dtype, tol, S, T, with_aux):
+    """ab2_radial_pq_fwd / bwd (per-type-pair matrices, optional silu' factor in the adjoint) against the specification."""
+    acc = _lib.ACC_DTYPE[dtype]
+    nb = 8
+    g = torch.Generator().manual_seed(S + T)
+    n_atoms, E = 50, 1000      # > 3 blocks of 256 edges, last one partial
+    ctr = torch.sort(torch.randint(0, n_atoms, (E,), generator=g)).values.to(torch.int32)
+    nbr = torch.randint(0, n_atoms, (E,), generator=g).to(torch.int32)
+    types = torch.randint(0, T, (n_atoms,), generator=g).to(torch.int32)
+    vec = (torch.randn(E, 3, generator=g, dtype=torch.float64) * 2.0).to(acc)
+    rmax = (3.0 + 2.0 * torch.rand(T, T, generator=g, dtype=torch.float64)).to(acc)
+    bw = torch.linspace(1.0, nb, nb, dtype=torch.float64).to(acc)
+    PQ = (torch.randn(T * T, nb, S, generator=g, dtype=torch.float64) / nb**0.5).to(acc)
+    p_cut = 6.0
+
+    def dev(t):
+        return None if t is None else t.to(DEV)
+
+    ref = kernel_spec.radial_pq_fwd(torch.float64, S, p_cut, vec.double(), ctr, nbr, types, rmax.double(), bw.double(), PQ.double())
+    out = _lib.radial_pq_fwd(dtype, S, p_cut, dev(vec), dev(ctr), dev(nbr), dev(types), dev(rmax), dev(bw), dev(PQ))
+    assert (out.cpu().double() - ref).abs().max() < tol * float(ref.abs().max())
+    g_out = torch.randn(E, S, generator=g, dtype=torch.float64).to(dtype)
+    aux = torch.randn(E, S, generator=g, dtype=torch.float64).to(dtype) if with_aux else None
+    gvec0 = torch.randn(E, 3, generator=g, dtype=torch.float64).to(acc)
+    gv_ref = gvec0.double().clone()
+    kernel_spec.radial_pq_bwd(torch.float64, S, p_cut, vec.double(), ctr, nbr, types, rmax.double(), bw.double(), PQ.double(), g_out.double(),
+                              None if aux is None else aux.double(), gv_ref)
+    gv = dev(gvec0.clone())
+    _lib.radial_pq_bwd(dtype, S, p_cut, dev(vec), dev(ctr), dev(nbr), dev(types), dev(rmax), dev(bw), dev(PQ), dev(g_out), dev(aux), gv)
+    assert (gv.cpu().double() - gv_ref).abs().max() < (tol if dtype != torch.bfloat16 else 1e-4) * float(gv_ref.abs().max()) * 10

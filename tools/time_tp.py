@@ -80,6 +80,6 @@ for label, opts in VARIANTS:
         f = timeit(fwd)
         b = timeit(bwd)
         fb = (4 * nir * U + 4 * Dd if implicit else 4 * U * d_in) + 4 + 4 * U * d_out
-        bb = fb + 4 * U * d_out + (4 * nir * U + 8 * Dd if implicit else 4 * U * d_in)
+        bb = fb + (4 * nir * U + 8 * Dd if implicit else 4 * U * d_in)  # inputs + gVout (same size as Vout) + input gradients
         line += f"  {name}: fwd {f:5.0f}us ({fb*E/f/1e3:5.0f}GB/s) bwd {b:5.0f}us ({bb*E/b/1e3:5.0f}GB/s)"
     print(line, flush=True)
