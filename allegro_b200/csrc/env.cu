@@ -174,6 +174,8 @@ extern "C" int ab2_env_sum(int dtype, int lmax, int64_t N, int U, const int32_t*
 }
 
 extern int g_ab2_opt_tp_fast;
+int ab2_env_bwd_stream(int dtype, int lmax, int64_t N, int64_t E, int U, const int32_t* ctr, const void* Y, const void* w, int64_t w_ld,
+                       const void* ggamma, double sf, void* gw, int64_t gw_ld, void* gY, cudaStream_t st);
 
 extern "C" int ab2_env_bwd(int dtype, int lmax, int64_t N, int64_t E, int U, const int32_t* row_ptr, const int32_t* ctr, const void* Y,
                            const void* w, int64_t w_ld, const void* ggamma, double sf, void* gw, int64_t gw_ld, void* gY,
@@ -181,6 +183,10 @@ extern "C" int ab2_env_bwd(int dtype, int lmax, int64_t N, int64_t E, int U, con
     if (E == 0) return 0;
     AB2_CHECK_ARG(ctr && Y && w && ggamma && gw && gY && U > 0, "null pointer / U");
     cudaStream_t st = (cudaStream_t)stream;
+    if (g_ab2_opt_tp_fast && ab2_env_bwd_stream(dtype, lmax, N, E, U, ctr, Y, w, w_ld, ggamma, sf, gw, gw_ld, gY, st) == 0) {
+        AB2_CUDA_LAUNCH_CHECK();
+        return 0;
+    }
     if (g_ab2_opt_tp_fast && row_ptr && lmax <= 3) {
         // auto (0): split only when a centre needs several channel chunks (U = 64: 500 -> 345 us; U = 32: no gain)
         const int opt = g_ab2_opt_env_split ? g_ab2_opt_env_split : (U > 32 && dtype != AB2_F64 ? 4 : 1);

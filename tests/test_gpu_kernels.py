@@ -175,10 +175,14 @@ def test_linear_prologue_mul_dsilu(dtype, shape):
 
 
 @pytest.mark.parametrize("lmax", [1, 2, 3])
-@pytest.mark.parametrize("U", [4, 32, 48])
+@pytest.mark.parametrize("U", [4, 32, 48, 64])
 @pytest.mark.parametrize("dtype", [torch.float64, torch.float32, torch.bfloat16])
-@pytest.mark.parametrize("fastpath", [True, False])
+@pytest.mark.parametrize("fastpath", [True, False, "dense"])
 def test_env_sum_and_bwd(lmax, U, dtype, fastpath):
+    """fastpath "dense": contiguous w / gw rows, what the pipeline passes -- the TMA-staged streaming adjoint
+    (env_stream.cu) takes these; the strided views exercise the round-1 kernels."""
+    dense = fastpath == "dense"
+    fastpath = bool(fastpath)
     N, E = 37, 600
     csr, ctr = _csr_random(N, E, seed=U)
     g = torch.Generator().manual_seed(lmax * 10 + U)
@@ -206,8 +210,16 @@ def test_env_sum_and_bwd(lmax, U, dtype, fastpath):
     gY_ref, gw_ref = torch.autograd.grad(loss, (Yt, wt))
     gw = torch.zeros(E, n_ir * U + 1, device=DEV, dtype=dtype)
     gY = torch.ones(E, Dd, device=DEV, dtype=acc)
-    _lib.env_bwd(dtype, lmax, U, csr.ctr, Y.to(DEV, acc), wbuf.to(DEV, dtype)[:, 2 : 2 + n_ir * U], gg.to(DEV, acc), sf, gw[:, 1:], gY,
+    w_dev = wbuf.to(DEV, dtype)[:, 2 : 2 + n_ir * U]
+    gw_view = gw[:, 1:]
+    if dense:
+        w_dev = w_dev.contiguous()
+        gw_dense = torch.zeros(E, n_ir * U, device=DEV, dtype=dtype)
+        gw_view = gw_dense
+    _lib.env_bwd(dtype, lmax, U, csr.ctr, Y.to(DEV, acc), w_dev, gg.to(DEV, acc), sf, gw_view, gY,
                  row_ptr=csr.row_ptr if fastpath else None)
+    if dense:
+        gw[:, 1:] = gw_dense
     tol = {torch.float64: 1e-12, torch.float32: 1e-5, torch.bfloat16: 1e-2}[dtype]
     assert _rel(gw[:, 1:], gw_ref) < tol
     assert _rel(gY - 1.0, gY_ref) < (1e-5 if dtype != torch.float64 else 1e-12)
