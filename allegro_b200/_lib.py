@@ -50,6 +50,17 @@ _SIGNATURES = {
     "ab2_radial_fwd": ([_i32, _i64, _i32, _i32, _dbl, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp], C.c_int),
     "ab2_radial_pq_fwd": ([_i32, _i64, _i32, _i32, _dbl, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _vp], C.c_int),
     "ab2_radial_pq_bwd": ([_i32, _i64, _i32, _i32, _dbl, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp], C.c_int),
+    "ab2_p2p_mailbox_bytes": ([_i32, _i32], C.c_int64),
+    "ab2_p2p_alloc": ([_i64, C.POINTER(C.c_void_p)], C.c_int),
+    "ab2_p2p_free": ([_vp], C.c_int),
+    "ab2_p2p_get_handle": ([_vp, _vp], C.c_int),
+    "ab2_p2p_open_handle": ([_vp, C.POINTER(C.c_void_p)], C.c_int),
+    "ab2_p2p_close_handle": ([_vp], C.c_int),
+    "ab2_p2p_error": ([_vp, _i32, _i32, _vp], C.c_int),
+    "ab2_p2p_begin": ([_vp, _vp], C.c_int),
+    "ab2_p2p_push_rows": ([_i32, _i32, _i32, _vp, _vp, _i32, _dbl, _vp, _i32, _i32, _vp, _vp, _vp], C.c_int),
+    "ab2_p2p_wait_unpack": ([_i32, _i32, _i32, _vp, _i32, _i32, _vp, _i32, _vp, _vp, _i32, _vp], C.c_int),
+    "ab2_p2p_allreduce_energy": ([_vp, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp], C.c_int),
     "ab2_nl_bin": ([_i32, _i64, _vp, _vp, _vp, _vp, _vp, _dbl, _vp, _vp], C.c_int),
     "ab2_nl_count": ([_i32, _i64, _vp, _vp, _vp, _vp, _vp, _dbl, _vp, _vp, _vp, _vp], C.c_int),
     "ab2_nl_fill": ([_i32, _i64, _vp, _vp, _vp, _vp, _vp, _dbl, _vp, _vp, _vp, _vp, _vp, _vp], C.c_int),

@@ -295,77 +295,60 @@ __global__ void __launch_bounds__(256) radial_pq_fwd_kernel(int64_t E, int S, TA
     }
 }
 
-// adjoint: gvec[z] += d out / d vec ^T (g_out[z] (* silu'(aux[z]) if aux))
+// adjoint: gvec[z] += d out / d vec ^T (g_out[z] (* silu'(aux[z]) if aux)).
+// ONE THREAD PER EDGE end to end: gx = sum_c g[c] * sum_n dB_n * PQ[pair][n][c] needs no cross-lane reduction when the
+// thread walks its own row (S contiguous values, 16-byte loads, all independent -> deep memory-level parallelism),
+// and the PQ entries are warp-uniform broadcasts (same type pair for most lanes; L1-resident 2-4 KB per pair).
+// The first version (warp per edge, lane = column) serialised 32 edges per warp behind a load -> shuffle-reduce chain.
 template <typename TAct, typename TAcc, int NB, int CPL>
-__global__ void __launch_bounds__(256) radial_pq_bwd_kernel(int64_t E, int S, TAcc p, const TAcc* __restrict__ vec,
+__global__ void __launch_bounds__(128) radial_pq_bwd_kernel(int64_t E, int S, TAcc p, const TAcc* __restrict__ vec,
                                                             const int32_t* __restrict__ ctr, const int32_t* __restrict__ nbr,
                                                             const int32_t* __restrict__ types, const TAcc* __restrict__ rmax_table,
                                                             int num_types, const TAcc* __restrict__ bw, const TAcc* __restrict__ PQ,
                                                             const TAct* __restrict__ g_out, const TAct* __restrict__ aux,
                                                             TAcc* __restrict__ gvec) {
-    __shared__ TAcc sdB[NB][256];
-    __shared__ TAcc s_gx[256];
-    __shared__ int s_pair[256];
-    const int t = threadIdx.x;
-    const int64_t z0 = (int64_t)blockIdx.x * 256;
-    const int64_t zt = z0 + t;
-    TAcc vx = 0, vy = 0, vz = 0, r = 1, rmax = 1;
-    {
-        TAcc B[NB], dB[NB];
-        int pair = 0;
-        if (zt < E) {
-            vx = vec[zt * 3]; vy = vec[zt * 3 + 1]; vz = vec[zt * 3 + 2];
-            r = sqrt(vx * vx + vy * vy + vz * vz);
-            pair = types[ctr[zt]] * num_types + types[nbr[zt]];
-            rmax = rmax_table[pair];
-            bessel_basis<TAcc, true>(r / rmax, p, NB, bw, B, dB);
-        } else {
+    const int64_t z = (int64_t)blockIdx.x * 128 + threadIdx.x;
+    if (z >= E) return;
+    const TAcc vx = vec[z * 3], vy = vec[z * 3 + 1], vz = vec[z * 3 + 2];
+    const TAcc r = sqrt(vx * vx + vy * vy + vz * vz);
+    const int pair = types[ctr[z]] * num_types + types[nbr[z]];
+    const TAcc rmax = rmax_table[pair];
+    TAcc B[NB], dB[NB];
+    bessel_basis<TAcc, true>(r / rmax, p, NB, bw, B, dB);
+    const TAcc* __restrict__ m = PQ + (int64_t)pair * NB * S;
+    const TAct* __restrict__ g = g_out + z * S;
+    const TAct* __restrict__ a = aux ? aux + z * S : nullptr;
+    TAcc gx = TAcc(0);
+    constexpr int V = 16 / (int)sizeof(TAct);  // elements per 16-byte load
+    if (S % V == 0) {
+        for (int c0 = 0; c0 < S; c0 += V) {
+            TAct gv[V], av[V];
+            *reinterpret_cast<uint4*>(gv) = *reinterpret_cast<const uint4*>(g + c0);
+            if (a) *reinterpret_cast<uint4*>(av) = *reinterpret_cast<const uint4*>(a + c0);
 #pragma unroll
-            for (int n = 0; n < NB; ++n) dB[n] = TAcc(0);
-        }
+            for (int k = 0; k < V; ++k) {
+                TAcc gc = to_acc<TAcc>(gv[k]);
+                if (a) gc *= dsilu_f(to_acc<TAcc>(av[k]));
+                TAcc sN = TAcc(0);
 #pragma unroll
-        for (int n = 0; n < NB; ++n) sdB[n][t] = dB[n];
-        s_pair[t] = pair;
-    }
-    __syncthreads();
-    const int warp = t >> 5, lane = t & 31;
-    TAcc m[NB][CPL];
-    int cur = -1;
-    for (int e = warp * 32; e < warp * 32 + 32; ++e) {
-        const int64_t z = z0 + e;
-        if (z >= E) break;
-        const int pair = s_pair[e];
-        if (pair != cur) {
-            cur = pair;
-#pragma unroll
-            for (int n = 0; n < NB; ++n)
-#pragma unroll
-                for (int q = 0; q < CPL; ++q) m[n][q] = (lane + 32 * q < S) ? PQ[((int64_t)pair * NB + n) * S + lane + 32 * q] : TAcc(0);
-        }
-        // gx = sum_n dB[n] sum_c g[c] m[n][c]: fold the n-sum per lane first, one warp reduction per edge
-        TAcc part = TAcc(0);
-#pragma unroll
-        for (int q = 0; q < CPL; ++q) {
-            const int c = lane + 32 * q;
-            if (c < S) {
-                TAcc g = to_acc<TAcc>(g_out[z * S + c]);
-                if (aux) g *= dsilu_f(to_acc<TAcc>(aux[z * S + c]));
-                TAcc s = TAcc(0);
-#pragma unroll
-                for (int n = 0; n < NB; ++n) s += sdB[n][e] * m[n][q];
-                part += g * s;
+                for (int n = 0; n < NB; ++n) sN += dB[n] * __ldg(m + n * S + c0 + k);
+                gx += gc * sN;
             }
         }
-        part = warp_sum(part);
-        if (lane == 0) s_gx[e] = part;
+    } else {
+        for (int c = 0; c < S; ++c) {
+            TAcc gc = to_acc<TAcc>(g[c]);
+            if (a) gc *= dsilu_f(to_acc<TAcc>(a[c]));
+            TAcc sN = TAcc(0);
+#pragma unroll
+            for (int n = 0; n < NB; ++n) sN += dB[n] * __ldg(m + n * S + c);
+            gx += gc * sN;
+        }
     }
-    __syncthreads();
-    if (zt < E) {
-        const TAcc f = s_gx[t] / (rmax * r);  // dx/dr_vec = r_vec / (|r| r_max)
-        gvec[zt * 3] += f * vx;
-        gvec[zt * 3 + 1] += f * vy;
-        gvec[zt * 3 + 2] += f * vz;
-    }
+    const TAcc f = gx / (rmax * r);  // dx/dr_vec = r_vec / (|r| r_max)
+    gvec[z * 3] += f * vx;
+    gvec[z * 3 + 1] += f * vy;
+    gvec[z * 3 + 2] += f * vz;
 }
 
 #define AB2_RADIAL_PQ_DISPATCH(KERNEL, ...)                                                                       \
@@ -396,8 +379,9 @@ extern "C" int ab2_radial_pq_bwd(int dtype, int64_t E, int S, int num_bessels, d
     AB2_CHECK_ARG(vec && ctr && nbr && types && rmax_table && bessel_w && PQ && g_out && gvec, "null pointer");
     AB2_CHECK_ARG(num_bessels == 8 && S > 0 && S <= 128, "radial_pq: 8 Bessel functions, at most 128 output columns");
     cudaStream_t st = (cudaStream_t)stream;
-    AB2_RADIAL_PQ_DISPATCH(radial_pq_bwd_kernel, E, S, (TAcc)p_cut, (const TAcc*)vec, ctr, nbr, types, (const TAcc*)rmax_table, num_types,
-                           (const TAcc*)bessel_w, (const TAcc*)PQ, (const TAct*)g_out, (const TAct*)aux, (TAcc*)gvec);
+    AB2_DISPATCH_DTYPE(dtype, radial_pq_bwd_kernel<TAct, TAcc, 8, 1><<<ab2_blocks(E, 128), 128, 0, st>>>(
+                                  E, S, (TAcc)p_cut, (const TAcc*)vec, ctr, nbr, types, (const TAcc*)rmax_table, num_types, (const TAcc*)bessel_w,
+                                  (const TAcc*)PQ, (const TAct*)g_out, (const TAct*)aux, (TAcc*)gvec));
     AB2_CUDA_LAUNCH_CHECK();
     return 0;
 }

@@ -166,19 +166,133 @@ class SlabDecomposition:
         return n * 3 * itemsize
 
 
+class P2PHalo:
+    """The three per-step exchanges over NVLink peer memory (csrc/halo_p2p.cu): every rank owns a mailbox that its peers
+    map through CUDA IPC; senders store rows straight into the receiver's mailbox and publish the step number, receivers
+    spin on it.  Kernels only -- the step stays one CUDA graph and makes no NCCL call.  Set-up (once) uses
+    torch.distributed to exchange the IPC handles."""
+
+    def __init__(self, dec: SlabDecomposition, device):
+        import ctypes as C
+
+        from . import _lib
+
+        self._lib, self._C = _lib, C
+        self.dec, self.dev = dec, torch.device(device)
+        lib = _lib.load()
+        world, rank = dec.world, dec.rank
+        mx = torch.tensor([max(int(dec.send_right_idx.shape[0]), int(dec.send_left_idx.shape[0]), dec.n_ghost_left, dec.n_ghost_right, 1)],
+                          device=self.dev)
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        self.max_rows = int(mx)
+        nbytes = int(lib.ab2_p2p_mailbox_bytes(self.max_rows, world))
+        ptr = C.c_void_p()
+        _lib._check(lib.ab2_p2p_alloc(nbytes, C.byref(ptr)))
+        self.mailbox = ptr.value
+        hbuf = C.create_string_buffer(64)
+        _lib._check(lib.ab2_p2p_get_handle(C.c_void_p(self.mailbox), hbuf))
+        handles = [None] * world
+        dist.all_gather_object(handles, bytes(hbuf.raw))
+        self.peers = []
+        for r, h in enumerate(handles):
+            if r == rank:
+                self.peers.append(self.mailbox)
+            else:
+                q = C.c_void_p()
+                _lib._check(lib.ab2_p2p_open_handle(C.create_string_buffer(h, 64), C.byref(q)))
+                self.peers.append(q.value)
+        self.peers_dev = torch.tensor(self.peers, dtype=torch.int64, device=self.dev)
+        self.step = torch.zeros(1, dtype=torch.int32, device=self.dev)
+        self.done = torch.zeros(4, dtype=torch.int32, device=self.dev)
+        self.e_tot = torch.zeros(1, dtype=torch.float64, device=self.dev)
+        self.pos_local = None
+        self.send_right = dec.send_right_idx.to(self.dev).contiguous()
+        self.send_left = dec.send_left_idx.to(self.dev).contiguous()
+        # periodic wrap along x as the RECEIVER sees my atoms (rank 0's left ghosts sit at x - Lx, ...)
+        self.shift_to_right = -dec.Lx if rank == world - 1 else 0.0
+        self.shift_to_left = dec.Lx if rank == 0 else 0.0
+        torch.cuda.synchronize(self.dev)
+        dist.barrier()
+
+    def _ptr(self, t, row_offset=0):
+        return self._C.c_void_p(t.data_ptr() + row_offset * 3 * t.element_size())
+
+    def forward(self, pos_owned: torch.Tensor) -> torch.Tensor:
+        """positions of my atoms -> [owned | ghosts from the left | ghosts from the right] (static buffer)."""
+        lib, dec, C = self._lib.load(), self.dec, self._C
+        st = self._lib._stream()
+        dt = self._lib.DTYPE_ENUM[pos_owned.dtype]
+        if self.pos_local is None or self.pos_local.dtype != pos_owned.dtype:
+            self.pos_local = torch.zeros(dec.n_owned + dec.n_ghost, 3, dtype=pos_owned.dtype, device=self.dev)
+        pos_owned = pos_owned.contiguous()
+        self.pos_local[: dec.n_owned].copy_(pos_owned)
+        ck = self._lib._check
+        ck(lib.ab2_p2p_begin(C.c_void_p(self.step.data_ptr()), st))
+        # I am the LEFT neighbour of my right peer (its slot 0) and the RIGHT neighbour of my left peer (its slot 1)
+        ck(lib.ab2_p2p_push_rows(dt, 0, 0, self._ptr(pos_owned), C.c_void_p(self.send_right.data_ptr()), int(self.send_right.shape[0]), self.shift_to_right,
+                                 C.c_void_p(self.peers[dec.right]), self.max_rows, dec.world, C.c_void_p(self.step.data_ptr()),
+                                 C.c_void_p(self.done.data_ptr()), st))
+        ck(lib.ab2_p2p_push_rows(dt, 0, 1, self._ptr(pos_owned), C.c_void_p(self.send_left.data_ptr()), int(self.send_left.shape[0]), self.shift_to_left,
+                                 C.c_void_p(self.peers[dec.left]), self.max_rows, dec.world, C.c_void_p(self.step.data_ptr()),
+                                 C.c_void_p(self.done.data_ptr() + 4), st))
+        ck(lib.ab2_p2p_wait_unpack(dt, 0, 0, C.c_void_p(self.mailbox), self.max_rows, dec.world, C.c_void_p(self.step.data_ptr()), dec.n_ghost_left,
+                                   self._ptr(self.pos_local, dec.n_owned), None, 0, st))
+        ck(lib.ab2_p2p_wait_unpack(dt, 0, 1, C.c_void_p(self.mailbox), self.max_rows, dec.world, C.c_void_p(self.step.data_ptr()), dec.n_ghost_right,
+                                   self._ptr(self.pos_local, dec.n_owned + dec.n_ghost_left), None, 0, st))
+        self._lib.PROF.launches += 5
+        return self.pos_local
+
+    def reverse(self, g_local: torch.Tensor, g_owned: torch.Tensor) -> torch.Tensor:
+        """gradients accumulated on my ghosts go back to their owners; what my neighbours accumulated on my boundary atoms
+        is added into g_owned (left neighbour's rows first, then the right one's: fixed order)."""
+        lib, dec, C = self._lib.load(), self.dec, self._C
+        st = self._lib._stream()
+        dt = self._lib.DTYPE_ENUM[g_local.dtype]
+        g_local = g_local.contiguous()
+        ck = self._lib._check
+        ck(lib.ab2_p2p_push_rows(dt, 1, 1, self._ptr(g_local, dec.n_owned), None, dec.n_ghost_left, 0.0, C.c_void_p(self.peers[dec.left]), self.max_rows,
+                                 dec.world, C.c_void_p(self.step.data_ptr()), C.c_void_p(self.done.data_ptr() + 8), st))
+        ck(lib.ab2_p2p_push_rows(dt, 1, 0, self._ptr(g_local, dec.n_owned + dec.n_ghost_left), None, dec.n_ghost_right, 0.0,
+                                 C.c_void_p(self.peers[dec.right]), self.max_rows, dec.world, C.c_void_p(self.step.data_ptr()),
+                                 C.c_void_p(self.done.data_ptr() + 12), st))
+        dto = self._lib.DTYPE_ENUM[g_owned.dtype]
+        ck(lib.ab2_p2p_wait_unpack(dto, 1, 0, C.c_void_p(self.mailbox), self.max_rows, dec.world, C.c_void_p(self.step.data_ptr()),
+                                   int(self.send_left.shape[0]), self._ptr(g_owned), C.c_void_p(self.send_left.data_ptr()), 1, st))
+        ck(lib.ab2_p2p_wait_unpack(dto, 1, 1, C.c_void_p(self.mailbox), self.max_rows, dec.world, C.c_void_p(self.step.data_ptr()),
+                                   int(self.send_right.shape[0]), self._ptr(g_owned), C.c_void_p(self.send_right.data_ptr()), 1, st))
+        self._lib.PROF.launches += 4
+        return g_owned
+
+    def energy(self, e_local: torch.Tensor) -> torch.Tensor:
+        """sum of one fp64 scalar over all ranks, in rank order (bitwise identical everywhere)."""
+        lib, dec, C = self._lib.load(), self.dec, self._C
+        self._e_in = e_local.detach().double().reshape(1).contiguous()
+        self._lib._check(lib.ab2_p2p_allreduce_energy(C.c_void_p(self._e_in.data_ptr()), dec.rank, dec.world, self.max_rows,
+                                                      C.c_void_p(self.peers_dev.data_ptr()), C.c_void_p(self.mailbox), C.c_void_p(self.step.data_ptr()),
+                                                      C.c_void_p(self.e_tot.data_ptr()), self._lib._stream()))
+        self._lib.PROF.launches += 2
+        return self.e_tot
+
+    def error(self) -> int:
+        return int(self._lib.load().ab2_p2p_error(self._C.c_void_p(self.mailbox), self.max_rows, self.dec.world, self._lib._stream()))
+
+
 class DistributedAllegro:
     """Energy + forces of a slab-decomposed frame.  ``energy_model(data) -> data`` must write
     ``atomic_energy`` for the local atoms (owned first) and be differentiable w.r.t. ``pos``
     (FusedAllegroEnergy on the GPU; any stand-in in the CPU tests)."""
 
-    def __init__(self, energy_model: Callable[[D.Type], D.Type], dec: SlabDecomposition):
-        self.model, self.dec = energy_model, dec
+    def __init__(self, energy_model: Callable[[D.Type], D.Type], dec: SlabDecomposition, p2p: Optional["P2PHalo"] = None):
+        self.model, self.dec, self.p2p = energy_model, dec, p2p
 
     def __call__(self, pos_owned: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
         """-> (total energy [all ranks], forces on owned atoms [n_owned,3], owned atomic energies)."""
         dec = self.dec
-        ghosts = dec.exchange_forward(pos_owned.detach())
-        pos_local = torch.cat([pos_owned.detach(), ghosts], 0).requires_grad_(True)
+        if self.p2p is not None:
+            pos_local = self.p2p.forward(pos_owned.detach())
+        else:
+            ghosts = dec.exchange_forward(pos_owned.detach())
+            pos_local = torch.cat([pos_owned.detach(), ghosts], 0).requires_grad_(True)
         data = {D.POSITIONS_KEY: pos_local, D.ATOM_TYPE_KEY: dec.types_local, D.CELL_KEY: dec.cell}
         if dec.csr is not None:
             data[D.CSR_KEY], data[D.EDGE_SHIFT_VEC_KEY] = dec.csr, dec.shift_vec
@@ -198,6 +312,10 @@ class DistributedAllegro:
                 e_local = e_atoms.sum()
                 (g,) = torch.autograd.grad(e_local, pos_local)
         g_owned = g[: dec.n_owned].clone()
+        if self.p2p is not None:
+            self.p2p.reverse(g, g_owned)
+            e_tot = self.p2p.energy(e_local)
+            return e_tot, -g_owned, e_atoms.detach()
         dec.exchange_reverse(g[dec.n_owned :].contiguous(), g_owned)
         e_tot = e_local.detach().double().clone().reshape(1)
         dist.all_reduce(e_tot)

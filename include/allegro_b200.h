@@ -217,6 +217,31 @@ int ab2_radial_pq_bwd(int dtype, int64_t E, int S, int num_bessels, double p_cut
                       int num_types, const void* bessel_w, const void* PQ, const void* g_out, const void* aux,
                       void* gvec, void* stream);
 
+/* ---- ghost-atom halo exchange over NVLink peer memory ------------------- */
+
+/* One mailbox per rank (cudaMalloc'ed here so that it can be exported through CUDA IPC), mapped by its peers.
+ * Per step: ab2_p2p_begin (bumps the step counter), ab2_p2p_push_rows into the neighbours' mailboxes (positions of
+ * my boundary atoms / gradients of my ghosts), ab2_p2p_wait_unpack of what they pushed into mine, and
+ * ab2_p2p_allreduce_energy -- kernels only (peer stores + system-scope release/acquire flags), so the whole step
+ * including the halo replays from one CUDA graph with no NCCL call.  Waits are bounded (~2 s): a protocol error sets
+ * the mailbox's error word (ab2_p2p_error) instead of hanging the GPU.  There is no reference counterpart (the
+ * reference leaves domain decomposition to LAMMPS' MPI, allegro/_compile.py:41-61 only defines the ghost format). */
+int64_t ab2_p2p_mailbox_bytes(int max_rows, int world);
+int ab2_p2p_alloc(int64_t bytes, void** ptr);
+int ab2_p2p_free(void* ptr);
+int ab2_p2p_get_handle(void* ptr, void* handle64_host);
+int ab2_p2p_open_handle(const void* handle64_host, void** ptr);
+int ab2_p2p_close_handle(void* ptr);
+int ab2_p2p_error(void* my_mailbox, int max_rows, int world, void* stream);
+int ab2_p2p_begin(void* step_counter, void* stream);
+int ab2_p2p_push_rows(int src_dtype, int kind, int side, const void* src, const int64_t* idx, int n, double shift_x,
+                      void* peer_mailbox, int max_rows, int world, const void* step_counter, void* done_counter,
+                      void* stream);
+int ab2_p2p_wait_unpack(int dst_dtype, int kind, int side, void* my_mailbox, int max_rows, int world,
+                        const void* step_counter, int n, void* dst, const int64_t* idx, int accumulate, void* stream);
+int ab2_p2p_allreduce_energy(const void* e_local, int rank, int world, int max_rows, void* const* peers_dev,
+                             void* my_mailbox, const void* step_counter, void* e_total, void* stream);
+
 /* layout helpers between the reference strided layout [z][u][i] and the internal [z][i][u] */
 int ab2_transpose_ui(int dtype, int64_t E, int U, int d, const void* src, void* dst, int to_internal,
                      void* stream);

@@ -17,7 +17,7 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, q):
+def _worker(rank, world, port, q, mode="nccl", reps=(6, 3, 3)):
     import torch.distributed as dist
 
     from allegro_b200 import systems
@@ -29,13 +29,20 @@ def _worker(rank, world, port, q):
     torch.cuda.set_device(dev)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
     try:
-        pos, cell, types = systems.make_positions("c2", (6, 3, 3))
+        pos, cell, types = systems.make_positions("c2", reps)
         kw = systems.model_kwargs("c2", 42.0, "float64")
         model = AllegroModel(**kw).to(dev).model
-        dec = SlabDecomposition(pos, cell, types, 5.0, rank, world)
+        # "p2p": NVLink peer-memory halo (no NCCL per step) + CUDA neighbour list straight into CSR
+        dec = SlabDecomposition(pos, cell, types, 5.0, rank, world, device=dev if mode == "p2p" else None)
         pos_owned = dec.local_positions_from_global(pos)[: dec.n_owned].to(dev)
         dec.to(dev)
-        runner = DistributedAllegro(model, dec)
+        p2p = None
+        if mode == "p2p":
+            from allegro_b200.halo import P2PHalo
+
+            assert dec.csr is not None
+            p2p = P2PHalo(dec, dev)
+        runner = DistributedAllegro(model, dec, p2p=p2p)
         e_tot, f_owned, e_atoms = runner(pos_owned)
         # the same step replayed from a CUDA graph (NCCL halo captured) on displaced positions
         from allegro_b200.halo import GraphedDistributedAllegro
@@ -47,6 +54,12 @@ def _worker(rank, world, port, q):
         eg, fg, _ = graphed(pos2)
         torch.cuda.synchronize()
         gerr = max(float((fg - f2).abs().max()), abs(float(eg) - float(e2)))
+        if p2p is not None:
+            # a few more replays: the mailbox parity / step-number protocol over several steps
+            for _ in range(5):
+                eg, fg, _ = graphed(pos2)
+            torch.cuda.synchronize()
+            gerr = max(gerr, float((fg - f2).abs().max()), abs(float(eg) - float(e2)), float(p2p.error()))
         # plain numpy payloads: torch tensors travel as shared-memory handles that die with this process
         q.put((rank, dec.owned.cpu().numpy(), f_owned.cpu().numpy(), e_atoms.cpu().numpy(), float(e_tot), gerr))
         # a live graph with captured NCCL kernels blocks communicator teardown: flush the queue and
@@ -61,7 +74,8 @@ def _worker(rank, world, port, q):
         raise
 
 
-def test_nccl_halo_matches_single_gpu():
+@pytest.mark.parametrize("mode,reps", [("nccl", (6, 3, 3)), ("p2p", (8, 5, 5))])
+def test_halo_matches_single_gpu(mode, reps):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     import torch.multiprocessing as mp
@@ -74,14 +88,14 @@ def test_nccl_halo_matches_single_gpu():
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q, mode, reps)) for r in range(world)]
     for p in procs:
         p.start()
-    res = [q.get(timeout=600) for _ in range(world)]
+    res = [q.get(timeout=300) for _ in range(world)]
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
-    d = systems.make_system("c2", (6, 3, 3))
+    d = systems.make_system("c2", reps)
     kw = systems.model_kwargs("c2", 42.0, "float64")
     ref = AllegroModel(**kw).to("cuda:0")({k: v.to("cuda:0") for k, v in d.items()})
     n = d[D.POSITIONS_KEY].shape[0]
