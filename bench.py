@@ -311,6 +311,33 @@ def run_ours_multi(args, rank, world):
     pos_owned = dec.local_positions_from_global(pos)[: dec.n_owned].to(dev)
     dec.to(dev)
     eager = DistributedAllegro(model, dec)
+    # halo over NVLink peer memory (kernels only, no NCCL call per step); checked once against the NCCL path on this
+    # very frame, and abandoned on every rank if any rank disagrees
+    halo_mode = args.halo
+    if halo_mode == "p2p":
+        from allegro_b200.halo import P2PHalo
+
+        ok = 1
+        try:
+            p2p = P2PHalo(dec, dev)
+            cand = DistributedAllegro(model, dec, p2p=p2p)
+            e1, f1, _ = eager(pos_owned)
+            e2, f2, _ = cand(pos_owned)
+            e3, f3, _ = cand(pos_owned)  # second step: the other mailbox parity
+            torch.cuda.synchronize()
+            scale = float(f1.abs().max())
+            if p2p.error() != 0 or float((f2 - f1).abs().max()) > 1e-5 * scale or float((f3 - f1).abs().max()) > 1e-5 * scale or \
+                    abs(float(e2) - float(e1)) > 1e-6 * abs(float(e1)) + 1e-9:
+                ok = 0
+        except Exception as exc:  # IPC not available, ...
+            print(f"[bench] rank {rank}: p2p halo unavailable: {exc}", file=sys.stderr)
+            ok = 0
+        okt = torch.tensor([ok], device=dev)
+        dist.all_reduce(okt, op=dist.ReduceOp.MIN)
+        if int(okt) == 1:
+            eager = cand
+        else:
+            halo_mode = "nccl (p2p self-check failed)"
     K, W = args.steps, args.warmup
     for _ in range(W):
         e, f, _ = eager(pos_owned)
@@ -385,8 +412,9 @@ def run_ours_multi(args, rank, world):
             "config": {"workload": f"{cfg} " + (f"split into {world} slabs" if strong else f"replicated x{world}") + f" along x: {n_global} atoms, {dec.n_owned} owned + <= {int(ghosts)} ghost atoms and "
                                    f"{n_edges} edges per GPU, l_max={kw['l_max']}, n_layers={kw['num_layers']}, S={kw['num_scalar_features']}, "
                                    f"U={kw['num_tensor_features']}, r_max={kw['r_max']}",
-                       "global_atoms": n_global, "parallelism": f"spatial slab decomposition x{world}, NCCL halo (positions fwd, gradients rev) "
-                       "+ 1 scalar all-reduce per step", "timing": "CUDA events, barrier + synchronize both sides, max over ranks; per-step working set >> L2",
+                       "global_atoms": n_global, "parallelism": f"spatial slab decomposition x{world}, ghost-atom halo (positions fwd, gradients rev) "
+                       "+ 1 scalar energy sum per step", "halo": halo_mode + (": NVLink peer-memory mailboxes (CUDA IPC), kernels only, inside the CUDA graph"
+                                                                              if halo_mode == "p2p" else ": torch.distributed P2P + all_reduce inside the CUDA graph"), "timing": "CUDA events, barrier + synchronize both sides, max over ranks; per-step working set >> L2",
                        "halo_bytes_per_step_per_gpu": dec.halo_bytes_per_step(8),
                        "cuda_graph": graphed, "eager_host_ms_per_step_max": float(host_t),
                        "host_cpus_visible": len(os.sched_getaffinity(0))},
@@ -552,6 +580,7 @@ def main():
                     help="activation storage; default float32 (GEMMs on tcgen05 as split-bf16, fp32-accurate): bfloat16 storage, the dtype BASELINE names for c2, measured 4e-3/4e-2 (E/F) against the fp64 oracle, outside the 1e-3 parity bar")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-parity-check", action="store_true", help="skip the pre-timing E/F check against the CPU oracle sub-sample")
+    ap.add_argument("--halo", default="p2p", choices=["p2p", "nccl"], help="N>1: ghost-atom exchange over NVLink peer memory (default) or NCCL")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel from Python instead of replaying a CUDA graph")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", 0))

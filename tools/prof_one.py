@@ -29,3 +29,15 @@ for awid, owid in (([64, 64, 32], [64]), ([64], [96, 64, 96])):
     pk = _lib.linear_pack(W)
     _lib.linear(a, W, o, W_packed=pk)
 torch.cuda.synchronize()
+# environment adjoint (streaming) and the radial kernels
+om = torch.randn(E, nir * U, device=dev); gom = torch.empty(E, nir * U, device=dev)
+_lib.env_bwd(dt, lmax, U, csr.ctr, Y, om, gg, 0.15, gom, gY, row_ptr=csr.row_ptr)
+_lib.env_sum(dt, lmax, N, U, csr.row_ptr, Y, om, 0.15)
+vec = torch.randn(E, 3, device=dev) * 2.0
+types = torch.zeros(N, dtype=torch.int32, device=dev)
+rmax = torch.full((1, 1), 5.0, device=dev); bwv = torch.arange(1, 9, device=dev, dtype=torch.float32)
+PQ = torch.randn(1, 8, 64, device=dev)
+h = _lib.radial_pq_fwd(dt, 64, 6.0, vec, csr.ctr, csr.nbr, types, rmax, bwv, PQ)
+gvec = torch.zeros(E, 3, device=dev)
+_lib.radial_pq_bwd(dt, 64, 6.0, vec, csr.ctr, csr.nbr, types, rmax, bwv, PQ, torch.randn(E, 64, device=dev), h, gvec)
+torch.cuda.synchronize()
