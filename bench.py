@@ -240,17 +240,24 @@ def run_ours(args, rank: int, world: int):
     avg_ms = per_kernel[dom_tp] / n_l
     bpe = algorithmic_bytes_per_edge(dom_tp, core)
     achieved = bpe * n_edges / (avg_ms * 1e-3) / 1e9
-    traffic = None
+    # DRAM traffic of that kernel from the latest committed `ncu --set full` capture (tools/ncu_summary.py writes
+    # profiles/ncu_traffic.json: dram__bytes_read.sum + dram__bytes_write.sum per launch, measured at the c2 shapes)
+    traffic = traffic_src = None
     try:
         tj = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
-        if cfg == "c2" and dtype == "float32":
-            traffic = tj["per_call_bytes"].get(dom_tp)
+        pat = {"tp_bwd@bwd.L0": "tp_stream_kernel<float, float, 9, 9, 1, 1,", "tp_fwd@fwd.L0": "tp_stream_kernel<float, float, 9, 9, 1, 0,",
+               "env_bwd@bwd.L0": "env_bwd_stream_kernel<float, 2,", "env_bwd@bwd.L1": "env_bwd_stream_kernel<float, 2,"}.get(dom_tp)
+        if cfg == "c2" and dtype == "float32" and pat:
+            for kname, rec in tj["per_kernel"].items():
+                if kname.startswith(pat):
+                    traffic = rec["dram_bytes_per_launch"]
+                    traffic_src = f"profiles/{tj['tag']}_ncu_full_summary.md ({tj['source']}: ncu --set full, dram__bytes_read+write per launch)"
     except Exception:
         pass
     roofline = {
         "kernel": dom_tp, "bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
-        "frac": round(achieved / peak, 4), "traffic": traffic, "traffic_source": "profiles/ncu_traffic.json (ncu dram__bytes_read+write per call)" if traffic else None,
-        "launches_per_call": 2 if dom_tp.startswith("tp_bwd@bwd.L0") else 1, "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 (of fallback)",
+        "frac": round(achieved / peak, 4), "traffic": traffic, "traffic_source": traffic_src,
+        "launches_per_call": int(round(n_l)), "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 (of fallback)",
         "algorithmic_bytes_per_edge": bpe, "avg_launch_ms": round(avg_ms, 5), "share_of_kernel_time": round(per_kernel[dom_tp] / kernel_total, 4),
     }
     res = {
@@ -306,7 +313,9 @@ def run_ours_multi(args, rank, world):
     n_global = pos.shape[0]
     dec = SlabDecomposition(pos, cell, types, systems.CONFIGS[cfg]["r_max"], rank, world, device=dev)
     n_edges = dec.n_edges
-    kw = systems.model_kwargs(cfg, n_edges / dec.n_owned, dtype)
+    cnt = torch.tensor([float(n_edges), float(dec.n_owned)], device=dev, dtype=torch.float64)
+    dist.all_reduce(cnt)  # one model for the whole frame: the global average neighbour count on every rank
+    kw = systems.model_kwargs(cfg, float(cnt[0] / cnt[1]), dtype)
     model = AllegroModel(**kw).to(dev).model  # energy model; forces via the halo-aware runner
     pos_owned = dec.local_positions_from_global(pos)[: dec.n_owned].to(dev)
     dec.to(dev)
