@@ -47,17 +47,21 @@ def main():
     nw, W = n_ir * U, S  # hidden widths = S in the benchmark configs
     peak = a.peak or d["roofline"]["peak"]
     per_edge_tp0 = b * nw + acc * D + 4 + b * U * D
+    # round 2: the first scalar-embed layer is folded into the radial kernel (it emits the pre-activation h [E, W]) and the
+    # embed linears into the MLP's last layer: upstream = radial kernel + ONE GEMM W -> (nw + S + nw) per direction
+    folded = "radial_fwd@fwd.embed" in d["kernels_ms_per_step"] or "radial_fwd@fwd.radial" not in d["kernels_ms_per_step"]
     ops = {
         "radial_fwd@fwd.radial": E * (acc * 3 + 8 + b * S),
+        "radial_fwd@fwd.embed": E * (acc * 3 + 8 + b * W),
         "linear@fwd.radial": mlp_fwd(E, b, [S, W, S]),
-        "linear@fwd.embed": E * b * (S + nw + S + nw),
+        "linear@fwd.embed": E * b * ((W if folded else S) + nw + S + nw),
         "sh_fwd@fwd.embed": E * acc * (3 + D),
         "edge_vec@fwd.radial": E * (8 + acc * 3),
         "linear@fwd.readout": mlp_fwd(E, b, [S * (L + 1), W, 1]),
         "linear@bwd.readout": mlp_bwd(E, b, [S * (L + 1), W, 1]),
         "linear@bwd.embed": E * b * (nw + S + nw + S),
-        "linear@bwd.radial": mlp_bwd(E, b, [S, W, S]),
-        "radial_bwd@bwd.radial": E * (acc * 6 + 8 + b * S),
+        "linear@bwd.radial": (E * b * (nw + S + nw + W)) if folded else mlp_bwd(E, b, [S, W, S]),
+        "radial_bwd@bwd.radial": E * (acc * 6 + 8 + (2 * b * W if folded else b * S)),
         "sh_bwd@bwd.embed": E * acc * (3 + D + 3),
         "edge_sum@fwd.readout": E * acc + N * acc,
         "edge_sum_bwd@bwd.readout": E * acc + N * acc,
