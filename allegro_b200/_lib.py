@@ -33,6 +33,7 @@ _SIGNATURES = {
     "ab2_op_scatter_env": ([_i32, _i64, _i64, _dbl, _vp, _vp, _vp, _vp], C.c_int),
     "ab2_op_contract": ([_i32, _i32, _i64, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp], C.c_int),
     "ab2_op_gather_rows": ([_i32, _i64, _i64, _dbl, _vp, _vp, _vp, _vp], C.c_int),
+    "ab2_op_contract_wgrad": ([_i32, _i64, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp], C.c_int),
     "ab2_sh_fwd": ([_i32, _i32, _i64, _vp, _vp, _vp], C.c_int),
     "ab2_sh_bwd": ([_i32, _i32, _i64, _vp, _vp, _vp, _i32, _vp], C.c_int),
     "ab2_linear": ([_i32, _i64, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _i32, _vp, _vp, _vp, _vp, _i32, _vp, _i64, _vp], C.c_int),
@@ -400,6 +401,16 @@ def op_contract(mode: int, U, d1, d2, dout, tab, cgw, a, b, idxs, out):
                 _ptr(_contig(idxs, "idxs")), _ptr(out), _stream(),
             )
         )
+    return out
+
+
+def op_contract_wgrad(U, d1, d2, dout, tab, x1, gamma, gout, idxs) -> torch.Tensor:
+    """gcgw[nnz][U] = sum_z x1 (x) gamma[idxs] (x) gout over the coupling table (training)."""
+    E = idxs.shape[0]
+    out = torch.zeros(tab.shape[0], U, dtype=x1.dtype, device=x1.device)
+    with _timed("op_contract_wgrad", 1):
+        _check(load().ab2_op_contract_wgrad(DTYPE_ENUM[x1.dtype], E, U, d1, d2, dout, tab.shape[0], _ptr(tab), _ptr(_contig(x1, "x1")),
+                                            _ptr(_contig(gamma, "gamma")), _ptr(_contig(gout, "gout")), _ptr(_contig(idxs, "idxs")), _ptr(out), _stream()))
     return out
 
 

@@ -117,3 +117,44 @@ extern "C" int ab2_op_contract(int dtype, int mode, int64_t E, int U, int d1, in
     AB2_CUDA_LAUNCH_CHECK();
     return 0;
 }
+
+// Gradient w.r.t. the weighted coupling table (training; the reference's weights are Parameters, _contract.py:170-177, and its
+// einsum path gets this product from autograd):  gcgw[n][u] += sum_z a[z][u][i_n] * b[idxs[z]][u][j_n] * g[z][u][k_n].
+// grid = (ceil(nnz*U / 128), z-chunks); thread = one (n, u) over a chunk of edges, one atomicAdd per thread and chunk.
+template <typename T>
+__global__ void __launch_bounds__(128) op_contract_wgrad_kernel(int64_t E, int64_t zchunk, int U, int d1, int d2, int dout, int nnz,
+                                                                const int32_t* __restrict__ tab, const T* __restrict__ a,
+                                                                const T* __restrict__ b, const T* __restrict__ g,
+                                                                const int64_t* __restrict__ idxs, T* __restrict__ out) {
+    const int t = blockIdx.x * 128 + threadIdx.x;
+    if (t >= nnz * U) return;
+    const int n = t / U, u = t - n * U;
+    const int i = tab[3 * n], j = tab[3 * n + 1], k = tab[3 * n + 2];
+    const int64_t z0 = (int64_t)blockIdx.y * zchunk;
+    const int64_t z1 = z0 + zchunk < E ? z0 + zchunk : E;
+    T acc = T(0);
+    for (int64_t z = z0; z < z1; ++z)
+        acc += a[(z * U + u) * d1 + i] * b[(idxs[z] * U + u) * d2 + j] * g[(z * U + u) * dout + k];
+    atomicAdd(&out[(int64_t)n * U + u], acc);
+}
+
+extern "C" int ab2_op_contract_wgrad(int dtype, int64_t E, int U, int d1, int d2, int dout, int nnz, const int32_t* tab_ijk, const void* x1,
+                                     const void* gamma, const void* gout, const int64_t* idxs, void* gcgw, void* stream) {
+    if (E == 0) return 0;
+    AB2_CHECK_ARG(dtype == AB2_F64 || dtype == AB2_F32, "operator-level kernels are fp32/fp64");
+    AB2_CHECK_ARG(d1 > 0 && d2 > 0 && dout > 0 && U > 0 && nnz > 0, "shape");
+    AB2_CHECK_ARG(tab_ijk && x1 && gamma && gout && idxs && gcgw, "null pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t zchunk = 512;
+    const int64_t ny = (E + zchunk - 1) / zchunk;
+    AB2_CHECK_ARG(ny <= 65535, "too many edges for one call");
+    const dim3 grid((unsigned)((nnz * U + 127) / 128), (unsigned)ny);
+    if (dtype == AB2_F64)
+        op_contract_wgrad_kernel<double><<<grid, 128, 0, st>>>(E, zchunk, U, d1, d2, dout, nnz, tab_ijk, (const double*)x1, (const double*)gamma,
+                                                              (const double*)gout, idxs, (double*)gcgw);
+    else
+        op_contract_wgrad_kernel<float><<<grid, 128, 0, st>>>(E, zchunk, U, d1, d2, dout, nnz, tab_ijk, (const float*)x1, (const float*)gamma,
+                                                             (const float*)gout, idxs, (float*)gcgw);
+    AB2_CUDA_LAUNCH_CHECK();
+    return 0;
+}

@@ -47,6 +47,38 @@ __device__ __forceinline__ void mbar_wait_backoff(uint32_t bar, uint32_t parity)
         __nanosleep(256);
     }
 }
+__device__ __forceinline__ void mbar_wait_sleep(uint32_t bar, uint32_t parity, uint32_t ns) {
+    while (true) {
+        uint32_t ok;
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t"
+            "}"
+            : "=r"(ok)
+            : "r"(bar), "r"(parity)
+            : "memory");
+        if (ok) return;
+        __nanosleep(ns);
+    }
+}
+// try_wait with a suspend-time hint: the thread may stay suspended up to `ns` before the instruction returns false
+__device__ __forceinline__ void mbar_wait_hint(uint32_t bar, uint32_t parity, uint32_t ns) {
+    while (true) {
+        uint32_t ok;
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t"
+            "}"
+            : "=r"(ok)
+            : "r"(bar), "r"(parity), "r"(ns)
+            : "memory");
+        if (ok) return;
+    }
+}
 __device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {
     uint32_t ok;
     asm volatile(
@@ -77,6 +109,19 @@ __device__ __forceinline__ void cp_async_arrive_noinc(uint32_t bar) {
     asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
 }
 __device__ __forceinline__ void named_bar(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
+
+
+// First centre of CTA b's range: the edge stream is cut every E/G edges, snapped forward to the next centre
+// boundary.  Two dependent loads (ctr[t], row_ptr[c]) instead of a binary search over row_ptr.
+__device__ __forceinline__ int64_t cut_centre(const int32_t* __restrict__ row_ptr, const int32_t* __restrict__ ctr, int64_t N, int64_t E,
+                                              int64_t b, int64_t G) {
+    if (b <= 0) return 0;
+    if (b >= G) return N;
+    const int64_t t = b * E / G;
+    if (t >= E) return N;
+    const int64_t c = ctr[t];
+    return row_ptr[c] == t ? c : c + 1;
+}
 
 
 // Reduce N (<= 8) per-lane values across the warp: P = next power of two, P/2 + P/4 + .. + 1 shuffles for the

@@ -27,3 +27,7 @@ int ab2_tp_stream(int mode, int dtype, int64_t N, int64_t E, int U, int D, int d
                   const void* w0, int64_t w0_ld, void* Vout, const void* gVout, void* gVin, void* gw0, int64_t gw0_ld, void* gY,
                   void* ggamma, cudaStream_t st);
 extern int g_ab2_opt_tp_stream, g_ab2_opt_tp_stream_te, g_ab2_opt_tp_stream_cps;
+// three-consumer-warp layer-0 backward (tp_stream3.cu): fp32, U = 32, 9 x 9 -> 9 with the baked table structure
+int ab2_tp_stream3_bwd(int64_t N, int64_t E, const int32_t* tab, const void* cgw, const int32_t* row_ptr, const int32_t* ctr, const void* gamma,
+                       const void* Y, const void* w0, const void* gVout, void* gw0, void* gY, void* ggamma, cudaStream_t st);
+extern int g_ab2_opt_tp_stream3;

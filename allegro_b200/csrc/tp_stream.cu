@@ -57,19 +57,8 @@ struct StreamParams {
     void* gw0;
     void* gY;
     void* ggamma;
+    int skip_if_baked;  // the three-warp kernel (tp_stream3.cu) was launched for this call: stand down where it works
 };
-
-// First centre of CTA b's range: the edge stream is cut every E/G edges, snapped forward to the next centre
-// boundary.  Two dependent loads (ctr[t], row_ptr[c]) instead of a binary search over row_ptr.
-__device__ __forceinline__ int64_t cut_centre(const int32_t* __restrict__ row_ptr, const int32_t* __restrict__ ctr, int64_t N, int64_t E,
-                                              int64_t b, int64_t G) {
-    if (b <= 0) return 0;
-    if (b >= G) return N;
-    const int64_t t = b * E / G;
-    if (t >= E) return N;
-    const int64_t c = ctr[t];
-    return row_ptr[c] == t ? c : c + 1;
-}
 
 // baked coupling-table structure for a shape (TabNone: none)
 template <int D_IN, int D_OUT>
@@ -207,6 +196,7 @@ __global__ void __launch_bounds__((2 * NCH + 1) * 32) tp_stream_kernel(const Str
             if (t4.x != TAB::I(n) || t4.y != TAB::J(n) || t4.z != TAB::K(n)) ok = 0;
         }
         baked = __syncthreads_and(ok) != 0 ;
+        if (p.skip_if_baked && baked) return;
     }
 
     // ---- this CTA's contiguous range of centres / edges ----
@@ -683,6 +673,13 @@ int ab2_tp_stream(int mode, int dtype, int64_t N, int64_t E, int U, int D, int d
     StreamParams p;
     p.N = N; p.E = E; p.U = U; p.D = D; p.nnz = nnz; p.tab = tab; p.cgw = cgw; p.row_ptr = row_ptr; p.ctr = ctr; p.gamma = gamma;
     p.Vin = Vin; p.Y = Y; p.w0 = w0; p.Vout = Vout; p.gVout = gVout; p.gVin = gVin; p.gw0 = gw0; p.gY = gY; p.ggamma = ggamma;
+    // layer-0 backward at the l_max = 2 shape: three consumer warps per centre stream (tp_stream3.cu).  That kernel only
+    // works on the baked table structure and checks it on the device; the two-warp kernel below runs with the
+    // complementary test, so exactly one of the two launches does the work (no host-side look at device data).
+    p.skip_if_baked = 0;
+    if (mode == 1 && implicit_v0 && dtype == AB2_F32 && d_in == 9 && D == 9 && U == 32 && nnz == Tab9x9x9::NNZ && E < ((int64_t)1 << 31) &&
+        ab2_tp_stream3_bwd(N, E, tab, cgw, row_ptr, ctr, gamma, Y, w0, gVout, gw0, gY, ggamma, st) == 0)
+        p.skip_if_baked = 1;
 #define AB2_STREAM_CASE(TA, DI)                                                                                        \
     if (d_in == DI) {                                                                                                   \
         if (mode == 0) return implicit_v0 ? launch_shape<TA, float, DI, DI, true, 0>(p, st) : launch_shape<TA, float, DI, DI, false, 0>(p, st); \

@@ -4,8 +4,10 @@ Mirrors allegro/nn/_strided/_contract.py:11-313 -- same constructor kwargs, same
 ``state_dict`` (``weights`` of shape (mul,P)/(mul,)/(P,)/(), dense ``w3j`` buffer), same
 ``forward(x1, x2, idxs, scatter_dim_size)`` on the strided [z][u][i] layout -- but the
 arithmetic runs in ``liballegro_b200.so`` (ab2_op_scatter_env / ab2_op_contract /
-ab2_op_gather_rows) with hand-written backward w.r.t. x1 and x2 (like the Triton back-end,
-_flashallegro.py:583-666, inference-style: no weight gradient, no double backward).
+ab2_op_gather_rows / ab2_op_contract_wgrad).  Every derivative of the underlying trilinear form is one of four
+hand-written products (_Tri), so the operator has gradients w.r.t. x1, x2 AND the weights and is differentiable to
+any order (forces in the loss) -- the reference gets that from autograd through its einsum path; its Triton back-end
+is inference-only (_flashallegro.py:583-666,727).
 There is no CPU path: tensors must be CUDA tensors.
 """
 from __future__ import annotations
@@ -19,37 +21,85 @@ from .. import _lib
 from ..o3 import CouplingTable, Irreps, build_coupling_table
 
 
-class _ContractFn(torch.autograd.Function):
-    @staticmethod
-    def forward(ctx, x1, x2, idxs, n_atoms: int, mod: "Contracter"):
-        U, d1, d2, dout = mod.mul, mod.base_dim1, mod.base_dim2, mod.base_dim_out
-        x1c = x1.reshape(-1, U, d1).contiguous()
-        x2c = x2.reshape(-1, U, d2).contiguous()
-        idxs = idxs.contiguous()
-        sf = 1.0 if mod.scatter_factor is None else float(mod.scatter_factor)
-        tab, cgw = mod.device_tables(x1c.dtype, x1c.device)
-        gamma = _lib.op_scatter_env(x2c, idxs, n_atoms, sf)
-        out = torch.empty(x1c.shape[0], U, dout, dtype=x1c.dtype, device=x1c.device)
-        _lib.op_contract(0, U, d1, d2, dout, tab, cgw, x1c, gamma, idxs, out)
-        ctx.save_for_backward(x1c, gamma, idxs, tab, cgw)
-        ctx.meta = (U, d1, d2, dout, sf, n_atoms, x1.shape, x2.shape)
-        return out
+class _Meta:
+    """Non-differentiable context of one contraction: shapes, table, scatter indices."""
+
+    __slots__ = ("U", "d1", "d2", "dout", "tab", "idxs", "n_atoms")
+
+    def __init__(self, U, d1, d2, dout, tab, idxs, n_atoms):
+        self.U, self.d1, self.d2, self.dout, self.tab, self.idxs, self.n_atoms = U, d1, d2, dout, tab, idxs, n_atoms
+
+
+_SLOTS = ("c", "a", "b", "g")
+
+
+class _Tri(torch.autograd.Function):
+    """One partial derivative of the trilinear form behind Contracter._contract (_contract.py:213-251)
+
+        T(c, a, b, g) = sum_{z,u,n} c[n,u] a[z,u,i_n] b[idxs[z],u,j_n] g[z,u,k_n]
+
+    with c = value * weights (the reference's ww3j), a = x1, b = the per-atom environment, g = a cotangent of the
+    output.  ``which`` names the slot that is differentiated away: "g" is the forward contraction, "a" / "b" the two
+    backward products of the Triton back-end (_flashallegro.py:347-360), "c" the weight gradient.  T is linear in every
+    slot, so the gradient of any of these products w.r.t. one of its inputs is again one of the four products with the
+    incoming cotangent put into the differentiated slot -- backward() therefore calls _Tri.apply itself, which makes the
+    operator differentiable to any order (weight gradients, and double backward for forces in the loss) on four kernels."""
 
     @staticmethod
-    def backward(ctx, gout):
-        x1c, gamma, idxs, tab, cgw = ctx.saved_tensors
-        U, d1, d2, dout, sf, n_atoms, s1, s2 = ctx.meta
-        gout = gout.contiguous()
-        gx1 = gx2 = None
-        if ctx.needs_input_grad[0]:
-            gx1 = torch.empty_like(x1c)
-            _lib.op_contract(1, U, d1, d2, dout, tab, cgw, gout, gamma, idxs, gx1)
-            gx1 = gx1.reshape(s1)
-        if ctx.needs_input_grad[1]:
-            ggamma = torch.zeros_like(gamma)
-            _lib.op_contract(2, U, d1, d2, dout, tab, cgw, x1c, gout, idxs, ggamma)
-            gx2 = _lib.op_gather_rows(ggamma, idxs, sf).reshape(s2)
-        return gx1, gx2, None, None, None
+    def forward(ctx, which: str, meta: _Meta, c, a, b, g):
+        ctx.which, ctx.meta = which, meta
+        ctx.save_for_backward(*[t for t in (c, a, b, g) if t is not None])
+        m = meta
+        if which == "g":
+            out = torch.empty(a.shape[0], m.U, m.dout, dtype=a.dtype, device=a.device)
+            return _lib.op_contract(0, m.U, m.d1, m.d2, m.dout, m.tab, c.contiguous(), a, b, m.idxs, out)
+        if which == "a":
+            out = torch.empty(g.shape[0], m.U, m.d1, dtype=g.dtype, device=g.device)
+            return _lib.op_contract(1, m.U, m.d1, m.d2, m.dout, m.tab, c.contiguous(), g, b, m.idxs, out)
+        if which == "b":
+            out = torch.zeros(m.n_atoms, m.U, m.d2, dtype=a.dtype, device=a.device)
+            return _lib.op_contract(2, m.U, m.d1, m.d2, m.dout, m.tab, c.contiguous(), a, g, m.idxs, out)
+        return _lib.op_contract_wgrad(m.U, m.d1, m.d2, m.dout, m.tab, a, b, g, m.idxs)
+
+    @staticmethod
+    def backward(ctx, h):
+        saved = list(ctx.saved_tensors)
+        slots = {}
+        for name in _SLOTS:
+            slots[name] = h.contiguous() if name == ctx.which else saved.pop(0)
+        grads = []
+        for pos, name in enumerate(_SLOTS):
+            if name == ctx.which or not ctx.needs_input_grad[2 + pos]:
+                grads.append(None)
+                continue
+            args = dict(slots)
+            args[name] = None
+            grads.append(_Tri.apply(name, ctx.meta, args["c"], args["a"], args["b"], args["g"]))
+        return (None, None, *grads)
+
+
+class _ScatterRows(torch.autograd.Function):
+    """gamma[n] = sf * sum_{z: idxs[z] = n} x[z]  (_contract.py:199-204); its adjoint is _GatherRows and vice versa."""
+
+    @staticmethod
+    def forward(ctx, x, idxs, n_atoms: int, sf: float):
+        ctx.idxs, ctx.n_atoms, ctx.sf = idxs, n_atoms, sf
+        return _lib.op_scatter_env(x.contiguous(), idxs, n_atoms, sf)
+
+    @staticmethod
+    def backward(ctx, h):
+        return _GatherRows.apply(h, ctx.idxs, ctx.n_atoms, ctx.sf), None, None, None
+
+
+class _GatherRows(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, src, idxs, n_atoms: int, sf: float):
+        ctx.idxs, ctx.n_atoms, ctx.sf = idxs, n_atoms, sf
+        return _lib.op_gather_rows(src.contiguous(), idxs, sf)
+
+    @staticmethod
+    def backward(ctx, h):
+        return _ScatterRows.apply(h, ctx.idxs, ctx.n_atoms, ctx.sf), None, None, None
 
 
 class Contracter(torch.nn.Module):
@@ -141,6 +191,19 @@ class Contracter(torch.nn.Module):
             out = (wp * val).unsqueeze(-1).expand(path.shape[0], self.mul)
         return out.contiguous().to(device=device, dtype=dtype)
 
+    def cgw_live(self, dtype, device) -> torch.Tensor:
+        """cgw as a differentiable function of ``self.weights`` (training): same values as ``cgw``."""
+        _, path, val = self.sparse_table()
+        path, val = path.to(device), val.to(device=device, dtype=dtype)
+        w = self.weights.to(device=device, dtype=dtype)
+        if self.num_paths > 1:
+            wp = w[..., path]
+        else:
+            wp = w.unsqueeze(-1).expand(*w.shape, path.shape[0])
+        if self.path_channel_coupling:
+            return (wp * val).transpose(0, 1).contiguous()
+        return (wp * val).unsqueeze(-1).expand(path.shape[0], self.mul).contiguous()
+
     def device_tables(self, dtype, device):
         key = (dtype, str(device), self.weights._version, self.weights.data_ptr(), self.w3j._version, self.w3j.data_ptr())
         hit = self._tab_cache.get("k")
@@ -157,7 +220,14 @@ class Contracter(torch.nn.Module):
         if x1.dtype not in (torch.float32, torch.float64):
             raise RuntimeError("operator-level Contracter supports float32/float64")
         n = int(scatter_dim_size.reshape(-1)[0]) if isinstance(scatter_dim_size, torch.Tensor) else int(scatter_dim_size)
-        return _ContractFn.apply(x1, x2.to(x1.dtype), idxs, n, self)
+        U, d1, d2, dout = self.mul, self.base_dim1, self.base_dim2, self.base_dim_out
+        tab, cgw = self.device_tables(x1.dtype, x1.device)
+        if torch.is_grad_enabled() and self.weights.requires_grad:
+            cgw = self.cgw_live(x1.dtype, x1.device)
+        idxs = idxs.contiguous()
+        sf = 1.0 if self.scatter_factor is None else float(self.scatter_factor)
+        gamma = _ScatterRows.apply(x2.to(x1.dtype).reshape(-1, U, d2), idxs, n, sf)
+        return _Tri.apply("g", _Meta(U, d1, d2, dout, tab, idxs, n), cgw, x1.reshape(-1, U, d1).contiguous(), gamma, None)
 
     def extra_repr(self):
         return f"{self.irreps_in1} x {self.irreps_in2} -> {self.irreps_out} | {self.mul} channels | {self.num_paths} paths"

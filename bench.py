@@ -304,7 +304,7 @@ def run_ours_multi(args, rank, world):
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
     cfg = args.config
     dtype = args.dtype or systems.CONFIGS[cfg]["dtype"]
-    base = {"c1": 2, "c2": 14, "c5": 14, "c3": 46, "c4": 69}[cfg]
+    base = args.reps or {"c1": 2, "c2": 14, "c5": 14, "c3": 46, "c4": 69}[cfg]
     # c4 IS the multi-GPU configuration (BASELINE configs[3]: the 1M-atom water box split into N slabs, fixed total
     # size); every other config is replicated N times along x (fixed per-GPU work, weak scaling)
     strong = cfg == "c4"
@@ -590,6 +590,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-parity-check", action="store_true", help="skip the pre-timing E/F check against the CPU oracle sub-sample")
     ap.add_argument("--halo", default="p2p", choices=["p2p", "nccl"], help="N>1: ghost-atom exchange over NVLink peer memory (default) or NCCL")
+    ap.add_argument("--reps", type=int, default=0, help="N>1: lattice repetitions per box edge instead of the config's own (smaller boxes for tests)")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel from Python instead of replaying a CUDA graph")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", 0))

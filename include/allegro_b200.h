@@ -42,6 +42,11 @@ int ab2_device_ok(void);
  *   "tp_fast"    1 shared-memory / register-tiled tensor product (default), 2 register-M variants, 0 shape-generic kernels
  *   "linear_tc"  1 tcgen05 tensor-core linear (default), 0 CUDA-core tile kernel
  *   "tp_variant" 1: 3 CTAs/SM (default), 0: 2 CTAs/SM for the shared-memory tensor-product kernel
+ *   "tp_stream"  1 TMA-staged streaming tensor product where instantiated (default), 0 round-1 kernels;
+ *                "tp_stream_te" edges per stage (0 = 8), "tp_stream_cps" cap on CTAs per SM (0 = occupancy limit),
+ *                "tp_stream3" 1: three consumer warps per centre stream for the layer-0 backward, 0: two (default)
+ *   "env_stream" 1 streaming adjoint of the environment sum (default), 0 round-1 kernel
+ *   "linear_tma" 1 TMA-producer variant of the tensor-core linear where eligible (default), 0 cp.async producers
  *   "env_split"  warps per (centre, channel chunk) in ab2_env_sum / ab2_env_bwd: 0 auto (default), 1, 2, 4
  *   "tc_debug"   stage knock-out mask of the tcgen05 linear (bit0 no stores, bit1 no loads, bit2 no MMA); results are
  *                wrong when non-zero -- for tools/exp_env.py only
@@ -67,6 +72,15 @@ int ab2_op_scatter_env(int dtype, int64_t E, int64_t row /* = U*d2 */, double sf
 int ab2_op_contract(int dtype, int mode, int64_t E, int U, int d1, int d2, int dout, int nnz,
                     const int32_t* tab_ijk, const void* cgw, const void* a, const void* b,
                     const int64_t* idxs, void* out, void* stream);
+
+/* Training support (the reference's `weights` are Parameters, _contract.py:170-177; its einsum path gets this product
+ * from autograd, its Triton path is inference-only, _flashallegro.py:727):
+ *   gcgw[n][u] += sum_z x1[z][u][i_n] * gamma[idxs[z]][u][j_n] * gout[z][u][k_n]      (gcgw pre-zeroed, atomics).
+ * Together with modes 0-2 above every derivative of the trilinear form is one of these four products, which is how
+ * allegro_b200.nn.Contracter provides weight gradients and double backward (forces in the loss). */
+int ab2_op_contract_wgrad(int dtype, int64_t E, int U, int d1, int d2, int dout, int nnz,
+                          const int32_t* tab_ijk, const void* x1, const void* gamma, const void* gout,
+                          const int64_t* idxs, void* gcgw, void* stream);
 
 /* Gather rows: out[z][:] = sf * src[idxs[z]][:]  (adjoint of the scatter; _contract.py:205). */
 int ab2_op_gather_rows(int dtype, int64_t E, int64_t row, double sf, const void* src,

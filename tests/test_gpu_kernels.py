@@ -242,18 +242,22 @@ def _tp_case(lmax, layer, L, U, coupling, dtype, seed=0):
     return c, b
 
 
-@pytest.fixture(params=[(1, 1, 8), (1, 1, 16), (1, 0, 8), (2, 0, 8), (0, 0, 8)], ids=["stream", "stream_te16", "fast", "regM", "generic"])
+@pytest.fixture(params=[(1, 1, 8, 1), (1, 1, 8, 0), (1, 1, 16, 0), (1, 0, 8, 0), (2, 0, 8, 0), (0, 0, 8, 0)],
+                ids=["stream3", "stream", "stream_te16", "fast", "regM", "generic"])
 def tp_fast(request):
-    """Kernel families of the tensor product: TMA-staged streaming kernels (round 2, default where instantiated), the
-    round-1 shared-memory-M / split kernels, the register-M kernels, the shape-generic kernels."""
-    fast, stream, te = request.param
+    """Kernel families of the tensor product: TMA-staged streaming kernels (round 2, default where instantiated; "stream3" =
+    with the three-consumer-warp layer-0 backward, an option that measured equal to the two-warp kernel), the round-1 shared-memory-M / split kernels, the
+    register-M kernels, the shape-generic kernels."""
+    fast, stream, te, s3 = request.param
     _lib.set_option("tp_fast", fast)
     _lib.set_option("tp_stream", stream)
     _lib.set_option("tp_stream_te", te)
+    _lib.set_option("tp_stream3", s3)
     yield request.param
     _lib.set_option("tp_fast", 1)
     _lib.set_option("tp_stream", 1)
     _lib.set_option("tp_stream_te", 0)
+    _lib.set_option("tp_stream3", 0)
 
 
 @pytest.mark.parametrize("case", [(1, 0, 1), (2, 0, 2), (2, 1, 2), (3, 0, 3), (3, 1, 3), (3, 2, 3), (1, 0, 2), (1, 1, 3)])
@@ -330,6 +334,60 @@ def test_tp_fwd_bwd_implicit_v0(lmax, dtype, U, tp_fast):
     assert _rel(ggam.transpose(1, 2), ggam_ref) < (tol if dtype != torch.bfloat16 else 1e-5)
 
 
+@pytest.mark.parametrize("s3", [1, 0], ids=["stream3", "stream"])
+def test_tp_stream_ragged_rows(s3):
+    """Layer-0 streaming kernels on a ragged CSR with more centres than CTAs: empty centres (also leading / trailing), rows of
+    1-3 edges (several centres begin inside one 8-edge stage), rows far longer than a stage.  Reference: the shape-generic
+    kernels on the same device data (themselves held to the oracle above); ggamma of empty centres must come back zero and
+    two runs must agree bitwise (every reduction is fixed-order)."""
+    g = torch.Generator().manual_seed(11)
+    N, U, lmax, Dd, n_ir = 3000, 32, 2, 9, 3
+    deg = torch.randint(0, 4, (N,), generator=g)
+    deg[torch.randint(0, N, (300,), generator=g)] = 0
+    deg[torch.randint(0, N, (40,), generator=g)] = torch.randint(60, 200, (40,), generator=g)
+    deg[:5] = 0
+    deg[-7:] = 0
+    ctr = torch.repeat_interleave(torch.arange(N), deg)
+    E = int(ctr.numel())
+    csr = D.build_csr(torch.stack([ctr, torch.randint(0, N, (E,), generator=g)]).to(DEV), N)
+    _, b = _tp_case(lmax, 0, 2, U, True, torch.float32)
+    ijk, _, _ = b.sparse_table()
+    tab, cgw = ijk.to(DEV), b.cgw(torch.float32, DEV)
+    Y = torch.randn(E, Dd, generator=g).to(DEV)
+    w0 = torch.randn(E, n_ir * U, generator=g).to(DEV)
+    gam = torch.randn(N, Dd, U, generator=g).to(DEV)
+    gout = torch.randn(E, Dd, U, generator=g).to(DEV)
+
+    def run():
+        Vout = torch.empty(E, Dd, U, device=DEV)
+        gw0 = torch.full((E, n_ir * U), float("nan"), device=DEV)
+        gY = torch.ones(E, Dd, device=DEV)  # accumulated into
+        ggam = torch.full((N, Dd, U), float("nan"), device=DEV)
+        _lib.tp_fwd(torch.float32, lmax, N, E, U, Dd, Dd, tab, cgw, csr.row_ptr, csr.ctr, gam, None, Y, w0, Vout)
+        _lib.tp_bwd(torch.float32, lmax, N, E, U, Dd, Dd, tab, cgw, csr.row_ptr, csr.ctr, gam, None, Y, w0, gout, None, gw0, gY, ggam)
+        torch.cuda.synchronize()
+        return Vout, gw0, gY, ggam
+
+    try:
+        _lib.set_option("tp_fast", 0)
+        _lib.set_option("tp_stream", 0)
+        ref = run()
+        _lib.set_option("tp_fast", 1)
+        _lib.set_option("tp_stream", 1)
+        _lib.set_option("tp_stream3", s3)
+        got, again = run(), run()
+    finally:
+        _lib.set_option("tp_fast", 1)
+        _lib.set_option("tp_stream", 1)
+        _lib.set_option("tp_stream3", 0)
+    for name, a, r in zip(("Vout", "gw0", "gY", "ggamma"), got, ref):
+        assert bool(torch.isfinite(a).all()), name
+        assert _rel(a, r) < 2e-5, name
+    assert bool((got[3][deg == 0] == 0).all())
+    for name, a, c in zip(("Vout", "gw0", "ggamma"), (got[0], got[1], got[3]), (again[0], again[1], again[3])):
+        assert torch.equal(a, c), name
+
+
 def test_edge_sum_force_scatter_transpose():
     N, E = 50, 900
     csr, ctr = _csr_random(N, E, seed=1)
@@ -390,6 +448,46 @@ def test_contract_kernel_vs_base(irreps_in1, irreps_in2, irreps_out, coupling, m
             (g_k,) = torch.autograd.grad(out_k, [b[arg]], go.to(DEV))
             torch.testing.assert_close(out_k.cpu(), out_o.detach(), atol=tol, rtol=tol)
             torch.testing.assert_close(g_k.cpu(), g_o, atol=tol, rtol=tol)
+    finally:
+        torch.set_default_dtype(prev)
+
+
+@pytest.mark.parametrize("coupling", [True, False])
+@pytest.mark.parametrize("irreps", [("0e + 1o + 2e", "0e + 1o + 2e", "0e + 1o + 2e"), ("2o + 1e + 0e", "0e + 0o + 1e + 1o", "1o + 2e")])
+def test_contracter_weight_grad_and_double_backward(irreps, coupling):
+    """Training support: the reference's ``weights`` are Parameters and its einsum path is differentiable
+    to any order through autograd (_contract.py:170-177, 213-251).  The B200 operator builds every derivative from four
+    hand-written products; held here to the oracle's autograd: d/d(weights, x1, x2) of a scalar loss, and the second-order
+    terms a force loss needs -- d/d(weights, x1, x2) of a function of dOut/dx1 and dOut/dx2."""
+    prev = torch.get_default_dtype()
+    torch.set_default_dtype(torch.float64)
+    try:
+        torch.manual_seed(3)
+        i1, i2, io = (o3_ref.Irreps(x) for x in irreps)
+        mul, E, N = 5, 23, 6
+        c_base = R.Contracter(i1, i2, io, mul=mul, path_channel_coupling=coupling, scatter_factor=0.37)
+        c_k = B200Contracter(irreps[0], irreps[1], irreps[2], mul=mul, instructions=c_base.instructions, path_channel_coupling=coupling,
+                             scatter_factor=0.37).to(DEV)
+        c_k.load_state_dict(c_base.state_dict())
+        idx = torch.randint(0, N, (E,))
+        x1, x2 = torch.randn(E, mul, i1.dim), torch.randn(E, mul, i2.dim)
+        go, v1, v2 = torch.randn(E, mul, io.dim), torch.randn(E, mul, i1.dim), torch.randn(E, mul, i2.dim)
+
+        def losses(c, dev):
+            a = x1.clone().to(dev).requires_grad_(True)
+            b = x2.clone().to(dev).requires_grad_(True)
+            out = c(a, b, idx.to(dev), torch.tensor([N], device=dev))
+            first = torch.autograd.grad((out * go.to(dev)).sum(), [c.weights, a, b], retain_graph=True)
+            # "force-like" quantities, then a loss on them (double backward)
+            ga, gb = torch.autograd.grad((out * torch.tanh(out)).sum(), [a, b], create_graph=True)
+            loss2 = (ga * v1.to(dev)).sum() + (gb * v2.to(dev)).pow(2).sum()
+            second = torch.autograd.grad(loss2, [c.weights, a, b])
+            return [t.detach().cpu() for t in (out, *first, *second)]
+
+        ref, got = losses(c_base, "cpu"), losses(c_k, DEV)
+        for name, r, g in zip(("out", "dL/dw", "dL/dx1", "dL/dx2", "d2/dw", "d2/dx1", "d2/dx2"), ref, got):
+            assert g.shape == r.shape, name
+            assert _rel(g, r) < 1e-10, (name, float(_rel(g, r)))
     finally:
         torch.set_default_dtype(prev)
 
