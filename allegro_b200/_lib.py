@@ -51,6 +51,7 @@ _SIGNATURES = {
     "ab2_radial_fwd": ([_i32, _i64, _i32, _i32, _dbl, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp], C.c_int),
     "ab2_radial_pq_fwd": ([_i32, _i64, _i32, _i32, _dbl, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _vp], C.c_int),
     "ab2_radial_pq_bwd": ([_i32, _i64, _i32, _i32, _dbl, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp], C.c_int),
+    "ab2_zbl": ([_i32, _i64, _i32, _dbl, _dbl, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp], C.c_int),
     "ab2_p2p_mailbox_bytes": ([_i32, _i32], C.c_int64),
     "ab2_p2p_alloc": ([_i64, C.POINTER(C.c_void_p)], C.c_int),
     "ab2_p2p_free": ([_vp], C.c_int),
@@ -402,6 +403,16 @@ def op_contract(mode: int, U, d1, d2, dout, tab, cgw, a, b, idxs, out):
             )
         )
     return out
+
+
+def zbl(p_cut: float, qq: float, vec, ctr, nbr, types, Z, rmax_table, gvec: Optional[torch.Tensor]) -> torch.Tensor:
+    """per-edge ZBL energies [E] (accumulate dtype); if ``gvec`` is given, dEz/dvec is added into it."""
+    E = ctr.shape[0]
+    Ez = torch.empty(E, dtype=vec.dtype, device=vec.device)
+    with _timed("zbl"):
+        _check(load().ab2_zbl(DTYPE_ENUM[vec.dtype], E, Z.shape[0], float(p_cut), float(qq), _ptr(_contig(vec, "vec")), _ptr(ctr), _ptr(nbr), _ptr(types),
+                              _ptr(_contig(Z, "Z")), _ptr(_contig(rmax_table, "rmax_table")), _ptr(Ez), _ptr(gvec) if gvec is not None else None, _stream()))
+    return Ez
 
 
 def op_contract_wgrad(U, d1, d2, dout, tab, x1, gamma, gout, idxs) -> torch.Tensor:

@@ -31,6 +31,7 @@ from ..nn._modules import (
 )
 from ..nn._mlp import ScalarMLPFunction
 from ..nn._pipeline import AllegroCore, UpstreamPack, core_apply, energy_forces
+from ..nn._zbl import instantiate_pair_potential
 from ..o3 import Irreps
 
 _DTYPES = {"float32": torch.float32, "float64": torch.float64, "bfloat16": torch.bfloat16}
@@ -86,8 +87,6 @@ class FusedAllegroEnergy(torch.nn.Module):
         model_dtype: str = "float32",
     ):
         super().__init__()
-        if pair_potential is not None:
-            raise NotImplementedError("pair_potential (ZBL) is SURVEY row f4, not built")
         assert avg_num_neighbors is not None, "`avg_num_neighbors` must be set for Allegro models"
         self.model_dtype = _DTYPES[model_dtype]
         self.type_names = list(type_names)
@@ -129,6 +128,8 @@ class FusedAllegroEnergy(torch.nn.Module):
             type_names, per_type_energy_scales, per_type_energy_shifts, per_type_energy_scales_trainable,
             per_type_energy_shifts_trainable,
         )
+        # pair potential after the scale/shift (allegro_models.py:270-288)
+        self.pair_potential = instantiate_pair_potential(pair_potential, type_names)
         self._core: Optional[AllegroCore] = None
         self._core_key = None
         self._caches: Dict[str, tuple] = {}
@@ -222,9 +223,14 @@ class FusedAllegroEnergy(torch.nn.Module):
         ss = self.per_type_energy_scale_shift
         gscale = ss.scales[types].to(core.acc)
         want_virial = bool(stress) and D.CELL_KEY in data
-        Ei, F, X, Ez, virial = energy_forces(core, self._upstream, csr, pos.detach().contiguous(), types_i32, shift_vec,
-                                             gscale, want_virial)
+        pair = None
+        if self.pair_potential is not None:
+            pair = (self.pair_potential, self.edge_norm.rmax_table.to(device=pos.device, dtype=core.acc))
+        Ei, F, X, Ez, virial, Ei_pair = energy_forces(core, self._upstream, csr, pos.detach().contiguous(), types_i32, shift_vec,
+                                                      gscale, want_virial, pair=pair)
         e_atom = ss(Ei.unsqueeze(-1), types)
+        if Ei_pair is not None:
+            e_atom = e_atom + Ei_pair.unsqueeze(-1).to(e_atom.dtype)
         out = dict(data)
         if csr.perm is not None:
             inv = torch.empty_like(csr.perm)
@@ -272,6 +278,9 @@ class FusedAllegroEnergy(torch.nn.Module):
         stash: Dict[str, torch.Tensor] = {}
         Ei = core_apply(core, csr, vec.to(core.acc), x_emb.to(self.model_dtype), stash)
         e_atom = self.per_type_energy_scale_shift(Ei.unsqueeze(-1), types)
+        if self.pair_potential is not None:
+            ez_pair = self.pair_potential.edge_energy(r, x_norm, tc, tn)
+            e_atom = e_atom + torch.zeros(n, dtype=ez_pair.dtype, device=ez_pair.device).index_add_(0, ctr, ez_pair).unsqueeze(-1).to(e_atom.dtype)
         out = dict(data)
         inv = None
         if csr.perm is not None:

@@ -379,11 +379,13 @@ class UpstreamPack:
 
 
 def energy_forces(core: "AllegroCore", up: UpstreamPack, csr: EdgeCSR, pos: torch.Tensor, types_i32: torch.Tensor,
-                  shift_vec: Optional[torch.Tensor], gEi_scale: Optional[torch.Tensor], want_virial: bool = False):
+                  shift_vec: Optional[torch.Tensor], gEi_scale: Optional[torch.Tensor], want_virial: bool = False, pair=None):
     """Whole path with no torch autograd: positions -> (Ei [N], forces [n_atoms,3], X, Ez, virial).
     ``gEi_scale`` = d E_total / d Ei (per-type scales), None = ones.  ``virial`` (only if asked for) is
     sum_z r_z (x) dE/dr_z [3,3] = dE/d(strain) before symmetrisation, from the per-edge gradients the
-    force scatter consumes anyway."""
+    force scatter consumes anyway.  ``pair`` = (ZBL module, r_max table) adds the pair potential's gradient to the
+    per-edge gradients and returns its per-atom energies as a sixth value (added AFTER the per-type scale/shift,
+    allegro_models.py:270-288)."""
     dt, acc = core.dtype, core.acc
     E = csr.num_edges
     if E == 0:
@@ -392,7 +394,8 @@ def energy_forces(core: "AllegroCore", up: UpstreamPack, csr: EdgeCSR, pos: torc
         dev = pos.device
         return (torch.zeros(csr.num_atoms, dtype=acc, device=dev), torch.zeros(pos.shape[0], 3, dtype=acc, device=dev),
                 torch.empty(0, core.S * (core.L + 1), dtype=dt, device=dev), torch.empty(0, 1, dtype=dt, device=dev),
-                torch.zeros(3, 3, dtype=acc, device=dev) if want_virial else None)
+                torch.zeros(3, 3, dtype=acc, device=dev) if want_virial else None,
+                torch.zeros(csr.num_atoms, dtype=acc, device=dev) if pair is not None else None)
     _lib.set_tag("fwd.radial")
     vec = _lib.edge_vec(pos, csr.ctr, csr.nbr, shift_vec, acc)
     if up.fold:
@@ -407,9 +410,13 @@ def energy_forces(core: "AllegroCore", up: UpstreamPack, csr: EdgeCSR, pos: torc
     gvec, gx_emb = core.backward(sv, gEi)
     _lib.set_tag("bwd.radial")
     up.backward(up_saved, gx_emb if up.fold else [gx_emb], vec, csr, types_i32, gvec)
+    Ei_pair = None
+    if pair is not None:
+        Ez_pair = pair[0].edge_energy_and_grad(vec, csr, types_i32, pair[1], gvec)
+        Ei_pair = _lib.edge_sum(Ez_pair, csr.row_ptr, 1.0)
     virial = (vec.T @ gvec.to(vec.dtype)) if want_virial else None
     F = _lib.force_scatter(gvec, csr, pos.shape[0])
-    return Ei, F, X, Ez, virial
+    return Ei, F, X, Ez, virial, Ei_pair
 
 
 class _CoreFn(torch.autograd.Function):

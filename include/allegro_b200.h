@@ -231,6 +231,17 @@ int ab2_radial_pq_bwd(int dtype, int64_t E, int S, int num_bessels, double p_cut
                       int num_types, const void* bessel_w, const void* PQ, const void* g_out, const void* aux,
                       void* gvec, void* stream);
 
+/* ZBL pair term (reference call site allegro/model/allegro_models.py:270-288; the module is nequip's
+ * nequip.nn.pair_potential.ZBL = LAMMPS pair_style zbl, constants of pair_zbl_const.h):
+ *   Ez[z] = qq * Z_i Z_j / r * phi((Z_i^0.23 + Z_j^0.23) r / 0.46850) * u(r / rmax_table[t_c][t_n]),
+ *   phi(x) = 0.18175 e^{-3.19980x} + 0.50986 e^{-0.94229x} + 0.28022 e^{-0.40290x} + 0.02817 e^{-0.20162x},
+ * u = polynomial cutoff of order p_cut, qq = qqr2e / 2 (each pair is two directed edges); and
+ *   gvec[z] += dEz/dvec[z].
+ * vec, Z [num_types], rmax_table [num_types^2], Ez [E], gvec [E][3] in the accumulate dtype; Ez or gvec may be null. */
+int ab2_zbl(int acc_dtype, int64_t E, int num_types, double p_cut, double qq, const void* vec, const int32_t* ctr,
+            const int32_t* nbr, const int32_t* types, const void* Z, const void* rmax_table, void* Ez, void* gvec,
+            void* stream);
+
 /* ---- ghost-atom halo exchange over NVLink peer memory ------------------- */
 
 /* One mailbox per rank (cudaMalloc'ed here so that it can be exported through CUDA IPC), mapped by its peers.

@@ -59,6 +59,7 @@ class AllegroEnergyOracle(torch.nn.Module):
         weight_individual_irreps: bool = True,
         per_type_energy_scales=None,
         per_type_energy_shifts=None,
+        pair_potential: Optional[Dict] = None,
         forward_normalize: bool = True,
         seed: int = 0,
         model_dtype: str = "float32",
@@ -129,6 +130,13 @@ class AllegroEnergyOracle(torch.nn.Module):
             self.per_type_energy_scale_shift = R.PerTypeScaleShift(
                 len(type_names), per_type_energy_scales, per_type_energy_shifts
             )
+            # pair potential after the scale/shift (allegro_models.py:270-288); only ZBL exists in nequip
+            self.pair_potential = None
+            if pair_potential is not None:
+                pp = dict(pair_potential)
+                target = pp.pop("_target_", "nequip.nn.pair_potential.ZBL").rsplit(".", 1)[-1]
+                assert target == "ZBL", target
+                self.pair_potential = R.ZBL(type_names=type_names, **pp)
 
     def forward(self, data: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
         data = self.edge_norm(data)
@@ -139,6 +147,8 @@ class AllegroEnergyOracle(torch.nn.Module):
         data[R.EDGE_ENERGY_KEY] = self.edge_readout(data[R.EDGE_FEATURES_KEY])
         data = self.edge_eng_sum(data)
         data = self.per_type_energy_scale_shift(data)
+        if self.pair_potential is not None:
+            data = self.pair_potential(data)
         data[R.TOTAL_ENERGY_KEY] = data[R.PER_ATOM_ENERGY_KEY].sum(dim=0, keepdim=True)
         return data
 

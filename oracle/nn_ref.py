@@ -534,3 +534,44 @@ class PerTypeScaleShift(torch.nn.Module):
         e = data[PER_ATOM_ENERGY_KEY]
         data[PER_ATOM_ENERGY_KEY] = e * self.scales[t].to(e.dtype).unsqueeze(-1) + self.shifts[t].to(e.dtype).unsqueeze(-1)
         return data
+
+
+# --------------------------------------------------------------------------------------
+# ZBL pair potential (nequip.nn.pair_potential.ZBL; call site allegro/model/allegro_models.py:270-288)
+# --------------------------------------------------------------------------------------
+# PARITY UNPINNED: nequip is not vendored under /root/reference and not installable here, so there is no reference code or
+# golden vector for this module.  Restated from its published algorithm: LAMMPS pair_style zbl with the constants of
+# pair_zbl_const.h, multiplied by the polynomial cutoff the Allegro builder puts in front (PolynomialCutoff(6) on the
+# normalised edge length) and by 1/2 (every pair appears as two directed edges).  Checked in tests against an independent
+# closed-form evaluation on dimers and by finite differences.
+_CHEMICAL_SYMBOLS = (
+    "X H He Li Be B C N O F Ne Na Mg Al Si P S Cl Ar K Ca Sc Ti V Cr Mn Fe Co Ni Cu Zn Ga Ge As Se Br Kr Rb Sr Y Zr Nb Mo Tc Ru Rh Pd Ag Cd "
+    "In Sn Sb Te I Xe Cs Ba La Ce Pr Nd Pm Sm Eu Gd Tb Dy Ho Er Tm Yb Lu Hf Ta W Re Os Ir Pt Au Hg Tl Pb Bi Po At Rn Fr Ra Ac Th Pa U Np Pu "
+    "Am Cm Bk Cf Es Fm Md No Lr"
+).split()
+ATOMIC_NUMBERS = {sym: z for z, sym in enumerate(_CHEMICAL_SYMBOLS)}
+_QQR2E = {"metal": 14.399645, "real": 332.06371}  # LAMMPS force->qqr2e
+
+
+class ZBL(torch.nn.Module):
+    def __init__(self, type_names: Sequence[str], chemical_species: Optional[Sequence[str]] = None, units: str = "metal", cutoff_p: float = 6.0):
+        super().__init__()
+        species = list(chemical_species) if chemical_species is not None else list(type_names)
+        assert len(species) == len(type_names)
+        self.register_buffer("atomic_numbers", torch.tensor([float(ATOMIC_NUMBERS[s]) for s in species], dtype=torch.float64))
+        self.qqr2exesquare = _QQR2E[units] * 0.5
+        self.cutoff_p = float(cutoff_p)
+
+    def forward(self, data):
+        r = data[EDGE_LENGTH_KEY]
+        ei = data[EDGE_INDEX_KEY]
+        et = data[EDGE_TYPE_KEY]
+        Z = self.atomic_numbers.to(r.dtype)
+        zi, zj = Z[et[0]], Z[et[1]]
+        x = (zi.pow(0.23) + zj.pow(0.23)) * r / 0.46850
+        psi = 0.02817 * torch.exp(-0.20162 * x) + 0.28022 * torch.exp(-0.40290 * x) + 0.50986 * torch.exp(-0.94229 * x) + 0.18175 * torch.exp(-3.19980 * x)
+        eng = self.qqr2exesquare * (zi * zj / r) * psi * polynomial_cutoff(data[NORM_LENGTH_KEY].squeeze(-1).to(r.dtype), self.cutoff_p)
+        n = data[PER_ATOM_ENERGY_KEY].shape[0]
+        atomic = torch.zeros(n, dtype=eng.dtype, device=eng.device).index_add_(0, ei[0], eng)
+        data[PER_ATOM_ENERGY_KEY] = data[PER_ATOM_ENERGY_KEY] + atomic.unsqueeze(-1).to(data[PER_ATOM_ENERGY_KEY].dtype)
+        return data

@@ -204,5 +204,24 @@ def radial_pq_bwd(dtype, S, p_cut, vec, ctr, nbr, types, rmax_table, bessel_w, P
     gvec += gv
 
 
-ALL = ("radial_pq_fwd", "radial_pq_bwd", "sh_fwd", "sh_bwd", "linear", "linear_pack", "env_sum", "env_bwd", "tp_fwd", "tp_bwd", "edge_sum", "edge_sum_bwd",
+def _zbl(p_cut, qq, vec, ctr, nbr, types, Z, rmax_table):
+    tc, tn = types.long()[ctr.long()], types.long()[nbr.long()]
+    r = vec.norm(dim=-1)
+    zi, zj = Z[tc], Z[tn]
+    xs = (zi**0.23 + zj**0.23) * r / 0.46850
+    phi = 0.18175 * torch.exp(-3.19980 * xs) + 0.50986 * torch.exp(-0.94229 * xs) + 0.28022 * torch.exp(-0.40290 * xs) + 0.02817 * torch.exp(-0.20162 * xs)
+    return qq * zi * zj / r * phi * R.polynomial_cutoff(r / rmax_table[tc, tn], float(p_cut))
+
+
+def zbl(p_cut, qq, vec, ctr, nbr, types, Z, rmax_table, gvec):
+    v = vec.detach().clone().requires_grad_(True)
+    with torch.enable_grad():
+        e = _zbl(p_cut, qq, v, ctr, nbr, types, Z, rmax_table)
+        if gvec is not None:
+            (gv,) = torch.autograd.grad(e.sum(), v)
+            gvec += gv
+    return e.detach()
+
+
+ALL = ("zbl", "radial_pq_fwd", "radial_pq_bwd", "sh_fwd", "sh_bwd", "linear", "linear_pack", "env_sum", "env_bwd", "tp_fwd", "tp_bwd", "edge_sum", "edge_sum_bwd",
        "force_scatter", "edge_vec", "radial_fwd", "radial_bwd")
