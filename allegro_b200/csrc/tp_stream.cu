@@ -34,6 +34,7 @@
 int g_ab2_opt_tp_stream = 1;    // 1: use these kernels where instantiated, 0: round-1 kernels
 int g_ab2_opt_tp_stream_te = 0;  // edges per stage (0 = default 8), 8 or 16
 int g_ab2_opt_tp_stream_cps = 0; // cap on CTAs per SM (0 = occupancy limit)
+int g_ab2_opt_tp_stream_gytile = 1;  // layer-0 backward: gY reduced through a shared-memory tile instead of per-edge shuffles
 
 namespace {
 
@@ -57,6 +58,7 @@ struct StreamParams {
     void* gw0;
     void* gY;
     void* ggamma;
+    int gy_tile;        // 1: shuffle-free gY reduction through a shared-memory tile (option tp_stream_gytile)
     int skip_if_baked;  // the three-warp kernel (tp_stream3.cu) was launched for this call: stand down where it works
 };
 
@@ -112,8 +114,10 @@ __host__ __device__ inline Plan make_plan(int U, int D, int NCH, int TE, int NS)
     return p;
 }
 
-template <typename TAct, typename TAcc, int D_IN, int D_OUT, bool IMPLICIT, int MODE, int NCH, int TE, int NS, int UT>
-__global__ void __launch_bounds__((2 * NCH + 1) * 32) tp_stream_kernel(const StreamParams p) {
+// GYT: shuffle-free gY reduction through a shared-memory tile (layer-0 backward, 9 x 9 -> 9, one channel chunk); that build
+// only works on the baked table structure and stands down otherwise (the plain build is launched behind it, skip_if_baked)
+template <typename TAct, typename TAcc, int D_IN, int D_OUT, bool IMPLICIT, int MODE, int NCH, int TE, int NS, int UT, bool GYT>
+__device__ __forceinline__ void tp_stream_body(const StreamParams& p) {
     extern __shared__ __align__(128) uint8_t smem[];
     constexpr int NCW = 2 * NCH;  // consumer warps
     constexpr int T = D_IN * D_OUT;
@@ -197,6 +201,7 @@ __global__ void __launch_bounds__((2 * NCH + 1) * 32) tp_stream_kernel(const Str
         }
         baked = __syncthreads_and(ok) != 0 ;
         if (p.skip_if_baked && baked) return;
+        if (GYT && !baked) return;
     }
 
     // ---- this CTA's contiguous range of centres / edges ----
@@ -441,6 +446,10 @@ __global__ void __launch_bounds__((2 * NCH + 1) * 32) tp_stream_kernel(const Str
         [[maybe_unused]] TAct* __restrict__ gvin_p = (MODE == 1 && !IMPLICIT) ? (TAct*)p.gVin + ((int64_t)e_lo * D_IN + I0) * U + u : nullptr;
         [[maybe_unused]] TAct* __restrict__ gw0_p = (MODE == 1 && IMPLICIT) ? (TAct*)p.gw0 + (int64_t)e_lo * (N_IR * U) + u : nullptr;
         [[maybe_unused]] float* __restrict__ gy_p = (MODE == 1 && IMPLICIT) ? (float*)p.gY + (int64_t)e_lo * D_IN + I0 : nullptr;
+        // shuffle-free gY reduction (layer-0 backward, 9 x 9 -> 9, one channel chunk, baked table): a warp-private tile in the
+        // part of the scratch buffer the baked per-centre code does not use ([0, 2 x 9 x 32) floats are its ggamma exchange)
+        static_assert(!GYT || (MODE == 1 && IMPLICIT && NCH == 1 && TE == 8 && D_IN == 9 && D_OUT == 9), "gY tile build");
+        [[maybe_unused]] float* const gy_tile = GYT ? scr + 2 * 9 * 32 + (ROLE ? TE * RowSplit<D_IN, IMPLICIT>::IS * 16 : 0) : nullptr;
         const int e_lo32 = (int)e_lo, e_hi32 = (int)e_hi;
         int row_end32 = e_lo32;
         for (int za = e_lo32; za < e_hi32; za += TE) {
@@ -569,11 +578,22 @@ __global__ void __launch_bounds__((2 * NCH + 1) * 32) tp_stream_kernel(const Str
                         }
 #pragma unroll
                         for (int i = 0; i < NI; ++i) part[i] = wl[sh_l_of(I0 + i)] * gin[i];
-                        const float tot = MultiSum<NI>::run(part, lane);
-                        const int idx = MultiSum<NI>::idx_of(lane);
-                        if (MultiSum<NI>::is_writer(lane) && idx < NI) {
-                            if (NCH == 1) atomicAdd(gy_p + idx, tot);  // RED (fire and forget), single writer per address
-                            else s_gyx[(q * TE + t) * D_IN + I0 + idx] = tot;
+                        if constexpr (GYT) {
+                            // one xor-16 step (independent shuffles, no chain), lanes 0-15 park the half sums in the tile;
+                            // the stage's rows are summed once per stage below.  The multi-level shuffle reduction per edge
+                            // was ~45 % of an edge's latency (profiles/r2j_bwd_l0_analysis.md).
+#pragma unroll
+                            for (int i = 0; i < NI; ++i) {
+                                const float pr = part[i] + __shfl_xor_sync(0xffffffffu, part[i], 16);
+                                if (lane < 16) gy_tile[(t * NI + i) * 16 + lane] = pr;
+                            }
+                        } else {
+                            const float tot = MultiSum<NI>::run(part, lane);
+                            const int idx = MultiSum<NI>::idx_of(lane);
+                            if (MultiSum<NI>::is_writer(lane) && idx < NI) {
+                                if (NCH == 1) atomicAdd(gy_p + idx, tot);  // RED (fire and forget), single writer per address
+                                else s_gyx[(q * TE + t) * D_IN + I0 + idx] = tot;
+                            }
                         }
                         gw0_p += N_IR * U;
                         gy_p += D_IN;
@@ -586,6 +606,21 @@ __global__ void __launch_bounds__((2 * NCH + 1) * 32) tp_stream_kernel(const Str
                     }
                 }
                 }  // run
+            }
+            if constexpr (GYT) {
+                {
+                    // row j = (edge j / NI, local row j % NI) of the tile: 16 floats, chunk order rotated per lane so that the
+                    // eight lanes of a 128-bit phase hit eight different bank groups; RED, one writer per gY element
+                    __syncwarp();
+                    for (int j = lane; j < n * NI; j += 32) {
+                        const float4* __restrict__ row = reinterpret_cast<const float4*>(gy_tile + j * 16);
+                        const int sw = (j >> 1) & 3;
+                        const float4 a = row[sw], b4 = row[1 ^ sw], c4 = row[2 ^ sw], d4 = row[3 ^ sw];
+                        const float tot = (((a.x + a.y) + (a.z + a.w)) + ((b4.x + b4.y) + (b4.z + b4.w))) + (((c4.x + c4.y) + (c4.z + c4.w)) + ((d4.x + d4.y) + (d4.z + d4.w)));
+                        const int tt = j / NI;
+                        atomicAdd((float*)p.gY + (int64_t)(za + tt) * D_IN + I0 + (j - tt * NI), tot);
+                    }
+                }
             }
             if constexpr (NCH > 1 && MODE == 1 && IMPLICIT) {
                 // channel chunks of one role meet here: fixed summation order over chunks (deterministic)
@@ -615,9 +650,23 @@ __global__ void __launch_bounds__((2 * NCH + 1) * 32) tp_stream_kernel(const Str
     else run(std::integral_constant<int, 1>{});
 }
 
+// Two entry points over the same body: the plain build keeps the compiler's own register choice (168 for the layer-0
+// backward -> 4 CTAs/SM); the gY-tile build needs a few registers more and is capped so that it keeps 4 CTAs/SM
+// (a second __launch_bounds__ argument on the plain build changes its allocation: 229 registers with minBlocks = 1).
 template <typename TAct, typename TAcc, int D_IN, int D_OUT, bool IMPLICIT, int MODE, int NCH, int TE, int NS, int UT>
+__global__ void __launch_bounds__((2 * NCH + 1) * 32) tp_stream_kernel(const StreamParams p) {
+    tp_stream_body<TAct, TAcc, D_IN, D_OUT, IMPLICIT, MODE, NCH, TE, NS, UT, false>(p);
+}
+template <typename TAct, typename TAcc, int D_IN, int D_OUT, bool IMPLICIT, int MODE, int NCH, int TE, int NS, int UT>
+__global__ void __launch_bounds__((2 * NCH + 1) * 32, 4) tp_stream_gyt_kernel(const StreamParams p) {
+    tp_stream_body<TAct, TAcc, D_IN, D_OUT, IMPLICIT, MODE, NCH, TE, NS, UT, true>(p);
+}
+
+template <typename TAct, typename TAcc, int D_IN, int D_OUT, bool IMPLICIT, int MODE, int NCH, int TE, int NS, int UT, bool GYT = false>
 int launch_cfg(const StreamParams& p, cudaStream_t st) {
-    auto kern = tp_stream_kernel<TAct, TAcc, D_IN, D_OUT, IMPLICIT, MODE, NCH, TE, NS, UT>;
+    void (*kern)(const StreamParams);
+    if constexpr (GYT) kern = tp_stream_gyt_kernel<TAct, TAcc, D_IN, D_OUT, IMPLICIT, MODE, NCH, TE, NS, UT>;
+    else kern = tp_stream_kernel<TAct, TAcc, D_IN, D_OUT, IMPLICIT, MODE, NCH, TE, NS, UT>;
     const Plan pl = make_plan<TAct, TAcc, D_IN, D_OUT, IMPLICIT, MODE>(p.U, p.D, NCH, TE, NS);
     static int num_sms = 0, max_smem = 0;
     if (num_sms == 0) {
@@ -647,7 +696,19 @@ int launch_cfg(const StreamParams& p, cudaStream_t st) {
 
 template <typename TAct, typename TAcc, int D_IN, int D_OUT, bool IMPLICIT, int MODE>
 int launch_shape(const StreamParams& p, cudaStream_t st) {
-    if (p.U == 32) return launch_cfg<TAct, TAcc, D_IN, D_OUT, IMPLICIT, MODE, 1, 8, 3, 32>(p, st);
+    if (p.U == 32) {
+        if constexpr (std::is_same<TAct, float>::value && D_IN == 9 && D_OUT == 9 && IMPLICIT && MODE == 1) {
+            if (p.gy_tile && !p.skip_if_baked) {
+                // tile build first (works iff the table has the baked structure), then the plain build with the complementary test
+                if (launch_cfg<TAct, TAcc, D_IN, D_OUT, IMPLICIT, MODE, 1, 8, 3, 32, true>(p, st) == 0) {
+                    StreamParams q = p;
+                    q.skip_if_baked = 1;
+                    return launch_cfg<TAct, TAcc, D_IN, D_OUT, IMPLICIT, MODE, 1, 8, 3, 32>(q, st);
+                }
+            }
+        }
+        return launch_cfg<TAct, TAcc, D_IN, D_OUT, IMPLICIT, MODE, 1, 8, 3, 32>(p, st);
+    }
     if (p.U < 32) return launch_cfg<TAct, TAcc, D_IN, D_OUT, IMPLICIT, MODE, 1, 8, 3, 0>(p, st);
     if (p.U == 64) return launch_cfg<TAct, TAcc, D_IN, D_OUT, IMPLICIT, MODE, 2, 8, 2, 64>(p, st);
     if (p.U < 64) return launch_cfg<TAct, TAcc, D_IN, D_OUT, IMPLICIT, MODE, 2, 8, 2, 0>(p, st);
@@ -677,6 +738,7 @@ int ab2_tp_stream(int mode, int dtype, int64_t N, int64_t E, int U, int D, int d
     // works on the baked table structure and checks it on the device; the two-warp kernel below runs with the
     // complementary test, so exactly one of the two launches does the work (no host-side look at device data).
     p.skip_if_baked = 0;
+    p.gy_tile = g_ab2_opt_tp_stream_gytile;
     if (mode == 1 && implicit_v0 && dtype == AB2_F32 && d_in == 9 && D == 9 && U == 32 && nnz == Tab9x9x9::NNZ && E < ((int64_t)1 << 31) &&
         ab2_tp_stream3_bwd(N, E, tab, cgw, row_ptr, ctr, gamma, Y, w0, gVout, gw0, gY, ggamma, st) == 0)
         p.skip_if_baked = 1;

@@ -221,14 +221,17 @@ class FusedAllegroEnergy(torch.nn.Module):
             raise ValueError(f"atom_types has {types.shape[0]} entries for {n} atoms")
         types_i32 = self._cached("types", (types_in,), (n,), lambda: types.to(torch.int32).contiguous())
         ss = self.per_type_energy_scale_shift
-        gscale = ss.scales[types].to(core.acc)
+        # a prepared CSR may hold rows for the first n_c atoms only (the owned centres of a slab, halo.py; neighbours index
+        # all n atoms): energies exist for those centres, forces for every atom
+        types_c = types[: csr.num_atoms]
+        gscale = ss.scales[types_c].to(core.acc)
         want_virial = bool(stress) and D.CELL_KEY in data
         pair = None
         if self.pair_potential is not None:
             pair = (self.pair_potential, self.edge_norm.rmax_table.to(device=pos.device, dtype=core.acc))
         Ei, F, X, Ez, virial, Ei_pair = energy_forces(core, self._upstream, csr, pos.detach().contiguous(), types_i32, shift_vec,
                                                       gscale, want_virial, pair=pair)
-        e_atom = ss(Ei.unsqueeze(-1), types)
+        e_atom = ss(Ei.unsqueeze(-1), types_c)
         if Ei_pair is not None:
             e_atom = e_atom + Ei_pair.unsqueeze(-1).to(e_atom.dtype)
         out = dict(data)

@@ -91,7 +91,17 @@ def test_halo_matches_single_gpu(mode, reps):
     procs = [ctx.Process(target=_worker, args=(r, world, port, q, mode, reps)) for r in range(world)]
     for p in procs:
         p.start()
-    res = [q.get(timeout=300) for _ in range(world)]
+    import queue
+    import time
+
+    res, deadline = [], time.time() + 300
+    while len(res) < world:  # fail fast when a worker dies instead of waiting out the queue timeout
+        try:
+            res.append(q.get(timeout=2))
+        except queue.Empty:
+            dead = [p.exitcode for p in procs if p.exitcode not in (None, 0)]
+            assert not dead, f"worker exited with {dead}"
+            assert time.time() < deadline, "timed out waiting for the workers"
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0

@@ -242,22 +242,25 @@ def _tp_case(lmax, layer, L, U, coupling, dtype, seed=0):
     return c, b
 
 
-@pytest.fixture(params=[(1, 1, 8, 1), (1, 1, 8, 0), (1, 1, 16, 0), (1, 0, 8, 0), (2, 0, 8, 0), (0, 0, 8, 0)],
-                ids=["stream3", "stream", "stream_te16", "fast", "regM", "generic"])
+@pytest.fixture(params=[(1, 1, 8, 0, 1), (1, 1, 8, 0, 0), (1, 1, 8, 1, 1), (1, 1, 16, 0, 1), (1, 0, 8, 0, 1), (2, 0, 8, 0, 1), (0, 0, 8, 0, 1)],
+                ids=["stream", "stream_shfl", "stream3", "stream_te16", "fast", "regM", "generic"])
 def tp_fast(request):
-    """Kernel families of the tensor product: TMA-staged streaming kernels (round 2, default where instantiated; "stream3" =
-    with the three-consumer-warp layer-0 backward, an option that measured equal to the two-warp kernel), the round-1 shared-memory-M / split kernels, the
-    register-M kernels, the shape-generic kernels."""
-    fast, stream, te, s3 = request.param
+    """Kernel families of the tensor product: TMA-staged streaming kernels (round 2, default where instantiated; "stream_shfl" =
+    layer-0 backward with the per-edge shuffle reduction of gY instead of the shared-memory tile, "stream3" = the
+    three-consumer-warp layer-0 backward, an option that measured equal to the two-warp kernel), the round-1
+    shared-memory-M / split kernels, the register-M kernels, the shape-generic kernels."""
+    fast, stream, te, s3, gyt = request.param
     _lib.set_option("tp_fast", fast)
     _lib.set_option("tp_stream", stream)
     _lib.set_option("tp_stream_te", te)
     _lib.set_option("tp_stream3", s3)
+    _lib.set_option("tp_stream_gytile", gyt)
     yield request.param
     _lib.set_option("tp_fast", 1)
     _lib.set_option("tp_stream", 1)
     _lib.set_option("tp_stream_te", 0)
     _lib.set_option("tp_stream3", 0)
+    _lib.set_option("tp_stream_gytile", 1)
 
 
 @pytest.mark.parametrize("case", [(1, 0, 1), (2, 0, 2), (2, 1, 2), (3, 0, 3), (3, 1, 3), (3, 2, 3), (1, 0, 2), (1, 1, 3)])
@@ -334,8 +337,8 @@ def test_tp_fwd_bwd_implicit_v0(lmax, dtype, U, tp_fast):
     assert _rel(ggam.transpose(1, 2), ggam_ref) < (tol if dtype != torch.bfloat16 else 1e-5)
 
 
-@pytest.mark.parametrize("s3", [1, 0], ids=["stream3", "stream"])
-def test_tp_stream_ragged_rows(s3):
+@pytest.mark.parametrize("s3,gyt", [(1, 1), (0, 1), (0, 0)], ids=["stream3", "stream", "stream_shfl"])
+def test_tp_stream_ragged_rows(s3, gyt):
     """Layer-0 streaming kernels on a ragged CSR with more centres than CTAs: empty centres (also leading / trailing), rows of
     1-3 edges (several centres begin inside one 8-edge stage), rows far longer than a stage.  Reference: the shape-generic
     kernels on the same device data (themselves held to the oracle above); ggamma of empty centres must come back zero and
@@ -375,11 +378,13 @@ def test_tp_stream_ragged_rows(s3):
         _lib.set_option("tp_fast", 1)
         _lib.set_option("tp_stream", 1)
         _lib.set_option("tp_stream3", s3)
+        _lib.set_option("tp_stream_gytile", gyt)
         got, again = run(), run()
     finally:
         _lib.set_option("tp_fast", 1)
         _lib.set_option("tp_stream", 1)
         _lib.set_option("tp_stream3", 0)
+        _lib.set_option("tp_stream_gytile", 1)
     for name, a, r in zip(("Vout", "gw0", "gY", "ggamma"), got, ref):
         assert bool(torch.isfinite(a).all()), name
         assert _rel(a, r) < 2e-5, name

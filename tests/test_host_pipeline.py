@@ -137,3 +137,39 @@ def test_host_pipeline_with_folded_embed_linears(name, plain, spec_kernels, monk
     for key in ("atomic_energy", "forces", "edge_energy", "edge_features"):
         if key in rec:
             assert _rel(out[key], rec[key]) < tol, (key, _rel(out[key], rec[key]))
+
+
+def test_prepared_csr_with_owned_centres_only(spec_kernels):
+    """A prepared CSR may hold rows for the first n_c atoms only (the owned centres of a slab; neighbours index owned + ghost
+    atoms, halo.py / _compile.py:41-61): energies come back for those centres, forces for every atom.  Reference: the oracle on
+    the same frame restricted to the edges centred on the first n_c atoms (strict locality makes that the same function).
+    Regression test for the multi-GPU path (r2k: the scale/shift was applied with the types of ALL atoms)."""
+    from allegro_b200 import data as D
+    from allegro_b200 import systems
+    from allegro_b200.model import AllegroModel
+    from oracle.model_ref import AllegroOracle
+
+    d = systems.make_system("c3", 3)
+    n = d[D.POSITIONS_KEY].shape[0]
+    nc = 17
+    ei, sh = d[D.EDGE_INDEX_KEY], d[D.EDGE_CELL_SHIFT_KEY]
+    keep = ei[0] < nc
+    kw = systems.model_kwargs("c3", ei.shape[1] / n, "float64")
+    kw.update(num_scalar_features=16, num_tensor_features=8, radial_chemical_embed_dim=16, scalar_embed_mlp_hidden_layers_width=16,
+              allegro_mlp_hidden_layers_width=16, readout_mlp_hidden_layers_width=16, per_type_energy_scales=[0.7, 1.3, 0.9],
+              per_type_energy_shifts=[0.1, -0.2, 0.3])
+    oracle = AllegroOracle(**kw)
+    model = AllegroModel(**kw)
+    model.load_state_dict(oracle.state_dict())
+    d_sub = dict(d)
+    d_sub[D.EDGE_INDEX_KEY], d_sub[D.EDGE_CELL_SHIFT_KEY] = ei[:, keep].contiguous(), sh[keep].contiguous()
+    ref = oracle(d_sub)
+    csr = D.build_csr(d_sub[D.EDGE_INDEX_KEY], nc)
+    assert csr.perm is None and csr.num_atoms == nc
+    shift_vec = d_sub[D.EDGE_CELL_SHIFT_KEY].double() @ d[D.CELL_KEY].view(3, 3)
+    data = {D.POSITIONS_KEY: d[D.POSITIONS_KEY], D.ATOM_TYPE_KEY: d[D.ATOM_TYPE_KEY], D.CELL_KEY: d[D.CELL_KEY], D.CSR_KEY: csr,
+            D.EDGE_SHIFT_VEC_KEY: shift_vec}
+    out = model.model._energy_and_forces(data, False)
+    assert out[D.PER_ATOM_ENERGY_KEY].shape[0] == nc and out[D.FORCE_KEY].shape[0] == n
+    assert _rel(out[D.PER_ATOM_ENERGY_KEY], ref[D.PER_ATOM_ENERGY_KEY][:nc]) < 1e-10
+    assert _rel(out[D.FORCE_KEY], ref[D.FORCE_KEY]) < 1e-10
