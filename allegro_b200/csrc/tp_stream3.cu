@@ -20,7 +20,7 @@
 #include "tp_tables_generated.cuh"
 #include "stream_common.cuh"
 
-int g_ab2_opt_tp_stream3 = 0;  // 1: three-warp backward where eligible, 0 (default): two-warp tp_stream kernel -- measured equal (305 us)
+int g_ab2_opt_tp_stream3 = 1;  // 1 (default): three-warp backward where eligible (265 us at the c2 shapes), 0: two-warp tp_stream kernel (285 us)
 // stage knock-outs for tools/time_tp3.py (results are WRONG when non-zero): bit0 consumers skip the edge arithmetic,
 // bit1 no gY reduction / RED, bit2 no RED only, bit3 producer polls without back-off, bit4 no Y copies, bit5 no per-centre work,
 // bit6 compute only (no bulk copies); bit8 selects the unroll-1 build (results stay right)

@@ -314,7 +314,9 @@ class DistributedAllegro:
         g_owned = g[: dec.n_owned].clone()
         if self.p2p is not None:
             self.p2p.reverse(g, g_owned)
-            e_tot = self.p2p.energy(e_local)
+            # the mailbox protocol sums into a persistent buffer: hand out a copy, so that a caller holding the result of one
+            # step does not see it change under the next one (under graph capture the copy is the graph's static output)
+            e_tot = self.p2p.energy(e_local).clone()
             return e_tot, -g_owned, e_atoms.detach()
         dec.exchange_reverse(g[dec.n_owned :].contiguous(), g_owned)
         e_tot = e_local.detach().double().clone().reshape(1)

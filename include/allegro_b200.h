@@ -44,7 +44,7 @@ int ab2_device_ok(void);
  *   "tp_variant" 1: 3 CTAs/SM (default), 0: 2 CTAs/SM for the shared-memory tensor-product kernel
  *   "tp_stream"  1 TMA-staged streaming tensor product where instantiated (default), 0 round-1 kernels;
  *                "tp_stream_te" edges per stage (0 = 8), "tp_stream_cps" cap on CTAs per SM (0 = occupancy limit),
- *                "tp_stream3" 1: three consumer warps per centre stream for the layer-0 backward, 0: two (default),
+ *                "tp_stream3" 1: three consumer warps per centre stream for the layer-0 backward (default), 0: two,
  *                "tp_stream_gytile" 1: gY of the layer-0 backward reduced through a shared-memory tile (default), 0: shuffles
  *   "env_stream" 1 streaming adjoint of the environment sum (default), 0 round-1 kernel
  *   "linear_tma" 1 TMA-producer variant of the tensor-core linear where eligible (default), 0 cp.async producers

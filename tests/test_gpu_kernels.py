@@ -246,8 +246,8 @@ def _tp_case(lmax, layer, L, U, coupling, dtype, seed=0):
                 ids=["stream", "stream_shfl", "stream3", "stream_te16", "fast", "regM", "generic"])
 def tp_fast(request):
     """Kernel families of the tensor product: TMA-staged streaming kernels (round 2, default where instantiated; "stream_shfl" =
-    layer-0 backward with the per-edge shuffle reduction of gY instead of the shared-memory tile, "stream3" = the
-    three-consumer-warp layer-0 backward, an option that measured equal to the two-warp kernel), the round-1
+    layer-0 backward with the per-edge shuffle reduction of gY instead of the shared-memory tile, "stream3" = with the
+    three-consumer-warp layer-0 backward, the default where eligible), the round-1
     shared-memory-M / split kernels, the register-M kernels, the shape-generic kernels."""
     fast, stream, te, s3, gyt = request.param
     _lib.set_option("tp_fast", fast)
@@ -259,7 +259,7 @@ def tp_fast(request):
     _lib.set_option("tp_fast", 1)
     _lib.set_option("tp_stream", 1)
     _lib.set_option("tp_stream_te", 0)
-    _lib.set_option("tp_stream3", 0)
+    _lib.set_option("tp_stream3", 1)
     _lib.set_option("tp_stream_gytile", 1)
 
 
@@ -383,7 +383,7 @@ def test_tp_stream_ragged_rows(s3, gyt):
     finally:
         _lib.set_option("tp_fast", 1)
         _lib.set_option("tp_stream", 1)
-        _lib.set_option("tp_stream3", 0)
+        _lib.set_option("tp_stream3", 1)
         _lib.set_option("tp_stream_gytile", 1)
     for name, a, r in zip(("Vout", "gw0", "gY", "ggamma"), got, ref):
         assert bool(torch.isfinite(a).all()), name
