@@ -351,71 +351,10 @@ __global__ void __launch_bounds__(128) radial_pq_bwd_kernel(int64_t E, int S, TA
     gvec[z * 3 + 2] += f * vz;
 }
 
-// fp32, S % 32 == 0: the thread-per-edge walk above reads its row with 16-byte loads that hit 32 different rows per warp
-// instruction (32 sectors for 512 useful bytes; ncu: lg_throttle + long scoreboard, 2.2 TB/s).  Here a warp owns 32 edges and
-// moves g / aux in 32-column chunks with row-contiguous 128-byte segments (8 lanes per row), applies silu' in that layout,
-// parks the chunk in a padded shared-memory tile and only then walks rows -- one thread per edge as before, PQ read as float4.
-template <int NB>
-__global__ void __launch_bounds__(128) radial_pq_bwd_tile_kernel(int64_t E, int S, float p, const float* __restrict__ vec,
-                                                                 const int32_t* __restrict__ ctr, const int32_t* __restrict__ nbr,
-                                                                 const int32_t* __restrict__ types, const float* __restrict__ rmax_table,
-                                                                 int num_types, const float* __restrict__ bw, const float* __restrict__ PQ,
-                                                                 const float* __restrict__ g_out, const float* __restrict__ aux,
-                                                                 float* __restrict__ gvec) {
-    constexpr int LD = 36;  // floats per tile row (32 + 4): 16-byte aligned rows, conflict-free 128-bit phases
-    __shared__ __align__(16) float tile[4][32 * LD];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int64_t z0 = ((int64_t)blockIdx.x * 4 + warp) * 32;
-    if (z0 >= E) return;
-    const int64_t z = z0 + lane;
-    const bool live = z < E;
-    const int64_t zc = live ? z : E - 1;
-    const float vx = vec[zc * 3], vy = vec[zc * 3 + 1], vz = vec[zc * 3 + 2];
-    const float r = sqrtf(vx * vx + vy * vy + vz * vz);
-    const int pair = types[ctr[zc]] * num_types + types[nbr[zc]];
-    const float rmax = rmax_table[pair];
-    float B[NB], dB[NB];
-    bessel_basis<float, true>(r / rmax, p, NB, bw, B, dB);
-    const float* __restrict__ m = PQ + (int64_t)pair * NB * S;
-    float* __restrict__ tw = tile[warp];
-    const int lr = lane >> 3, lc = (lane & 7) * 4;  // this lane's (row mod 4, column) inside a 4-row x 32-column slab
-    float gx = 0.f;
-    for (int c0 = 0; c0 < S; c0 += 32) {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const int row = 4 * i + lr;
-            int64_t zr = z0 + row;
-            if (zr >= E) zr = E - 1;
-            float4 gv = *reinterpret_cast<const float4*>(g_out + zr * S + c0 + lc);
-            if (aux) {
-                const float4 av = *reinterpret_cast<const float4*>(aux + zr * S + c0 + lc);
-                gv.x *= dsilu_f(av.x); gv.y *= dsilu_f(av.y); gv.z *= dsilu_f(av.z); gv.w *= dsilu_f(av.w);
-            }
-            *reinterpret_cast<float4*>(tw + row * LD + lc) = gv;
-        }
-        __syncwarp();
-#pragma unroll
-        for (int q = 0; q < 8; ++q) {
-            const float4 gc = *reinterpret_cast<const float4*>(tw + lane * LD + 4 * q);
-            float4 sN = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-            for (int n = 0; n < NB; ++n) {
-                const float4 pq = __ldg(reinterpret_cast<const float4*>(m + n * S + c0 + 4 * q));
-                sN.x = fmaf(dB[n], pq.x, sN.x); sN.y = fmaf(dB[n], pq.y, sN.y); sN.z = fmaf(dB[n], pq.z, sN.z); sN.w = fmaf(dB[n], pq.w, sN.w);
-            }
-            gx = fmaf(gc.x, sN.x, gx); gx = fmaf(gc.y, sN.y, gx); gx = fmaf(gc.z, sN.z, gx); gx = fmaf(gc.w, sN.w, gx);
-        }
-        __syncwarp();
-    }
-    if (live) {
-        const float f = gx / (rmax * r);  // dx/dr_vec = r_vec / (|r| r_max)
-        gvec[z * 3] += f * vx;
-        gvec[z * 3 + 1] += f * vy;
-        gvec[z * 3 + 2] += f * vz;
-    }
-}
-
-int g_ab2_opt_radial_tile = 1;  // 1: row-coalesced tile variant of radial_pq_bwd where eligible (fp32, S % 32 == 0)
+// (A warp-cooperative variant -- 32-column chunks moved with row-contiguous 128-byte segments through a padded shared-memory
+// tile, then the same row walk -- was tried in round 2 and lost: 174 us instead of 115 us at the c2 shapes.  The tile's
+// load -> silu' -> store -> sync -> load chain with 16 resident warps hides less latency than 32 independent 16-byte loads per
+// thread with 32+ resident warps, uncoalesced as they are; profiles/README.md, r2q.)
 
 #define AB2_RADIAL_PQ_DISPATCH(KERNEL, ...)                                                                       \
     do {                                                                                                          \
@@ -445,14 +384,6 @@ extern "C" int ab2_radial_pq_bwd(int dtype, int64_t E, int S, int num_bessels, d
     AB2_CHECK_ARG(vec && ctr && nbr && types && rmax_table && bessel_w && PQ && g_out && gvec, "null pointer");
     AB2_CHECK_ARG(num_bessels == 8 && S > 0 && S <= 128, "radial_pq: 8 Bessel functions, at most 128 output columns");
     cudaStream_t st = (cudaStream_t)stream;
-    auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
-    if (g_ab2_opt_radial_tile && dtype == AB2_F32 && S % 32 == 0 && al16(g_out) && al16(PQ) && (!aux || al16(aux))) {
-        radial_pq_bwd_tile_kernel<8><<<ab2_blocks(E, 128), 128, 0, st>>>(E, S, (float)p_cut, (const float*)vec, ctr, nbr, types, (const float*)rmax_table,
-                                                                         num_types, (const float*)bessel_w, (const float*)PQ, (const float*)g_out,
-                                                                         (const float*)aux, (float*)gvec);
-        AB2_CUDA_LAUNCH_CHECK();
-        return 0;
-    }
     AB2_DISPATCH_DTYPE(dtype, radial_pq_bwd_kernel<TAct, TAcc, 8, 1><<<ab2_blocks(E, 128), 128, 0, st>>>(
                                   E, S, (TAcc)p_cut, (const TAcc*)vec, ctr, nbr, types, (const TAcc*)rmax_table, num_types, (const TAcc*)bessel_w,
                                   (const TAcc*)PQ, (const TAct*)g_out, (const TAct*)aux, (TAcc*)gvec));

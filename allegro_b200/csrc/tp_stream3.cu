@@ -23,7 +23,7 @@
 int g_ab2_opt_tp_stream3 = 1;  // 1 (default): three-warp backward where eligible (265 us at the c2 shapes), 0: two-warp tp_stream kernel (285 us)
 // stage knock-outs for tools/time_tp3.py (results are WRONG when non-zero): bit0 consumers skip the edge arithmetic,
 // bit1 no gY reduction / RED, bit2 no RED only, bit3 producer polls without back-off, bit4 no Y copies, bit5 no per-centre work,
-// bit6 compute only (no bulk copies); bit8 selects the unroll-1 build (results stay right)
+// bit6 compute only (no bulk copies); bit8 selects the unroll-2 build instead of the default unroll-1 (results stay right)
 int g_ab2_opt_tp_stream3_debug = 0;
 
 namespace {
@@ -433,7 +433,7 @@ int ab2_tp_stream3_bwd(int64_t N, int64_t E, const int32_t* tab, const void* cgw
     p.N = N; p.E = E; p.tab = tab; p.cgw = (const float*)cgw; p.row_ptr = row_ptr; p.ctr = ctr; p.gamma = (const float*)gamma;
     p.Y = (const float*)Y; p.w0 = (const float*)w0; p.gVout = (const float*)gVout; p.gw0 = (float*)gw0; p.gY = (float*)gY; p.ggamma = (float*)ggamma;
     p.debug = g_ab2_opt_tp_stream3_debug & 0xff;
-    const int unr1 = (g_ab2_opt_tp_stream3_debug >> 8) & 1;  // bit 8: unroll 1 instead of 2
+    const int unr1 = ((g_ab2_opt_tp_stream3_debug >> 8) & 1) ^ 1;  // default: the unroll-1 build (259 us vs 265 us); bit 8 selects unroll 2
     kerns[(p.debug ? 2 : 0) + unr1]<<<(unsigned)grid, 128, SMEM3, st>>>(p);
     return 0;
 }

@@ -245,11 +245,12 @@ def run_ours(args, rank: int, world: int):
     traffic = traffic_src = None
     try:
         tj = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
-        pat = {"tp_bwd@bwd.L0": "tp_stream_kernel<float, float, 9, 9, 1, 1,", "tp_fwd@fwd.L0": "tp_stream_kernel<float, float, 9, 9, 1, 0,",
+        pat = {"tp_bwd@bwd.L0": "tp_bwd3_kernel", "tp_fwd@fwd.L0": "tp_stream_kernel<float, float, 9, 9, 1, 0,",
+               "tp_bwd@bwd.L1": "tp_smem_kernel<float, float, 9, 1,",
                "env_bwd@bwd.L0": "env_bwd_stream_kernel<float, 2,", "env_bwd@bwd.L1": "env_bwd_stream_kernel<float, 2,"}.get(dom_tp)
         if cfg == "c2" and dtype == "float32" and pat:
             for kname, rec in tj["per_kernel"].items():
-                if kname.startswith(pat):
+                if pat in kname:
                     traffic = rec["dram_bytes_per_launch"]
                     traffic_src = f"profiles/{tj['tag']}_ncu_full_summary.md ({tj['source']}: ncu --set full, dram__bytes_read+write per launch)"
     except Exception:

@@ -46,7 +46,6 @@ int ab2_device_ok(void);
  *                "tp_stream_te" edges per stage (0 = 8), "tp_stream_cps" cap on CTAs per SM (0 = occupancy limit),
  *                "tp_stream3" 1: three consumer warps per centre stream for the layer-0 backward (default), 0: two,
  *                "tp_stream_gytile" 1: gY of the layer-0 backward reduced through a shared-memory tile (default), 0: shuffles
- *   "radial_tile" 1 row-coalesced tile variant of ab2_radial_pq_bwd where eligible (default), 0 thread-per-edge walk
  *   "env_stream" 1 streaming adjoint of the environment sum (default), 0 round-1 kernel
  *   "linear_tma" 1 TMA-producer variant of the tensor-core linear where eligible (default), 0 cp.async producers
  *   "env_split"  warps per (centre, channel chunk) in ab2_env_sum / ab2_env_bwd: 0 auto (default), 1, 2, 4

@@ -35,7 +35,7 @@ def timeit(fn, reps=20):
 
 
 bwd = lambda: _lib.tp_bwd(dt, lmax, N, E, U, 9, 9, tab, cgw, csr.row_ptr, csr.ctr, gam, None, Y, w0, go, None, gw0, gY, gg)
-names = {0: "full (unroll 2)", 256: "full, unroll 1", 1: "no edge arithmetic", 2: "no gY reduction", 32: "no per-centre work", 64: "compute only (no bulk copies)",
+names = {0: "full (unroll 1, default)", 256: "full, unroll 2", 1: "no edge arithmetic", 2: "no gY reduction", 32: "no per-centre work", 64: "compute only (no bulk copies)",
          1 | 32: "pipeline only", 2 | 32: "no gY, no centre work", 16: "no Y copies"}
 for cps in (0, 3, 2, 1):
     _lib.set_option("tp_stream_cps", cps)
