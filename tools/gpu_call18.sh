@@ -12,3 +12,4 @@ try:
 except Exception as e:
     print("ERR", e); print(open("gpurun_out/r2r_bench_c2.err").read()[-1500:])
 PY
+timeout 300 python tools/time_triton_ref.py > gpurun_out/r2r_time_triton_ref.txt 2>&1; tail -11 gpurun_out/r2r_time_triton_ref.txt

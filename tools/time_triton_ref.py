@@ -88,3 +88,33 @@ print(f"reference operator fwd+bwd (autograd)     : {t_ref_fb:7.0f} us")
 print(f"ours tp_fwd (explicit Vin)                : {t_f:7.0f} us   ({t_ref_k / t_f:.1f}x vs kernel, {t_ref_op / t_f:.1f}x vs operator)")
 print(f"ours tp_fwd + tp_bwd                      : {t_f + t_b:7.0f} us   ({t_ref_fb / (t_f + t_b):.1f}x vs operator fwd+bwd)")
 print(f"parity ours vs reference Triton: out {err_f:.1e}  d/dx1 {err_b:.1e}  d/dgamma {err_g:.1e}")
+
+# ---- ours, OPERATOR level (row a14: the plug-in replacement of the reference's kernel back-ends, strided [z][u][i]
+#      layout, unsorted idxs, generic SIMT kernels + the recursively differentiable autograd function) ----
+oursd = ours.to(dev)
+oursd.weights.requires_grad_(False)
+with torch.no_grad():
+    t_op_f = timeit(lambda: oursd(x1, x2, ctr, N))
+x1o, x2o = x1.clone().requires_grad_(True), x2.clone().requires_grad_(True)
+
+
+def ours_fb():
+    x1o.grad = x2o.grad = None
+    oursd(x1o, x2o, ctr, N).backward(gout)
+
+
+t_op_fb = timeit(ours_fb)
+oursd.weights.requires_grad_(True)
+
+
+def ours_fb_w():
+    x1o.grad = x2o.grad = oursd.weights.grad = None
+    oursd(x1o, x2o, ctr, N).backward(gout)
+
+
+t_op_fbw = timeit(ours_fb_w, reps=3)
+err_op = float((oursd(x1, x2, ctr, N) - out_ref).abs().max() / out_ref.abs().max())
+print(f"ours OPERATOR fwd (no grad)                : {t_op_f:7.0f} us   ({t_ref_op / t_op_f:.1f}x vs reference operator fwd)")
+print(f"ours OPERATOR fwd+bwd (x1, x2)             : {t_op_fb:7.0f} us   ({t_ref_fb / t_op_fb:.1f}x vs reference operator fwd+bwd)")
+print(f"ours OPERATOR fwd+bwd incl. weight grads   : {t_op_fbw:7.0f} us   (the reference's Triton path has no weight gradient)")
+print(f"parity ours operator vs reference Triton operator: out {err_op:.1e}")
