@@ -22,7 +22,7 @@ int g_ab2_opt_env_split = 0;  // 0: auto (env.cu)
 extern int g_ab2_opt_tp_variant;
 extern int g_ab2_opt_tp_stream, g_ab2_opt_tp_stream_te, g_ab2_opt_tp_stream_cps;
 extern int g_ab2_opt_env_stream;
-extern int g_ab2_opt_tp_stream3, g_ab2_opt_tp_stream3_debug, g_ab2_opt_tp_stream_gytile;
+extern int g_ab2_opt_tp_stream3, g_ab2_opt_tp_stream3_debug, g_ab2_opt_tp_stream_gytile, g_ab2_opt_tp_stream_last;
 
 extern "C" const char* ab2_last_error(void) { return g_err; }
 extern "C" int ab2_set_option(const char* key, int value) {
@@ -35,6 +35,7 @@ extern "C" int ab2_set_option(const char* key, int value) {
     if (!strcmp(key, "tp_variant")) { g_ab2_opt_tp_variant = value; return 0; }
     if (!strcmp(key, "env_stream")) { g_ab2_opt_env_stream = value; return 0; }
     if (!strcmp(key, "tp_stream")) { g_ab2_opt_tp_stream = value; return 0; }
+    if (!strcmp(key, "tp_stream_last")) { g_ab2_opt_tp_stream_last = value; return 0; }
     if (!strcmp(key, "tp_stream_gytile")) { g_ab2_opt_tp_stream_gytile = value; return 0; }
     if (!strcmp(key, "tp_stream3")) { g_ab2_opt_tp_stream3 = value; return 0; }
     if (!strcmp(key, "tp_stream3_debug")) { g_ab2_opt_tp_stream3_debug = value; return 0; }

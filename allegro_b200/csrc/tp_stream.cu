@@ -34,6 +34,7 @@
 int g_ab2_opt_tp_stream = 1;    // 1: use these kernels where instantiated, 0: round-1 kernels
 int g_ab2_opt_tp_stream_te = 0;  // edges per stage (0 = default 8), 8 or 16
 int g_ab2_opt_tp_stream_cps = 0; // cap on CTAs per SM (0 = occupancy limit)
+int g_ab2_opt_tp_stream_last = 1;    // 9 -> 1 (last layer) backward through the streaming kernel instead of tp_smem + split
 int g_ab2_opt_tp_stream_gytile = 1;  // layer-0 backward: gY reduced through a shared-memory tile instead of per-edge shuffles
 
 namespace {
@@ -706,6 +707,8 @@ int launch_cfg(const StreamParams& p, cudaStream_t st) {
         cudaGetLastError();
         return -1;
     }
+    // the 9 -> 1 backward is purely memory-bound: 3 CTAs/SM stream 5.9 TB/s, the 5 the occupancy allows 5.3 TB/s (r2s)
+    if (D_OUT == 1 && MODE == 1 && cps > 3 && g_ab2_opt_tp_stream_cps == 0) cps = 3;
     if (g_ab2_opt_tp_stream_cps > 0 && cps > g_ab2_opt_tp_stream_cps) cps = g_ab2_opt_tp_stream_cps;
     int64_t grid = (int64_t)num_sms * cps;
     if (grid > p.N) grid = p.N;
@@ -743,7 +746,9 @@ int ab2_tp_stream(int mode, int dtype, int64_t N, int64_t E, int U, int D, int d
                   const void* w0, int64_t w0_ld, void* Vout, const void* gVout, void* gVin, void* gw0, int64_t gw0_ld, void* gY,
                   void* ggamma, cudaStream_t st) {
     if (!g_ab2_opt_tp_stream || !ctr || dtype == AB2_F64 || nnz > MAX_NNZ || nnz <= 0 || E <= 0 || N <= 0) return -1;
-    if (d_in != d_out || !(d_in == 4 || d_in == 9) || (implicit_v0 && D != d_in)) return -1;
+    // last layer of an l_max = 2 model: 9 -> 1 backward (explicit input features), generic per-centre table walk (9 entries)
+    const bool last9 = g_ab2_opt_tp_stream_last && mode == 1 && !implicit_v0 && d_in == 9 && d_out == 1 && D == 9;
+    if (!last9 && (d_in != d_out || !(d_in == 4 || d_in == 9) || (implicit_v0 && D != d_in))) return -1;
     const int esz = dtype == AB2_F32 ? 4 : 2;
     // bulk copies move whole rows: 16-byte multiples, 16-byte aligned bases, dense rows
     if ((U * esz) % 16 != 0 || (U * 4) % 16 != 0) return -1;
@@ -762,6 +767,12 @@ int ab2_tp_stream(int mode, int dtype, int64_t N, int64_t E, int U, int D, int d
     if (mode == 1 && implicit_v0 && dtype == AB2_F32 && d_in == 9 && D == 9 && U == 32 && nnz == Tab9x9x9::NNZ && E < ((int64_t)1 << 31) &&
         ab2_tp_stream3_bwd(N, E, tab, cgw, row_ptr, ctr, gamma, Y, w0, gVout, gw0, gY, ggamma, st) == 0)
         p.skip_if_baked = 1;
+    if (last9) {
+        p.skip_if_baked = 0;
+        p.gy_tile = 0;
+        if (dtype == AB2_F32) return launch_shape<float, float, 9, 1, false, 1>(p, st);
+        return launch_shape<bf16, float, 9, 1, false, 1>(p, st);
+    }
 #define AB2_STREAM_CASE(TA, DI)                                                                                        \
     if (d_in == DI) {                                                                                                   \
         if (mode == 0) return implicit_v0 ? launch_shape<TA, float, DI, DI, true, 0>(p, st) : launch_shape<TA, float, DI, DI, false, 0>(p, st); \

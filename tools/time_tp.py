@@ -36,8 +36,11 @@ def timeit(fn, reps=10):
 VARIANTS = [  # (label, options)
     ("stream te8", dict(tp_fast=1, tp_stream=1, tp_stream_te=8)),
     ("stream shfl gY", dict(tp_fast=1, tp_stream=1, tp_stream_te=8, tp_stream_gytile=0)),
+    ("stream, L1 bwd smem", dict(tp_fast=1, tp_stream=1, tp_stream_te=8, tp_stream3=1, tp_stream_last=0)),
     ("stream3", dict(tp_fast=1, tp_stream=1, tp_stream_te=8, tp_stream3=1)),
     ("stream3 cps3", dict(tp_fast=1, tp_stream=1, tp_stream_te=8, tp_stream3=1, tp_stream_cps=3)),
+    ("stream3 cps2", dict(tp_fast=1, tp_stream=1, tp_stream_te=8, tp_stream3=1, tp_stream_cps=2)),
+    ("stream3 cps4", dict(tp_fast=1, tp_stream=1, tp_stream_te=8, tp_stream3=1, tp_stream_cps=4)),
     ("stream te8 cps3", dict(tp_fast=1, tp_stream=1, tp_stream_te=8, tp_stream_cps=3)),
     ("stream te8 cps2", dict(tp_fast=1, tp_stream=1, tp_stream_te=8, tp_stream_cps=2)),
     ("stream te16", dict(tp_fast=1, tp_stream=1, tp_stream_te=16)),
@@ -46,8 +49,8 @@ VARIANTS = [  # (label, options)
 ]
 ref = {}
 for label, opts in VARIANTS:
-    for k in ("tp_stream_cps", "tp_stream_te", "tp_variant", "tp_stream3", "tp_stream_gytile"):
-        _lib.set_option(k, 1 if k in ("tp_variant", "tp_stream_gytile") else 0)
+    for k in ("tp_stream_cps", "tp_stream_te", "tp_variant", "tp_stream3", "tp_stream_gytile", "tp_stream_last"):
+        _lib.set_option(k, 1 if k in ("tp_variant", "tp_stream_gytile", "tp_stream_last") else 0)
     for k, v in opts.items():
         _lib.set_option(k, v)
     line = f"{label:16s}:"
