@@ -9,12 +9,13 @@
 // Layouts: Y[E][D] (TAcc), w[z][n_ir][U] (TAct, leading dim w_ld), gamma[N][D][U] (TAcc).
 #include "common.cuh"
 
-extern int g_ab2_opt_env_split;  // warps per (centre, channel chunk) in env_sum / env_bwd: 1, 2 or 4
+extern int g_ab2_opt_env_split;
+int g_ab2_opt_env_unroll = 2;  // edge-loop unroll of env_sum with 4 warps per centre: 2 or 4  // warps per (centre, channel chunk) in env_sum / env_bwd: 1, 2 or 4
 
 // SPLIT warps of one CTA share a (centre, 32-channel chunk): each streams every SPLIT-th edge of the
 // row, the partial sums meet in shared memory.  One warp per centre (SPLIT = 1) leaves only ~2 waves
 // of long serial loops (42 edges/centre on c2) and is latency-bound at ~50 % of the HBM rate.
-template <typename TAct, typename TAcc, int LMAX, int SPLIT>
+template <typename TAct, typename TAcc, int LMAX, int SPLIT, int UNR = 2>
 __global__ void __launch_bounds__(128) env_sum_kernel(int64_t N, int U, const int32_t* __restrict__ row_ptr,
                                                       const TAcc* __restrict__ Y, const TAct* __restrict__ w, int64_t w_ld,
                                                       TAcc sf, TAcc* __restrict__ gamma) {
@@ -32,7 +33,7 @@ __global__ void __launch_bounds__(128) env_sum_kernel(int64_t N, int U, const in
     TAcc acc[D];
 #pragma unroll
     for (int j = 0; j < D; ++j) acc[j] = TAcc(0);
-#pragma unroll 2
+#pragma unroll UNR
     for (int z = beg + sub; z < end; z += SPLIT) {
         const TAcc* __restrict__ Yz = Y + (int64_t)z * D;
         const TAct* __restrict__ wz = w + (int64_t)z * w_ld;
@@ -159,7 +160,10 @@ extern "C" int ab2_env_sum(int dtype, int lmax, int64_t N, int U, const int32_t*
     // auto (0): 4 warps per centre when one warp would cover all channels (U <= 32: +85 % on c2),
     // one otherwise (U = 64 measured slower when split)
     const int split = g_ab2_opt_env_split ? g_ab2_opt_env_split : (U <= 32 ? 4 : 1);
-    if (split >= 4) {
+    if (split >= 4 && g_ab2_opt_env_unroll == 4) {
+        AB2_DISPATCH_DTYPE(dtype, AB2_DISPATCH_LMAX(lmax, env_sum_kernel<TAct, TAcc, LMAX, 4, 4><<<ab2_blocks(groups * 4 * 32, 128), 128, 0, st>>>(
+                                                              N, U, row_ptr, (const TAcc*)Y, (const TAct*)w, w_ld, (TAcc)sf, (TAcc*)gamma)));
+    } else if (split >= 4) {
         AB2_DISPATCH_DTYPE(dtype, AB2_DISPATCH_LMAX(lmax, env_sum_kernel<TAct, TAcc, LMAX, 4><<<ab2_blocks(groups * 4 * 32, 128), 128, 0, st>>>(
                                                               N, U, row_ptr, (const TAcc*)Y, (const TAct*)w, w_ld, (TAcc)sf, (TAcc*)gamma)));
     } else if (split >= 2) {

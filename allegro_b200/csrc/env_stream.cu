@@ -13,6 +13,7 @@
 #include "stream_common.cuh"
 
 int g_ab2_opt_env_stream = 1;
+int g_ab2_opt_env_stream_cps = 0;  // cap on CTAs per SM of the streaming env adjoint (0 = min(occupancy, 8))
 
 namespace {
 
@@ -189,6 +190,8 @@ int launch(const EnvParams& p, cudaStream_t st) {
         return -1;
     }
     if (cps > 8) cps = 8;
+    extern int g_ab2_opt_env_stream_cps;
+    if (g_ab2_opt_env_stream_cps > 0 && cps > g_ab2_opt_env_stream_cps) cps = g_ab2_opt_env_stream_cps;
     int64_t grid = (int64_t)num_sms * cps;
     const int64_t max_grid = (p.E + TE - 1) / TE;
     if (grid > max_grid) grid = max_grid;

@@ -21,7 +21,7 @@ int g_ab2_opt_tc_debug = 0;
 int g_ab2_opt_env_split = 0;  // 0: auto (env.cu)
 extern int g_ab2_opt_tp_variant;
 extern int g_ab2_opt_tp_stream, g_ab2_opt_tp_stream_te, g_ab2_opt_tp_stream_cps;
-extern int g_ab2_opt_env_stream;
+extern int g_ab2_opt_env_stream, g_ab2_opt_env_stream_cps, g_ab2_opt_env_unroll;
 extern int g_ab2_opt_tp_stream3, g_ab2_opt_tp_stream3_debug, g_ab2_opt_tp_stream_gytile, g_ab2_opt_tp_stream_last;
 
 extern "C" const char* ab2_last_error(void) { return g_err; }
@@ -33,6 +33,8 @@ extern "C" int ab2_set_option(const char* key, int value) {
     if (!strcmp(key, "tc_debug")) { g_ab2_opt_tc_debug = value; return 0; }
     if (!strcmp(key, "env_split")) { g_ab2_opt_env_split = value; return 0; }
     if (!strcmp(key, "tp_variant")) { g_ab2_opt_tp_variant = value; return 0; }
+    if (!strcmp(key, "env_stream_cps")) { g_ab2_opt_env_stream_cps = value; return 0; }
+    if (!strcmp(key, "env_unroll")) { g_ab2_opt_env_unroll = value; return 0; }
     if (!strcmp(key, "env_stream")) { g_ab2_opt_env_stream = value; return 0; }
     if (!strcmp(key, "tp_stream")) { g_ab2_opt_tp_stream = value; return 0; }
     if (!strcmp(key, "tp_stream_last")) { g_ab2_opt_tp_stream_last = value; return 0; }

@@ -709,6 +709,8 @@ int launch_cfg(const StreamParams& p, cudaStream_t st) {
     }
     // the 9 -> 1 backward is purely memory-bound: 3 CTAs/SM stream 5.9 TB/s, the 5 the occupancy allows 5.3 TB/s (r2s)
     if (D_OUT == 1 && MODE == 1 && cps > 3 && g_ab2_opt_tp_stream_cps == 0) cps = 3;
+    // explicit 9 x 9 -> 9 forward (middle layers of deeper models): 187 us at 3 CTAs/SM, 213 us at the occupancy limit (r2t)
+    if (D_IN == 9 && D_OUT == 9 && MODE == 0 && !IMPLICIT && NCH == 1 && cps > 3 && g_ab2_opt_tp_stream_cps == 0) cps = 3;
     if (g_ab2_opt_tp_stream_cps > 0 && cps > g_ab2_opt_tp_stream_cps) cps = g_ab2_opt_tp_stream_cps;
     int64_t grid = (int64_t)num_sms * cps;
     if (grid > p.N) grid = p.N;
