@@ -190,7 +190,6 @@ int launch(const EnvParams& p, cudaStream_t st) {
         return -1;
     }
     if (cps > 8) cps = 8;
-    extern int g_ab2_opt_env_stream_cps;
     if (g_ab2_opt_env_stream_cps > 0 && cps > g_ab2_opt_env_stream_cps) cps = g_ab2_opt_env_stream_cps;
     int64_t grid = (int64_t)num_sms * cps;
     const int64_t max_grid = (p.E + TE - 1) / TE;
