@@ -82,11 +82,16 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if failed:
         raise RuntimeError("nvcc failed; see output above")
     # export only the extern "C" ab2_* symbols
-    cmd = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB] + objs
+    # link into a temporary name and move it into place: a failed link must not take the previous library with it
+    tmp = LIB + ".tmp"
+    cmd = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", tmp] + objs
     r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if r.returncode != 0:
         sys.stderr.write(r.stdout)
+        if os.path.exists(tmp):
+            os.remove(tmp)
         raise RuntimeError("link failed")
+    os.replace(tmp, LIB)
     with open(STAMP, "w") as f:
         f.write(_digest())
     return LIB
