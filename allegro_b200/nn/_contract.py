@@ -24,10 +24,35 @@ from ..o3 import CouplingTable, Irreps, build_coupling_table
 class _Meta:
     """Non-differentiable context of one contraction: shapes, table, scatter indices."""
 
-    __slots__ = ("U", "d1", "d2", "dout", "tab", "idxs", "n_atoms")
+    __slots__ = ("U", "d1", "d2", "dout", "tab", "idxs", "n_atoms", "csr", "lmax")
 
-    def __init__(self, U, d1, d2, dout, tab, idxs, n_atoms):
+    def __init__(self, U, d1, d2, dout, tab, idxs, n_atoms, csr=None, lmax=-1):
         self.U, self.d1, self.d2, self.dout, self.tab, self.idxs, self.n_atoms = U, d1, d2, dout, tab, idxs, n_atoms
+        # centre-sorted indices + a full spherical-harmonic second operand: the products can run on the fused pipeline's
+        # tensor-product kernels (component-major layout, CSR rows) instead of the generic operator kernels
+        self.csr, self.lmax = csr, lmax
+
+
+def _fast_product(which: str, m: _Meta, c, a, b, g):
+    """One of the products "g" / "a" / "b" of _Tri on the fused pipeline's kernels (ab2_tp_fwd / ab2_tp_bwd): the operands
+    are transposed to the component-major layout, the kernels see the CSR of the sorted indices.  The backward kernel
+    produces both input gradients at once; the one that is not asked for is computed against a zero operand and dropped."""
+    csr, dt = m.csr, (a if a is not None else g).dtype
+    E, N, U = csr.num_edges, m.n_atoms, m.U
+    dev = (a if a is not None else g).device
+    c = c.contiguous()
+    if which == "g":
+        Vi, gi = _lib.transpose_ui(a, True), _lib.transpose_ui(b, True)
+        out = torch.empty(E, m.dout, U, dtype=dt, device=dev)
+        _lib.tp_fwd(dt, m.lmax, N, E, U, m.d1, m.dout, m.tab, c, csr.row_ptr, csr.ctr, gi, Vi, None, None, out)
+        return _lib.transpose_ui(out, False)
+    go = _lib.transpose_ui(g, True)
+    Vi = _lib.transpose_ui(a, True) if a is not None else torch.zeros(E, m.d1, U, dtype=dt, device=dev)
+    gi = _lib.transpose_ui(b, True) if b is not None else torch.zeros(N, m.d2, U, dtype=dt, device=dev)
+    gVin = torch.empty(E, m.d1, U, dtype=dt, device=dev)
+    ggam = torch.empty(N, m.d2, U, dtype=dt, device=dev)
+    _lib.tp_bwd(dt, m.lmax, N, E, U, m.d1, m.dout, m.tab, c, csr.row_ptr, csr.ctr, gi, Vi, None, None, go, gVin, None, None, ggam)
+    return _lib.transpose_ui(gVin if which == "a" else ggam, False)
 
 
 _SLOTS = ("c", "a", "b", "g")
@@ -50,6 +75,8 @@ class _Tri(torch.autograd.Function):
         ctx.which, ctx.meta = which, meta
         ctx.save_for_backward(*[t for t in (c, a, b, g) if t is not None])
         m = meta
+        if m.csr is not None and which != "c":
+            return _fast_product(which, m, c, a, b, g)
         if which == "g":
             out = torch.empty(a.shape[0], m.U, m.dout, dtype=a.dtype, device=a.device)
             return _lib.op_contract(0, m.U, m.d1, m.d2, m.dout, m.tab, c.contiguous(), a, b, m.idxs, out)
@@ -220,6 +247,9 @@ class Contracter(torch.nn.Module):
         if x1.dtype not in (torch.float32, torch.float64):
             raise RuntimeError("operator-level Contracter supports float32/float64")
         n = int(scatter_dim_size.reshape(-1)[0]) if isinstance(scatter_dim_size, torch.Tensor) else int(scatter_dim_size)
+        return self._forward_impl(x1, x2, idxs, n)
+
+    def _forward_impl(self, x1: torch.Tensor, x2: torch.Tensor, idxs: torch.Tensor, n: int) -> torch.Tensor:
         U, d1, d2, dout = self.mul, self.base_dim1, self.base_dim2, self.base_dim_out
         tab, cgw = self.device_tables(x1.dtype, x1.device)
         if torch.is_grad_enabled() and self.weights.requires_grad:
@@ -227,7 +257,27 @@ class Contracter(torch.nn.Module):
         idxs = idxs.contiguous()
         sf = 1.0 if self.scatter_factor is None else float(self.scatter_factor)
         gamma = _ScatterRows.apply(x2.to(x1.dtype).reshape(-1, U, d2), idxs, n, sf)
-        return _Tri.apply("g", _Meta(U, d1, d2, dout, tab, idxs, n), cgw, x1.reshape(-1, U, d1).contiguous(), gamma, None)
+        csr, lmax = self._fast_route(idxs, n, d2)
+        return _Tri.apply("g", _Meta(U, d1, d2, dout, tab, idxs, n, csr, lmax), cgw, x1.reshape(-1, U, d1).contiguous(), gamma, None)
+
+    def _fast_route(self, idxs: torch.Tensor, n: int, d2: int):
+        """(EdgeCSR, l_max) when the call can use the fused pipeline's tensor-product kernels: scatter indices sorted by
+        centre (what a centre-sorted neighbour list gives; checked once per index tensor) and a second operand that is a full
+        spherical-harmonic basis (d2 = (l+1)^2).  ALLEGRO_B200_OP_FAST=0 keeps the generic operator kernels."""
+        import os
+
+        from ..data import build_csr
+
+        lmax = int(round(d2 ** 0.5)) - 1
+        if os.environ.get("ALLEGRO_B200_OP_FAST", "1") != "1" or (lmax + 1) ** 2 != d2 or lmax > 4 or idxs.numel() == 0:
+            return None, -1
+        hit = self._tab_cache.get("route")
+        if hit is None or hit[0] is not idxs or hit[1] != idxs._version or hit[2] != n:
+            is_sorted = bool((idxs[1:] >= idxs[:-1]).all())
+            csr = build_csr(torch.stack([idxs, idxs]), n) if is_sorted else None
+            hit = (idxs, idxs._version, n, csr)
+            self._tab_cache["route"] = hit
+        return hit[3], (lmax if hit[3] is not None else -1)
 
     def extra_repr(self):
         return f"{self.irreps_in1} x {self.irreps_in2} -> {self.irreps_out} | {self.mul} channels | {self.num_paths} paths"

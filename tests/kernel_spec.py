@@ -223,5 +223,44 @@ def zbl(p_cut, qq, vec, ctr, nbr, types, Z, rmax_table, gvec):
     return e.detach()
 
 
+# ---- operator-level kernels (reference "strided" layout [z][u][i], unsorted scatter indices) -----------------------
+def transpose_ui(x, to_internal):
+    return x.transpose(1, 2).contiguous()
+
+
+def op_scatter_env(x2, idxs, n, sf):
+    return torch.zeros((n,) + tuple(x2.shape[1:]), dtype=x2.dtype).index_add_(0, idxs, sf * x2)
+
+
+def op_gather_rows(src, idxs, sf):
+    return sf * src[idxs]
+
+
+def op_contract(mode, U, d1, d2, dout, tab, cgw, a, b, idxs, out):
+    res = torch.zeros_like(out)
+    for n, (i, j, k) in enumerate(tab.tolist()):
+        c = cgw[n].unsqueeze(0)
+        if mode == 0:
+            res[:, :, k] += c * a[:, :, i] * b[idxs][:, :, j]
+        elif mode == 1:
+            res[:, :, i] += c * a[:, :, k] * b[idxs][:, :, j]
+        else:
+            term = torch.zeros(a.shape[0], U, d2, dtype=a.dtype)
+            term[:, :, j] = c * a[:, :, i] * b[:, :, k]
+            res.index_add_(0, idxs, term)
+    out.copy_(res) if mode != 2 else out.add_(res)
+    return out
+
+
+def op_contract_wgrad(U, d1, d2, dout, tab, x1, gamma, gout, idxs):
+    out = torch.zeros(tab.shape[0], U, dtype=x1.dtype)
+    g = gamma[idxs]
+    for n, (i, j, k) in enumerate(tab.tolist()):
+        out[n] = (x1[:, :, i] * g[:, :, j] * gout[:, :, k]).sum(0)
+    return out
+
+
+OPERATOR = ("transpose_ui", "op_scatter_env", "op_gather_rows", "op_contract", "op_contract_wgrad")
+
 ALL = ("zbl", "radial_pq_fwd", "radial_pq_bwd", "sh_fwd", "sh_bwd", "linear", "linear_pack", "env_sum", "env_bwd", "tp_fwd", "tp_bwd", "edge_sum", "edge_sum_bwd",
        "force_scatter", "edge_vec", "radial_fwd", "radial_bwd")

@@ -457,9 +457,10 @@ def test_contract_kernel_vs_base(irreps_in1, irreps_in2, irreps_out, coupling, m
         torch.set_default_dtype(prev)
 
 
+@pytest.mark.parametrize("sorted_idx", [False, True], ids=["generic", "sorted"])
 @pytest.mark.parametrize("coupling", [True, False])
 @pytest.mark.parametrize("irreps", [("0e + 1o + 2e", "0e + 1o + 2e", "0e + 1o + 2e"), ("2o + 1e + 0e", "0e + 0o + 1e + 1o", "1o + 2e")])
-def test_contracter_weight_grad_and_double_backward(irreps, coupling):
+def test_contracter_weight_grad_and_double_backward(irreps, coupling, sorted_idx):
     """Training support: the reference's ``weights`` are Parameters and its einsum path is differentiable
     to any order through autograd (_contract.py:170-177, 213-251).  The B200 operator builds every derivative from four
     hand-written products; held here to the oracle's autograd: d/d(weights, x1, x2) of a scalar loss, and the second-order
@@ -475,6 +476,8 @@ def test_contracter_weight_grad_and_double_backward(irreps, coupling):
                              scatter_factor=0.37).to(DEV)
         c_k.load_state_dict(c_base.state_dict())
         idx = torch.randint(0, N, (E,))
+        if sorted_idx:  # centre-sorted indices + a full SH second operand take the fused pipeline's kernels (Contracter._fast_route)
+            idx = torch.sort(idx).values
         x1, x2 = torch.randn(E, mul, i1.dim), torch.randn(E, mul, i2.dim)
         go, v1, v2 = torch.randn(E, mul, io.dim), torch.randn(E, mul, i1.dim), torch.randn(E, mul, i2.dim)
 
@@ -490,6 +493,8 @@ def test_contracter_weight_grad_and_double_backward(irreps, coupling):
             return [t.detach().cpu() for t in (out, *first, *second)]
 
         ref, got = losses(c_base, "cpu"), losses(c_k, DEV)
+        route = c_k._tab_cache.get("route")
+        assert (route is not None and route[3] is not None) == (sorted_idx and i2.dim == 9)
         for name, r, g in zip(("out", "dL/dw", "dL/dx1", "dL/dx2", "d2/dw", "d2/dx1", "d2/dx2"), ref, got):
             assert g.shape == r.shape, name
             assert _rel(g, r) < 1e-10, (name, float(_rel(g, r)))
