@@ -22,7 +22,7 @@ int g_ab2_opt_env_split = 0;  // 0: auto (env.cu)
 extern int g_ab2_opt_tp_variant;
 extern int g_ab2_opt_tp_stream, g_ab2_opt_tp_stream_te, g_ab2_opt_tp_stream_cps;
 extern int g_ab2_opt_env_stream, g_ab2_opt_env_stream_cps, g_ab2_opt_env_unroll;
-extern int g_ab2_opt_tp_stream3, g_ab2_opt_tp_stream3_debug, g_ab2_opt_tp_stream_gytile, g_ab2_opt_tp_stream_last;
+extern int g_ab2_opt_tp_stream3, g_ab2_opt_tp_stream3_debug, g_ab2_opt_tp_stream_gytile, g_ab2_opt_tp_stream_last, g_ab2_opt_tp_baked64;
 
 extern "C" const char* ab2_last_error(void) { return g_err; }
 extern "C" int ab2_set_option(const char* key, int value) {
@@ -37,6 +37,7 @@ extern "C" int ab2_set_option(const char* key, int value) {
     if (!strcmp(key, "env_unroll")) { g_ab2_opt_env_unroll = value; return 0; }
     if (!strcmp(key, "env_stream")) { g_ab2_opt_env_stream = value; return 0; }
     if (!strcmp(key, "tp_stream")) { g_ab2_opt_tp_stream = value; return 0; }
+    if (!strcmp(key, "tp_baked64")) { g_ab2_opt_tp_baked64 = value; return 0; }
     if (!strcmp(key, "tp_stream_last")) { g_ab2_opt_tp_stream_last = value; return 0; }
     if (!strcmp(key, "tp_stream_gytile")) { g_ab2_opt_tp_stream_gytile = value; return 0; }
     if (!strcmp(key, "tp_stream3")) { g_ab2_opt_tp_stream3 = value; return 0; }

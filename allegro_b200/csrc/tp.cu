@@ -32,7 +32,8 @@ __global__ void __launch_bounds__(128) tp_fwd_generic_kernel(int64_t E, int U, i
                                                              const int32_t* __restrict__ ctr, const TAcc* __restrict__ gamma,
                                                              const TAct* __restrict__ Vin, int implicit_v0,
                                                              const TAcc* __restrict__ Y, const TAct* __restrict__ w0, int64_t w0_ld,
-                                                             TAct* __restrict__ Vout) {
+                                                             TAct* __restrict__ Vout, const int* __restrict__ skip_flag) {
+    if (skip_flag && *skip_flag) return;  // the baked-structure kernel launched in front of this one did the work
     const int64_t idx = (int64_t)blockIdx.x * 128 + threadIdx.x;
     if (idx >= E * U) return;
     const int64_t z = idx / U;
@@ -57,7 +58,8 @@ __global__ void __launch_bounds__(128) tp_bwd_generic_kernel(int64_t E, int U, i
                                                              const TAcc* __restrict__ Y, const TAct* __restrict__ w0, int64_t w0_ld,
                                                              const TAct* __restrict__ gVout, TAct* __restrict__ gVin,
                                                              TAct* __restrict__ gw0, int64_t gw0_ld, TAcc* __restrict__ gY,
-                                                             TAcc* __restrict__ ggamma) {
+                                                             TAcc* __restrict__ ggamma, const int* __restrict__ skip_flag) {
+    if (skip_flag && *skip_flag) return;
     const int64_t idx = (int64_t)blockIdx.x * 128 + threadIdx.x;
     if (idx >= E * U) return;
     const int64_t z = idx / U;
@@ -115,9 +117,14 @@ extern "C" int ab2_tp_fwd(int dtype, int lmax, int64_t N, int64_t E, int U, int 
             return 0;
         }
     }
+    // fp64, l_max = 3 layer shapes: baked-structure kernel first; it reports through a device flag whether the table was its
+    // own, the shape-generic kernel behind it stands down if so (no host-side look at device data, graph-capturable)
+    int* skip = nullptr;
+    ab2_tp_baked64(0, dtype, E, U, D, d_in, d_out, nnz, tab_ijk, cgw, ctr, gamma, Vin, implicit_v0, Y, w0, w0_ld, Vout, nullptr, nullptr, nullptr,
+                   0, nullptr, nullptr, &skip, st);
     AB2_DISPATCH_DTYPE(dtype, tp_fwd_generic_kernel<TAct, TAcc><<<ab2_blocks(E * U, 128), 128, 0, st>>>(
                                   E, U, D, d_in, d_out, nnz, tab_ijk, (const TAcc*)cgw, ctr, (const TAcc*)gamma, (const TAct*)Vin,
-                                  implicit_v0, (const TAcc*)Y, (const TAct*)w0, w0_ld, (TAct*)Vout));
+                                  implicit_v0, (const TAcc*)Y, (const TAct*)w0, w0_ld, (TAct*)Vout, skip));
     AB2_CUDA_LAUNCH_CHECK();
     return 0;
 }
@@ -149,10 +156,13 @@ extern "C" int ab2_tp_bwd(int dtype, int lmax, int64_t N, int64_t E, int U, int 
     // generic path: ggamma is accumulated with atomics: zero it first
     const size_t acc_size = (dtype == AB2_F64) ? 8 : 4;
     AB2_CUDA_CALL(cudaMemsetAsync(ggamma, 0, (size_t)N * D * U * acc_size, st));
+    int* skip = nullptr;
+    ab2_tp_baked64(1, dtype, E, U, D, d_in, d_out, nnz, tab_ijk, cgw, ctr, gamma, Vin, implicit_v0, Y, w0, w0_ld, nullptr, gVout, gVin, gw0,
+                   gw0_ld, gY, ggamma, &skip, st);
     AB2_DISPATCH_DTYPE(dtype, tp_bwd_generic_kernel<TAct, TAcc><<<ab2_blocks(E * U, 128), 128, 0, st>>>(
                                   E, U, D, d_in, d_out, nnz, tab_ijk, (const TAcc*)cgw, ctr, (const TAcc*)gamma, (const TAct*)Vin,
                                   implicit_v0, (const TAcc*)Y, (const TAct*)w0, w0_ld, (const TAct*)gVout, (TAct*)gVin, (TAct*)gw0,
-                                  gw0_ld, (TAcc*)gY, (TAcc*)ggamma));
+                                  gw0_ld, (TAcc*)gY, (TAcc*)ggamma, skip));
     AB2_CUDA_LAUNCH_CHECK();
     return 0;
 }

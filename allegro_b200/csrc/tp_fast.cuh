@@ -31,3 +31,9 @@ extern int g_ab2_opt_tp_stream, g_ab2_opt_tp_stream_te, g_ab2_opt_tp_stream_cps;
 int ab2_tp_stream3_bwd(int64_t N, int64_t E, const int32_t* tab, const void* cgw, const int32_t* row_ptr, const int32_t* ctr, const void* gamma,
                        const void* Y, const void* w0, const void* gVout, void* gw0, void* gY, void* ggamma, cudaStream_t st);
 extern int g_ab2_opt_tp_stream3;
+// baked-structure fp64 kernels for the l_max = 3 layer shapes (tp_baked64.cu)
+int ab2_tp_baked64(int mode, int dtype, int64_t E, int U, int D, int d_in, int d_out, int nnz, const int32_t* tab, const void* cgw,
+                   const int32_t* ctr, const void* gamma, const void* Vin, int implicit_v0, const void* Y, const void* w0, int64_t w0_ld,
+                   void* Vout, const void* gVout, void* gVin, void* gw0, int64_t gw0_ld, void* gY, void* ggamma, int** flag_out,
+                   cudaStream_t st);
+extern int g_ab2_opt_tp_baked64;

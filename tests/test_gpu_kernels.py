@@ -393,6 +393,58 @@ def test_tp_stream_ragged_rows(s3, gyt):
         assert torch.equal(a, c), name
 
 
+@pytest.mark.parametrize("layer", [0, 1, 2])
+@pytest.mark.parametrize("implicit", [False, True])
+def test_tp_baked64_matches_generic(layer, implicit):
+    """fp64 kernels with the baked l_max = 3 table structure (csrc/tp_baked64.cu; the three layer shapes of BASELINE configs[4])
+    against the shape-generic kernels on the same device data (those are held to the oracle above); U = 64 = two channel chunks,
+    ragged CSR with empty centres."""
+    if implicit and layer == 1:
+        pytest.skip("only a first layer (d_in = d_env) has implicit input features")
+    lmax, L, U, N = 3, 3, 64, 37
+    _, b = _tp_case(lmax, layer, L, U, True, torch.float64)
+    g = torch.Generator().manual_seed(21 + layer)
+    deg = torch.randint(0, 9, (N,), generator=g)
+    deg[3] = 0
+    deg[-1] = 0
+    ctr = torch.repeat_interleave(torch.arange(N), deg)
+    E = int(ctr.numel())
+    csr = D.build_csr(torch.stack([ctr, torch.randint(0, N, (E,), generator=g)]).to(DEV), N)
+    ijk, _, _ = b.sparse_table()
+    tab, cgw = ijk.to(DEV), b.cgw(torch.float64, DEV)
+    d_in, d_out, Dd, n_ir = b.base_dim1, b.base_dim_out, 16, 4
+    assert (d_in, d_out) == [(16, 31), (31, 16), (16, 1)][layer]
+    dd = dict(dtype=torch.float64, generator=g)
+    Y, w0 = torch.randn(E, Dd, **dd).to(DEV), torch.randn(E, n_ir * U, **dd).to(DEV)
+    Vin = None if implicit else torch.randn(E, d_in, U, **dd).to(DEV)
+    gam, gout = torch.randn(N, Dd, U, **dd).to(DEV), torch.randn(E, d_out, U, **dd).to(DEV)
+
+    def run():
+        Vout = torch.full((E, d_out, U), float("nan"), dtype=torch.float64, device=DEV)
+        gVin = None if implicit else torch.full((E, d_in, U), float("nan"), dtype=torch.float64, device=DEV)
+        gw0 = torch.full((E, n_ir * U), float("nan"), dtype=torch.float64, device=DEV) if implicit else None
+        gY = torch.ones(E, Dd, dtype=torch.float64, device=DEV) if implicit else None
+        ggam = torch.full((N, Dd, U), float("nan"), dtype=torch.float64, device=DEV)
+        _lib.tp_fwd(torch.float64, lmax, N, E, U, d_in, d_out, tab, cgw, csr.row_ptr, csr.ctr, gam, Vin, Y if implicit else None, w0 if implicit else None, Vout)
+        _lib.tp_bwd(torch.float64, lmax, N, E, U, d_in, d_out, tab, cgw, csr.row_ptr, csr.ctr, gam, Vin, Y if implicit else None,
+                    w0 if implicit else None, gout, gVin, gw0, gY, ggam)
+        torch.cuda.synchronize()
+        return [t for t in (Vout, gVin, gw0, gY, ggam) if t is not None]
+
+    try:
+        _lib.set_option("tp_baked64", 0)
+        ref = run()
+        _lib.set_option("tp_baked64", 1)
+        got = run()
+    finally:
+        _lib.set_option("tp_baked64", 1)
+    for a, r in zip(got, ref):
+        assert bool(torch.isfinite(a).all())
+        assert _rel(a, r) < 1e-12
+    # the baked kernels sum in a different order: bitwise identical results would mean they stood down
+    assert any(not torch.equal(a, r) for a, r in zip(got, ref))
+
+
 def test_edge_sum_force_scatter_transpose():
     N, E = 50, 900
     csr, ctr = _csr_random(N, E, seed=1)
