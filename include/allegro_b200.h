@@ -47,6 +47,7 @@ int ab2_device_ok(void);
  *                "tp_stream3" 1: three consumer warps per centre stream for the layer-0 backward (default), 0: two,
  *                "tp_stream_last" 1: 9 -> 1 (last layer) backward through the streaming kernel (default), 0: tp_smem + split,
  *                "tp_stream_gytile" 1: gY of the layer-0 backward reduced through a shared-memory tile (default), 0: shuffles
+ *   "tp_baked64" 1 fp64 tensor-product kernels with the baked l_max = 3 table structure (default), 0 shape-generic kernels
  *   "env_stream" 1 streaming adjoint of the environment sum (default), 0 round-1 kernel
  *   "linear_tma" 1 TMA-producer variant of the tensor-core linear where eligible (default), 0 cp.async producers
  *   "env_split"  warps per (centre, channel chunk) in ab2_env_sum / ab2_env_bwd: 0 auto (default), 1, 2, 4
