@@ -273,6 +273,8 @@ class Contracter(torch.nn.Module):
             return None, -1
         hit = self._tab_cache.get("route")
         if hit is None or hit[0] is not idxs or hit[1] != idxs._version or hit[2] != n:
+            if idxs.is_cuda and torch.cuda.is_current_stream_capturing():
+                return None, -1  # the sortedness test synchronises: not while a CUDA graph is being captured
             is_sorted = bool((idxs[1:] >= idxs[:-1]).all())
             csr = build_csr(torch.stack([idxs, idxs]), n) if is_sorted else None
             hit = (idxs, idxs._version, n, csr)
